@@ -1,0 +1,116 @@
+/* liblsted -- C ABI of the B200-native line_sted_tools hot path.
+ *
+ * Every entry point returns 0 on success and a non-zero status otherwise;
+ * lsted_last_error() then returns a thread-local, human-readable message.
+ * All array arguments are HOST pointers to C-contiguous float64 data unless
+ * the name says otherwise; the library owns all device memory.  Handles are
+ * not thread-safe; each owns one CUDA stream.  There is no CPU fallback: a
+ * call without a usable CUDA device fails with LSTED_ERR_CUDA.
+ *
+ * Each function names the reference interface it replaces
+ * (figure_generation/line_sted_tools.py of AndrewGYork/rescan_line_sted).
+ */
+#ifndef LSTED_H
+#define LSTED_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    LSTED_OK = 0,
+    LSTED_ERR_ARG = 1,   /* bad argument / unsupported size */
+    LSTED_ERR_CUDA = 2,  /* CUDA runtime failure (message has the details) */
+    LSTED_ERR_NCCL = 3,
+    LSTED_ERR_STATE = 4  /* call order (e.g. iterate before data) */
+};
+
+/* which-array selectors of lsted_deconv_get / lsted_deconv_set: the public
+ * attributes of the reference Deconvolver (line_sted_tools.py:478-594) */
+enum {
+    LSTED_TRUE_OBJECT = 0,
+    LSTED_NOISELESS = 1,     /* noiseless_measurement[k] */
+    LSTED_NOISY = 2,         /* noisy_measurement[k]     */
+    LSTED_ESTIMATE = 3,
+    LSTED_NORMALIZATION = 4  /* H_t_normalization        */
+};
+
+int lsted_version(void);
+const char* lsted_last_error(void);
+int lsted_device_count(int* count);
+/* Pinned host buffers for end-to-end pipelines (numpy wraps them). */
+int lsted_host_alloc(void** ptr, size_t bytes);
+int lsted_host_free(void* ptr);
+
+/* ---------------- PSF synthesis: generate_psfs, line_sted_tools.py:168-363 -------------
+ * One operating point = (excitation_brightness, depletion_brightness); `taps`
+ * are the 2*radius+1 normalised Gaussian FIR taps (scipy truncate=4 rule,
+ * computed by the host mirror exactly like scipy does).
+ * psf_type: 0 = point, 1 = line.  All outputs are [batch][n][n] float64.   */
+int lsted_psf_illumination(int device, int psf_type, int batch, int n, const double* taps,
+                           int radius, const double* excitation_brightness,
+                           const double* depletion_brightness, double* excitation,
+                           double* depletion, double* excitation_fraction,
+                           double* depletion_fraction, double* sted); /* :180-243 */
+/* Rescan / descan system PSFs from the STED centre rows ([batch][n]) and the
+ * integer rescan ratios ([batch], from the host Gaussian fit :252-256).
+ * `wide` ([n][ratio*n], batch 1 only) may be NULL.                          :258-310 */
+int lsted_psf_rescan(int device, int batch, int n, const double* taps, int radius,
+                     const double* sted_rows, const int* ratios, double* emission,
+                     double* rescan, double* descan, double* wide);
+
+/* ---------------- Deconvolver, line_sted_tools.py:478-594 -------------------------------- */
+typedef struct lsted_deconv lsted_deconv;
+
+typedef struct {
+    int K, ny, nx, Ny, Nx;       /* PSF count / size, image size                     */
+    int Ly, Lx;                  /* FFT lengths (columns, rows)                      */
+    int cols_per_cta, row_pairs_per_cta;
+    int precision;               /* 32 or 64                                         */
+    int iterations_done;
+    int device;
+    size_t row_smem_bytes, col_smem_bytes;
+    size_t device_bytes;         /* HBM held by the handle                           */
+    /* algorithmic bytes: A = sizeof(T)*Ny*Nx                         */
+    double bytes_forward;        /* (2K+1) A                                         */
+    double bytes_normalization;  /* A                                                */
+    double bytes_iteration;      /* (K+4) A                                          */
+} lsted_deconv_info_t;
+
+/* Deconvolver.__init__ (:479-494): psfs = [K][ny][nx].  precision 32 | 64.          */
+int lsted_deconv_create(lsted_deconv** out, int device, const double* psfs, int K, int ny, int nx,
+                        int Ny, int Nx, int precision);
+int lsted_deconv_destroy(lsted_deconv* h);
+int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info);
+/* options: "exact_clip" (0|1: clip every H_t term before the sum, like :587),
+ *          "profile" (0|1: per-kernel CUDA-event timing)                           */
+int lsted_deconv_set_option(lsted_deconv* h, const char* name, double value);
+/* create_data_from_object (:496-512).  rescale != 0 applies total_brightness.
+ * Noise: in-kernel Philox4x32-10 Poisson, stream selected by `seed`.               */
+int lsted_deconv_create_data(lsted_deconv* h, const double* object, double total_brightness,
+                             int rescale, uint64_t seed);
+/* iterate() n times (:520-531); no host transfers.                                 */
+int lsted_deconv_iterate(lsted_deconv* h, int n);
+/* attribute access; k is the PSF index for the per-PSF lists, else 0.
+ * Setting LSTED_NOISY is the injection point for bit-exact noise fields.           */
+int lsted_deconv_get(lsted_deconv* h, int which, int k, double* out);
+int lsted_deconv_set(lsted_deconv* h, int which, int k, const double* in);
+/* H (:567-577): x[Ny][Nx] -> out[K][Ny][Nx];  H_t (:579-594): y[K][Ny][Nx] -> out[Ny][Nx]. */
+int lsted_deconv_H(lsted_deconv* h, const double* x, double* out);
+int lsted_deconv_Ht(lsted_deconv* h, const double* y, double* out, int normalize);
+int lsted_deconv_sync(lsted_deconv* h);
+/* CUDA-event stopwatch on the handle's stream.                                     */
+int lsted_deconv_timer_start(lsted_deconv* h);
+int lsted_deconv_timer_stop(lsted_deconv* h, float* milliseconds);
+/* Per-kernel statistics gathered while option "profile" is on.  Kernel kinds:
+ * 0 row_fwd, 1 row_inv_store, 2 row_inv_sim, 3 row_mid, 4 row_final,
+ * 5 col_otf, 6 col_h, 7 col_ht, 8 elementwise.                                      */
+enum { LSTED_NUM_KERNEL_KINDS = 9 };
+int lsted_deconv_profile(lsted_deconv* h, int reset, double* total_ms, long long* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,234 @@
+"""ctypes binding of liblsted.so (the C ABI declared in include/lsted.h).
+
+There is no CPU fallback: `get()` raises if the CUDA library has not been
+built (`python -c "import __graft_entry__ as g; g.build()"`), and every call
+raises RuntimeError with the library's message when CUDA fails.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBRARY_PATH = os.path.join(_HERE, 'liblsted.so')
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+NUM_KERNEL_KINDS = 9
+KERNEL_KINDS = ('row_fwd', 'row_inv_store', 'row_inv_sim', 'row_mid',
+                'row_final', 'col_otf', 'col_h', 'col_ht', 'elementwise')
+
+TRUE_OBJECT, NOISELESS, NOISY, ESTIMATE, NORMALIZATION = range(5)
+
+
+class DeconvInfo(ctypes.Structure):
+    _fields_ = [('K', ctypes.c_int), ('ny', ctypes.c_int), ('nx', ctypes.c_int),
+                ('Ny', ctypes.c_int), ('Nx', ctypes.c_int),
+                ('Ly', ctypes.c_int), ('Lx', ctypes.c_int),
+                ('cols_per_cta', ctypes.c_int),
+                ('row_pairs_per_cta', ctypes.c_int),
+                ('precision', ctypes.c_int),
+                ('iterations_done', ctypes.c_int),
+                ('device', ctypes.c_int),
+                ('row_smem_bytes', ctypes.c_size_t),
+                ('col_smem_bytes', ctypes.c_size_t),
+                ('device_bytes', ctypes.c_size_t),
+                ('bytes_forward', ctypes.c_double),
+                ('bytes_normalization', ctypes.c_double),
+                ('bytes_iteration', ctypes.c_double)]
+
+
+# name -> (argtypes); all return int status except the two noted below
+_DECONV_SIGNATURES = {
+    'lsted_deconv_create': [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                            c_double_p, ctypes.c_int, ctypes.c_int,
+                            ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                            ctypes.c_int],
+    'lsted_deconv_destroy': [ctypes.c_void_p],
+    'lsted_deconv_info': [ctypes.c_void_p, ctypes.POINTER(DeconvInfo)],
+    'lsted_deconv_set_option': [ctypes.c_void_p, ctypes.c_char_p,
+                                ctypes.c_double],
+    'lsted_deconv_create_data': [ctypes.c_void_p, c_double_p, ctypes.c_double,
+                                 ctypes.c_int, ctypes.c_uint64],
+    'lsted_deconv_iterate': [ctypes.c_void_p, ctypes.c_int],
+    'lsted_deconv_get': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                         c_double_p],
+    'lsted_deconv_set': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                         c_double_p],
+    'lsted_deconv_H': [ctypes.c_void_p, c_double_p, c_double_p],
+    'lsted_deconv_Ht': [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int],
+    'lsted_deconv_sync': [ctypes.c_void_p],
+    'lsted_deconv_timer_start': [ctypes.c_void_p],
+    'lsted_deconv_timer_stop': [ctypes.c_void_p,
+                                ctypes.POINTER(ctypes.c_float)],
+    'lsted_deconv_profile': [ctypes.c_void_p, ctypes.c_int, c_double_p,
+                             ctypes.POINTER(ctypes.c_longlong)],
+}
+
+_CORE_SIGNATURES = {
+    'lsted_version': [],
+    'lsted_device_count': [c_int_p],
+    'lsted_host_alloc': [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t],
+    'lsted_host_free': [ctypes.c_void_p],
+    'lsted_psf_illumination': [ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                               ctypes.c_int, c_double_p, ctypes.c_int,
+                               c_double_p, c_double_p, c_double_p, c_double_p,
+                               c_double_p, c_double_p, c_double_p],
+    'lsted_psf_rescan': [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
+                         ctypes.c_int, c_double_p, c_int_p, c_double_p,
+                         c_double_p, c_double_p, c_double_p],
+}
+
+# every symbol include/lsted.h declares (checked by tests/test_cabi_symbols.py)
+EXPORTED_SYMBOLS = (['lsted_last_error'] + sorted(_CORE_SIGNATURES) +
+                    sorted(_DECONV_SIGNATURES))
+
+
+class Library:
+    """A loaded C-ABI library with typed entry points and error mapping."""
+
+    def __init__(self, path, signatures):
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        self.cdll.lsted_last_error.restype = ctypes.c_char_p
+        self.cdll.lsted_last_error.argtypes = []
+        for name, argtypes in signatures.items():
+            fn = getattr(self.cdll, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
+
+    def last_error(self):
+        msg = self.cdll.lsted_last_error()
+        return msg.decode('utf-8', 'replace') if msg else ''
+
+    def call(self, name, *args):
+        status = getattr(self.cdll, name)(*args)
+        if status != 0:
+            raise RuntimeError('%s failed (status %d): %s'
+                               % (name, status, self.last_error()))
+
+
+def as_f64(a):
+    """C-contiguous float64 view/copy + its ctypes pointer."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(c_double_p)
+
+
+_library = None
+
+
+def get():
+    """The product library.  Raises when liblsted.so is missing."""
+    global _library
+    if _library is None:
+        if not os.path.isfile(LIBRARY_PATH):
+            raise RuntimeError(
+                'liblsted.so is not built (%s). Build it with '
+                '`python -c "import __graft_entry__ as g; g.build()"` or '
+                '`make -C rescan_line_sted_b200/csrc`. There is no CPU '
+                'fallback.' % LIBRARY_PATH)
+        sigs = dict(_CORE_SIGNATURES)
+        sigs.update(_DECONV_SIGNATURES)
+        _library = Library(LIBRARY_PATH, sigs)
+    return _library
+
+
+def bind_deconv_only(path):
+    """Bind a library that exports just the Deconvolver subset (used by the
+    CPU tests on the host replay of the kernel bodies)."""
+    return Library(path, dict(_DECONV_SIGNATURES))
+
+
+class DeconvHandle:
+    """Thin RAII wrapper over lsted_deconv_* for one Deconvolver."""
+
+    def __init__(self, lib, psfs, image_shape, precision=32, device=0):
+        self.lib = lib
+        psfs = np.ascontiguousarray(psfs, dtype=np.float64)
+        assert psfs.ndim == 3
+        self.K, self.ny, self.nx = psfs.shape
+        self.Ny, self.Nx = int(image_shape[0]), int(image_shape[1])
+        self.precision = precision
+        self._h = ctypes.c_void_p()
+        lib.call('lsted_deconv_create', ctypes.byref(self._h), device,
+                 psfs.ctypes.data_as(c_double_p), self.K, self.ny, self.nx,
+                 self.Ny, self.Nx, precision)
+
+    def close(self):
+        if self._h:
+            self.lib.cdll.lsted_deconv_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        info = DeconvInfo()
+        self.lib.call('lsted_deconv_info', self._h, ctypes.byref(info))
+        return info
+
+    def set_option(self, name, value):
+        self.lib.call('lsted_deconv_set_option', self._h, name.encode(),
+                      float(value))
+
+    def create_data(self, obj, total_brightness, seed):
+        obj, p = as_f64(obj)
+        assert obj.size == self.Ny * self.Nx
+        rescale = total_brightness is not None
+        self.lib.call('lsted_deconv_create_data', self._h, p,
+                      float(total_brightness or 0.0), int(rescale),
+                      ctypes.c_uint64(seed))
+
+    def iterate(self, n=1):
+        self.lib.call('lsted_deconv_iterate', self._h, int(n))
+
+    def get(self, which, k=0):
+        out = np.empty((1, self.Ny, self.Nx), dtype=np.float64)
+        self.lib.call('lsted_deconv_get', self._h, which, k,
+                      out.ctypes.data_as(c_double_p))
+        return out
+
+    def get_into(self, which, k, out):
+        self.lib.call('lsted_deconv_get', self._h, which, k,
+                      out.ctypes.data_as(c_double_p))
+
+    def set(self, which, k, arr):
+        arr, p = as_f64(arr)
+        assert arr.size == self.Ny * self.Nx
+        self.lib.call('lsted_deconv_set', self._h, which, k, p)
+
+    def H(self, x):
+        x, p = as_f64(x)
+        assert x.size == self.Ny * self.Nx
+        out = np.empty((self.K, self.Ny, self.Nx), dtype=np.float64)
+        self.lib.call('lsted_deconv_H', self._h, p,
+                      out.ctypes.data_as(c_double_p))
+        return out
+
+    def Ht(self, y, normalize=True):
+        y, p = as_f64(y)
+        assert y.size == self.K * self.Ny * self.Nx
+        out = np.empty((1, self.Ny, self.Nx), dtype=np.float64)
+        self.lib.call('lsted_deconv_Ht', self._h, p,
+                      out.ctypes.data_as(c_double_p), int(bool(normalize)))
+        return out
+
+    def sync(self):
+        self.lib.call('lsted_deconv_sync', self._h)
+
+    def timer_start(self):
+        self.lib.call('lsted_deconv_timer_start', self._h)
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        self.lib.call('lsted_deconv_timer_stop', self._h, ctypes.byref(ms))
+        return ms.value
+
+    def profile(self, reset=False):
+        ms = (ctypes.c_double * NUM_KERNEL_KINDS)()
+        n = (ctypes.c_longlong * NUM_KERNEL_KINDS)()
+        self.lib.call('lsted_deconv_profile', self._h, int(reset), ms, n)
+        return {kind: (ms[i], n[i]) for i, kind in enumerate(KERNEL_KINDS)}

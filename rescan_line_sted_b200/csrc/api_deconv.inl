@@ -1,0 +1,193 @@
+// extern "C" Deconvolver entry points of include/lsted.h, written once over
+// the backend type LSTED_BACKEND (CudaBackend in lsted_api.cu; the CPU
+// replay backend in tests/host_emul/emul.cpp, test infrastructure only).
+// The including file provides: LSTED_BACKEND, set_error(), g_error.
+
+struct lsted_deconv {
+    int precision;
+    int device;
+    LSTED_BACKEND* bk;
+    lsted::DeconvEngine<float, LSTED_BACKEND>* e32;
+    lsted::DeconvEngine<double, LSTED_BACKEND>* e64;
+};
+
+#define LSTED_TRY try {
+#define LSTED_CATCH                                                        \
+    }                                                                      \
+    catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }  \
+    catch (const std::string& s) { return set_error(LSTED_ERR_ARG, s); }   \
+    catch (const std::bad_alloc&) { return set_error(LSTED_ERR_ARG, "host allocation failed"); }
+#define LSTED_ENGINE(h, call)                  \
+    do {                                       \
+        (h)->bk->activate();                   \
+        if ((h)->precision == 32) (h)->e32->call; \
+        else (h)->e64->call;                   \
+    } while (0)
+
+extern "C" int lsted_deconv_create(lsted_deconv** out, int device, const double* psfs, int K, int ny,
+                                   int nx, int Ny, int Nx, int precision) {
+    if (!out || !psfs) return set_error(LSTED_ERR_ARG, "null pointer");
+    if (precision != 32 && precision != 64) return set_error(LSTED_ERR_ARG, "precision must be 32 or 64");
+    if (K < 1) return set_error(LSTED_ERR_ARG, "need at least one PSF");
+    lsted_deconv* h = new lsted_deconv();
+    h->precision = precision; h->device = device; h->bk = 0; h->e32 = 0; h->e64 = 0;
+    LSTED_TRY
+    h->bk = new LSTED_BACKEND(device);
+    h->bk->activate();
+    if (precision == 32) {
+        h->e32 = new lsted::DeconvEngine<float, LSTED_BACKEND>(*h->bk, K, ny, nx, Ny, Nx);
+        h->e32->set_psfs(psfs);
+    } else {
+        h->e64 = new lsted::DeconvEngine<double, LSTED_BACKEND>(*h->bk, K, ny, nx, Ny, Nx);
+        h->e64->set_psfs(psfs);
+    }
+    *out = h;
+    return LSTED_OK;
+    }
+    catch (const lsted::ApiError& e) { lsted_deconv_destroy(h); return set_error(e.code, e.msg); }
+    catch (const std::string& s) { lsted_deconv_destroy(h); return set_error(LSTED_ERR_ARG, s); }
+}
+
+extern "C" int lsted_deconv_destroy(lsted_deconv* h) {
+    if (!h) return LSTED_OK;
+    try {
+        if (h->bk) h->bk->activate();
+        delete h->e32;
+        delete h->e64;
+        delete h->bk;
+    } catch (...) {}
+    delete h;
+    return LSTED_OK;
+}
+
+extern "C" int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info) {
+    if (!h || !info) return set_error(LSTED_ERR_ARG, "null pointer");
+    memset(info, 0, sizeof(*info));
+    const lsted::ConvGeom& g = h->precision == 32 ? h->e32->g : h->e64->g;
+    const int K = h->precision == 32 ? h->e32->K : h->e64->K;
+    const int cb = h->precision == 32 ? 8 : 16;
+    info->K = K;
+    info->ny = h->precision == 32 ? h->e32->ny : h->e64->ny;
+    info->nx = h->precision == 32 ? h->e32->nx : h->e64->nx;
+    info->Ny = g.Ny; info->Nx = g.Nx; info->Ly = g.Ly; info->Lx = g.Lx;
+    info->cols_per_cta = g.C; info->row_pairs_per_cta = g.PR;
+    info->precision = h->precision;
+    info->iterations_done = h->precision == 32 ? h->e32->iterations_done : h->e64->iterations_done;
+    info->device = h->device;
+    info->row_smem_bytes = lsted::row_smem_bytes(g, cb);
+    info->col_smem_bytes = lsted::col_smem_bytes(g, cb);
+    info->device_bytes = h->bk->bytes_allocated();
+    const double A = (double)(cb / 2) * g.Ny * g.Nx;
+    info->bytes_forward = (2.0 * K + 1.0) * A;
+    info->bytes_normalization = A;
+    info->bytes_iteration = (K + 4.0) * A;
+    return LSTED_OK;
+}
+
+extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double value) {
+    if (!h || !name) return set_error(LSTED_ERR_ARG, "null pointer");
+    if (!strcmp(name, "exact_clip")) {
+        if (h->precision == 32) h->e32->exact_clip = value != 0;
+        else h->e64->exact_clip = value != 0;
+        return LSTED_OK;
+    }
+    if (!strcmp(name, "profile")) { h->bk->set_profile(value != 0); return LSTED_OK; }
+    return set_error(LSTED_ERR_ARG, std::string("unknown option ") + name);
+}
+
+extern "C" int lsted_deconv_create_data(lsted_deconv* h, const double* object, double total_brightness,
+                                        int rescale, uint64_t seed) {
+    if (!h || !object) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    LSTED_ENGINE(h, create_data(object, total_brightness, rescale != 0, seed));
+    h->bk->sync();
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_iterate(lsted_deconv* h, int n) {
+    if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    LSTED_ENGINE(h, iterate(n));
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+static int check_which(lsted_deconv* h, int which, int k) {
+    const int K = h->precision == 32 ? h->e32->K : h->e64->K;
+    if (which < 0 || which > 4) return 1;
+    if ((which == LSTED_NOISELESS || which == LSTED_NOISY) ? (k < 0 || k >= K) : (k != 0)) return 1;
+    return 0;
+}
+
+extern "C" int lsted_deconv_get(lsted_deconv* h, int which, int k, double* out) {
+    if (!h || !out) return set_error(LSTED_ERR_ARG, "null pointer");
+    if (check_which(h, which, k)) return set_error(LSTED_ERR_ARG, "bad array selector");
+    LSTED_TRY
+    LSTED_ENGINE(h, get_array(which, k, out));
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_set(lsted_deconv* h, int which, int k, const double* in) {
+    if (!h || !in) return set_error(LSTED_ERR_ARG, "null pointer");
+    if (check_which(h, which, k)) return set_error(LSTED_ERR_ARG, "bad array selector");
+    LSTED_TRY
+    LSTED_ENGINE(h, set_array(which, k, in));
+    h->bk->sync();
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_H(lsted_deconv* h, const double* x, double* out) {
+    if (!h || !x || !out) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    LSTED_ENGINE(h, H_host(x, out));
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_Ht(lsted_deconv* h, const double* y, double* out, int normalize) {
+    if (!h || !y || !out) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    LSTED_ENGINE(h, Ht_host(y, out, normalize != 0));
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_sync(lsted_deconv* h) {
+    if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    h->bk->activate();
+    h->bk->sync();
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_timer_start(lsted_deconv* h) {
+    if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    h->bk->activate();
+    h->bk->timer_start();
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_timer_stop(lsted_deconv* h, float* ms) {
+    if (!h || !ms) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    h->bk->activate();
+    *ms = h->bk->timer_stop();
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_profile(lsted_deconv* h, int reset, double* total_ms, long long* launches) {
+    if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    h->bk->activate();
+    h->bk->profile_collect(total_ms, launches);
+    if (reset) h->bk->profile_reset();
+    return LSTED_OK;
+    LSTED_CATCH
+}

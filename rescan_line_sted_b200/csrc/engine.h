@@ -1,0 +1,280 @@
+// Multi-view Richardson-Lucy engine: orchestration of the row/column passes
+// of conv_bodies.cuh.  Templated on the storage precision T and on a
+// Backend that owns memory and launches kernel bodies (CudaBackend in
+// lsted_api.cu for the product; HostBackend in tests/host_emul for the
+// CPU replay of the same bodies).
+//
+// State mirrors the attributes of the reference `Deconvolver`
+// (figure_generation/line_sted_tools.py:478-594): psfs (as OTFs),
+// true_object, noiseless_measurement[K], noisy_measurement[K], estimate,
+// H_t_normalization.
+#pragma once
+#include <string>
+#include <vector>
+#include "plan.h"
+
+namespace lsted {
+
+enum ArrayId {
+    ARR_TRUE_OBJECT = 0,
+    ARR_NOISELESS = 1,
+    ARR_NOISY = 2,
+    ARR_ESTIMATE = 3,
+    ARR_NORMALIZATION = 4
+};
+
+template <typename T, class BK> class DeconvEngine {
+  public:
+    ConvGeom g;
+    int K, ny, nx;
+    int iterations_done;
+    bool have_norm, have_estimate, exact_clip;
+
+    DeconvEngine(BK& backend, int K_, int ny_, int nx_, int Ny, int Nx)
+        : K(K_), ny(ny_), nx(nx_), iterations_done(0), have_norm(false), have_estimate(false),
+          exact_clip(false), bk(backend) {
+        const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g);
+        if (why[0]) throw std::string(why);
+        npix = (size_t)Ny * Nx;
+        std::vector<cplx<T> > tw;
+        tw.resize(g.Lx); fill_twiddles<T>(g.Lx, tw.data());
+        tw_x = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * g.Lx);
+        bk.upload(tw_x, tw.data(), sizeof(cplx<T>) * g.Lx);
+        tw.resize(g.Ly); fill_twiddles<T>(g.Ly, tw.data());
+        tw_y = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * g.Ly);
+        bk.upload(tw_y, tw.data(), sizeof(cplx<T>) * g.Ly);
+        otf = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * spec_elems(g, g.Ly) * K);
+        spec1 = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * spec_elems(g, g.Ny));
+        specK = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * spec_elems(g, g.Ny) * K);
+        true_object = (T*)bk.alloc(sizeof(T) * npix);
+        estimate = (T*)bk.alloc(sizeof(T) * npix);
+        norm = (T*)bk.alloc(sizeof(T) * npix);
+        scratch = (T*)bk.alloc(sizeof(T) * npix);
+        noiseless = (T*)bk.alloc(sizeof(T) * npix * K);
+        noisy = (T*)bk.alloc(sizeof(T) * npix * K);
+        stage64 = (double*)bk.alloc(sizeof(double) * npix * K);
+        partial = (double*)bk.alloc(sizeof(double) * kReduceBlocks);
+    }
+    ~DeconvEngine() {
+        void* all[] = {tw_x, tw_y, otf, spec1, specK, true_object, estimate, norm,
+                       scratch, noiseless, noisy, stage64, partial};
+        for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) bk.free(all[i]);
+    }
+
+    size_t pixels() const { return npix; }
+
+    // K7: PSFs (host, float64, [K][ny][nx]) -> OTFs, 1/(Lx*Ly) folded in.
+    void set_psfs(const double* psfs_host) {
+        const size_t n = (size_t)K * ny * nx;
+        double* d64 = (double*)bk.alloc(sizeof(double) * n);
+        T* dT = (T*)bk.alloc(sizeof(T) * n);
+        bk.upload(d64, psfs_host, sizeof(double) * n);
+        bk.cast_in(dT, d64, n, 1.0);
+        ConvGeom gp = g;  // same transform lengths, image := PSF
+        gp.Ny = ny; gp.Nx = nx;
+        cplx<T>* rows = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * spec_elems(gp, ny) * K);
+        RowArgs<T> ra = row_args(gp);
+        ra.nimg = K; ra.real_in = dT; ra.spec_out = rows;
+        bk.template launch_row<ROW_FWD, T>(row_blocks(gp) * K, ra);
+        ColArgs<T> ca = col_args(gp);
+        ca.src = rows; ca.dst = otf; ca.K = K; ca.rows_in = ny;
+        ca.scale = (T)(1.0 / ((double)g.Lx * (double)g.Ly));
+        bk.template launch_col<COL_OTF, T>(g.nxb * K, ca);
+        bk.sync();
+        bk.free(rows); bk.free(dT); bk.free(d64);
+        have_norm = false;
+    }
+
+    // ---- operators on device arrays ------------------------------------
+    // H: x[Ny][Nx] -> out[K][Ny][Nx] (clipped); optional Poisson copy.
+    void op_H(const T* x, T* out, T* out_noisy, unsigned long long seed) {
+        RowArgs<T> ra = row_args(g);
+        ra.nimg = 1; ra.real_in = x; ra.spec_out = spec1;
+        bk.template launch_row<ROW_FWD, T>(row_blocks(g), ra);
+        ColArgs<T> ca = col_args(g);
+        ca.src = spec1; ca.dst = specK; ca.K = K;
+        bk.template launch_col<COL_H, T>(g.nxb, ca);
+        RowArgs<T> rb = row_args(g);
+        rb.nimg = K; rb.spec_in = specK; rb.real_out = out; rb.clip = 1;
+        if (out_noisy) {
+            rb.real_out2 = out_noisy; rb.seed = seed; rb.img0 = 0;
+            bk.template launch_row<ROW_INV_SIM, T>(row_blocks(g) * K, rb);
+        } else {
+            bk.template launch_row<ROW_INV_STORE, T>(row_blocks(g) * K, rb);
+        }
+    }
+
+    // H_t without normalisation: y[K][Ny][Nx] -> out[Ny][Nx].
+    // Default: products summed in the Fourier domain, one inverse transform,
+    // clip after the sum.  exact_clip: inverse-transform and clip each term
+    // before summing, like the reference loop (line_sted_tools.py:585-588).
+    void op_Ht_raw(const T* y, T* out) {
+        RowArgs<T> ra = row_args(g);
+        ra.nimg = K; ra.real_in = y; ra.spec_out = specK;
+        bk.template launch_row<ROW_FWD, T>(row_blocks(g) * K, ra);
+        ht_from_specK(out);
+    }
+
+    // ---- Deconvolver methods ---------------------------------------------
+    void create_data(const double* obj_host, double total_brightness, bool rescale,
+                     unsigned long long seed) {
+        bk.upload(stage64, obj_host, sizeof(double) * npix);
+        double s = 1.0;
+        if (rescale) s = total_brightness / bk.sum(stage64, npix, partial);
+        bk.cast_in(true_object, stage64, npix, s);
+        op_H(true_object, noiseless, noisy, seed);
+        iterations_done = 0;
+        have_estimate = false;
+    }
+
+    void iterate(int n) {
+        for (int it = 0; it < n; ++it) {
+            ensure_norm();
+            if (!have_estimate) {
+                bk.fill(estimate, npix, (T)1);
+                RowArgs<T> ra = row_args(g);
+                ra.nimg = 1; ra.real_in = estimate; ra.spec_out = spec1;
+                bk.template launch_row<ROW_FWD, T>(row_blocks(g), ra);
+                have_estimate = true;
+            }
+            // expected = H(estimate); ratio = measurement / expected -> row spectra
+            ColArgs<T> ca = col_args(g);
+            ca.src = spec1; ca.dst = specK; ca.K = K;
+            bk.template launch_col<COL_H, T>(g.nxb, ca);
+            RowArgs<T> rm = row_args(g);
+            rm.nimg = K; rm.spec_in = specK; rm.spec_out = specK; rm.aux = noisy;
+            bk.template launch_row<ROW_MID, T>(row_blocks(g) * K, rm);
+            if (!exact_clip) {
+                ColArgs<T> ct = col_args(g);
+                ct.src = specK; ct.dst = spec1; ct.K = K;
+                bk.template launch_col<COL_HT, T>(g.nxb, ct);
+                RowArgs<T> rf = row_args(g);
+                rf.nimg = 1; rf.spec_in = spec1; rf.spec_out = spec1;
+                rf.real_out = estimate; rf.aux = norm;
+                bk.template launch_row<ROW_FINAL, T>(row_blocks(g), rf);
+            } else {
+                ht_from_specK(scratch);
+                bk.rl_update(estimate, scratch, norm, npix);
+                RowArgs<T> ra = row_args(g);
+                ra.nimg = 1; ra.real_in = estimate; ra.spec_out = spec1;
+                bk.template launch_row<ROW_FWD, T>(row_blocks(g), ra);
+            }
+            ++iterations_done;
+        }
+    }
+
+    // The estimate spectrum cached in spec1 goes stale when anything else
+    // uses spec1 or when the caller overwrites the estimate.
+    void invalidate_estimate_spectrum() {
+        if (!have_estimate) return;
+        RowArgs<T> ra = row_args(g);
+        ra.nimg = 1; ra.real_in = estimate; ra.spec_out = spec1;
+        bk.template launch_row<ROW_FWD, T>(row_blocks(g), ra);
+    }
+
+    T* array(int id, int k) {
+        switch (id) {
+            case ARR_TRUE_OBJECT: return true_object;
+            case ARR_NOISELESS: return noiseless + npix * k;
+            case ARR_NOISY: return noisy + npix * k;
+            case ARR_ESTIMATE: return estimate;
+            case ARR_NORMALIZATION: return norm;
+        }
+        return 0;
+    }
+
+    void get_array(int id, int k, double* host) {
+        if (id == ARR_NORMALIZATION) ensure_norm();
+        bk.cast_out(stage64, array(id, k), npix);
+        bk.download(host, stage64, sizeof(double) * npix);
+    }
+    void set_array(int id, int k, const double* host) {
+        bk.upload(stage64, host, sizeof(double) * npix);
+        bk.cast_in(array(id, k), stage64, npix, 1.0);
+        if (id == ARR_ESTIMATE) { have_estimate = true; invalidate_estimate_spectrum(); }
+        if (id == ARR_NORMALIZATION) have_norm = true;
+    }
+
+    // Host-array forms of H / H_t for the Python methods.
+    void H_host(const double* x, double* out) {
+        bk.upload(stage64, x, sizeof(double) * npix);
+        bk.cast_in(scratch, stage64, npix, 1.0);
+        T* tmp = (T*)bk.alloc(sizeof(T) * npix * K);
+        op_H(scratch, tmp, 0, 0);
+        bk.cast_out(stage64, tmp, npix * K);
+        bk.download(out, stage64, sizeof(double) * npix * K);
+        bk.free(tmp);
+        invalidate_estimate_spectrum();
+    }
+    void Ht_host(const double* y, double* out, bool normalize) {
+        T* tmp = (T*)bk.alloc(sizeof(T) * npix * K);
+        if (normalize) ensure_norm();
+        bk.upload(stage64, y, sizeof(double) * npix * K);
+        bk.cast_in(tmp, stage64, npix * K, 1.0);
+        op_Ht_raw(tmp, scratch);
+        if (normalize) bk.divide(scratch, norm, npix);
+        bk.cast_out(stage64, scratch, npix);
+        bk.download(out, stage64, sizeof(double) * npix);
+        bk.free(tmp);
+        invalidate_estimate_spectrum();
+    }
+
+  private:
+    enum { kReduceBlocks = 1024 };
+    BK& bk;
+    size_t npix;
+    cplx<T>*tw_x, *tw_y, *otf, *spec1, *specK;
+    T *true_object, *estimate, *norm, *scratch, *noiseless, *noisy;
+    double *stage64, *partial;
+
+    RowArgs<T> row_args(const ConvGeom& gg) {
+        RowArgs<T> a;
+        memset(&a, 0, sizeof(a));
+        a.g = gg; a.tw = tw_x;
+        return a;
+    }
+    ColArgs<T> col_args(const ConvGeom& gg) {
+        ColArgs<T> a;
+        memset(&a, 0, sizeof(a));
+        a.g = gg; a.tw = tw_y; a.otf = otf; a.rows_in = gg.Ny; a.scale = (T)1;
+        return a;
+    }
+    // specK holds K row-spectra -> out = sum_k conv_k (spec1 is clobbered)
+    void ht_from_specK(T* out) {
+        if (!exact_clip) {
+            ColArgs<T> ct = col_args(g);
+            ct.src = specK; ct.dst = spec1; ct.K = K;
+            bk.template launch_col<COL_HT, T>(g.nxb, ct);
+            RowArgs<T> rb = row_args(g);
+            rb.nimg = 1; rb.spec_in = spec1; rb.real_out = out; rb.clip = 1;
+            bk.template launch_row<ROW_INV_STORE, T>(row_blocks(g), rb);
+        } else {
+            // one orientation at a time: product, inverse, clip, accumulate
+            for (int k = 0; k < K; ++k) {
+                ColArgs<T> ct = col_args(g);
+                ct.src = specK + spec_elems(g, g.Ny) * k;
+                ct.otf = otf + spec_elems(g, g.Ly) * k;
+                ct.dst = spec1; ct.K = 1;
+                bk.template launch_col<COL_HT, T>(g.nxb, ct);
+                RowArgs<T> rb = row_args(g);
+                rb.nimg = 1; rb.spec_in = spec1; rb.real_out = out; rb.clip = 1;
+                rb.accumulate = (k > 0);
+                bk.template launch_row<ROW_INV_STORE, T>(row_blocks(g), rb);
+            }
+        }
+    }
+  public:
+    // H_t_normalization = H_t(ones, normalize=False) (line_sted_tools.py:589-593)
+    void ensure_norm() {
+        if (have_norm) return;
+        T* ones = (T*)bk.alloc(sizeof(T) * npix * K);
+        bk.fill(ones, npix * K, (T)1);
+        op_Ht_raw(ones, norm);
+        bk.sync();
+        bk.free(ones);
+        have_norm = true;
+        invalidate_estimate_spectrum();  // op_Ht_raw clobbered spec1
+    }
+};
+
+}  // namespace lsted

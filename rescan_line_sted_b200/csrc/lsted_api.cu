@@ -1,0 +1,422 @@
+// liblsted.so -- sm_100a kernels + the C ABI of include/lsted.h.
+//
+// Build: see Makefile (nvcc -gencode arch=compute_100a,code=sm_100a).
+// The kernels are thin __global__ shells around the bodies in
+// conv_bodies.cuh / psf_kernels.cuh; orchestration lives in engine.h.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lsted.h"
+#include "engine.h"
+#include "ew_bodies.cuh"
+#include "psf_kernels.cuh"
+
+namespace lsted {
+struct ApiError { int code; std::string msg; };
+}
+
+static thread_local std::string g_error;
+static int set_error(int code, const std::string& msg) { g_error = msg; return code; }
+
+#define CUDA_CHECK(expr)                                                                  \
+    do {                                                                                  \
+        cudaError_t err__ = (expr);                                                       \
+        if (err__ != cudaSuccess) {                                                       \
+            lsted::ApiError e__;                                                          \
+            e__.code = LSTED_ERR_CUDA;                                                    \
+            e__.msg = std::string(#expr) + ": " + cudaGetErrorString(err__);              \
+            throw e__;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Device-side CTA context and kernel shells
+// ---------------------------------------------------------------------------
+struct DeviceCtx {
+    template <class F> __device__ __forceinline__ void parallel_for(int n, F f) {
+        for (int w = threadIdx.x; w < n; w += blockDim.x) f(w);
+        __syncthreads();
+    }
+};
+
+enum { kRowThreads = 256, kColThreads32 = 512, kColThreads64 = 256, kEwThreads = 256 };
+
+template <int MODE, typename T>
+__global__ void __launch_bounds__(kRowThreads)
+row_kernel(const __grid_constant__ lsted::RowArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DeviceCtx cx;
+    lsted::row_body<MODE, T>(cx, blockIdx.x, a, reinterpret_cast<lsted::cplx<T>*>(smem_raw));
+}
+
+template <int MODE, typename T>
+__global__ void __launch_bounds__(sizeof(T) == 4 ? kColThreads32 : kColThreads64)
+col_kernel(const __grid_constant__ lsted::ColArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DeviceCtx cx;
+    lsted::col_body<MODE, T>(cx, blockIdx.x, a, reinterpret_cast<lsted::cplx<T>*>(smem_raw));
+}
+
+template <int OP, typename T>
+__global__ void __launch_bounds__(kEwThreads) ew_kernel(const lsted::EwArgs<T> a) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
+        lsted::ew_apply<OP, T>(a, i);
+}
+
+// Two-stage deterministic sum in double: per-block partials, then block 0.
+__global__ void __launch_bounds__(256) sum_partial_kernel(const double* x, size_t n, double* partial) {
+    __shared__ double sh[256];
+    double s = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s += x[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) sum_final_kernel(double* partial, int nblocks) {
+    __shared__ double sh[256];
+    double s = 0;
+    for (int i = threadIdx.x; i < nblocks; i += 256) s += partial[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[0] = sh[0];
+}
+
+// ---------------------------------------------------------------------------
+// CUDA backend of the engine
+// ---------------------------------------------------------------------------
+enum KernelKind { KK_ROW_FWD = 0, KK_ROW_INV_STORE, KK_ROW_INV_SIM, KK_ROW_MID, KK_ROW_FINAL,
+                  KK_COL_OTF, KK_COL_H, KK_COL_HT, KK_EW };
+
+class CudaBackend {
+  public:
+    explicit CudaBackend(int device) : device_(device), stream_(0), bytes_(0), profile_(false),
+                                       t0_(0), t1_(0), num_sms_(148) {
+        int count = 0;
+        CUDA_CHECK(cudaGetDeviceCount(&count));
+        if (device < 0 || device >= count) {
+            lsted::ApiError e; e.code = LSTED_ERR_CUDA;
+            e.msg = "CUDA device " + std::to_string(device) + " not available (" +
+                    std::to_string(count) + " visible); there is no CPU fallback";
+            throw e;
+        }
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreate(&t0_));
+        CUDA_CHECK(cudaEventCreate(&t1_));
+        CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device));
+        memset(prof_ms_, 0, sizeof(prof_ms_));
+        memset(prof_n_, 0, sizeof(prof_n_));
+    }
+    ~CudaBackend() {
+        cudaSetDevice(device_);
+        for (size_t i = 0; i < ev_pool_.size(); ++i) cudaEventDestroy(ev_pool_[i]);
+        if (t0_) cudaEventDestroy(t0_);
+        if (t1_) cudaEventDestroy(t1_);
+        if (stream_) cudaStreamDestroy(stream_);
+    }
+    void activate() { CUDA_CHECK(cudaSetDevice(device_)); }
+    void sync() { CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+    cudaStream_t stream() const { return stream_; }
+
+    void* alloc(size_t bytes) {
+        void* p = 0;
+        CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));
+        bytes_ += bytes;
+        return p;
+    }
+    void free(void* p) { if (p) cudaFree(p); }
+    size_t bytes_allocated() const { return bytes_; }
+    void upload(void* d, const void* s, size_t n) {
+        CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream_));
+    }
+    void download(void* d, const void* s, size_t n) {
+        CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream_));
+        sync();
+    }
+
+    // ---- timing ----
+    void timer_start() { CUDA_CHECK(cudaEventRecord(t0_, stream_)); }
+    float timer_stop() {
+        CUDA_CHECK(cudaEventRecord(t1_, stream_));
+        CUDA_CHECK(cudaEventSynchronize(t1_));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, t0_, t1_));
+        return ms;
+    }
+    void set_profile(bool on) { profile_ = on; }
+    void profile_reset() {
+        profile_drain();
+        memset(prof_ms_, 0, sizeof(prof_ms_));
+        memset(prof_n_, 0, sizeof(prof_n_));
+    }
+    void profile_collect(double* ms, long long* n) {
+        profile_drain();
+        for (int i = 0; i < LSTED_NUM_KERNEL_KINDS; ++i) {
+            if (ms) ms[i] = prof_ms_[i];
+            if (n) n[i] = prof_n_[i];
+        }
+    }
+
+    // ---- launches ----
+    template <int MODE, typename T> void launch_row(int grid, const lsted::RowArgs<T>& a) {
+        if (grid <= 0) return;
+        const size_t smem = lsted::row_smem_bytes(a.g, (int)sizeof(lsted::cplx<T>));
+        static size_t configured = 0;  // per instantiation
+        if (smem > configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(row_kernel<MODE, T>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        const int kind = MODE == lsted::ROW_FWD ? KK_ROW_FWD
+                       : MODE == lsted::ROW_INV_STORE ? KK_ROW_INV_STORE
+                       : MODE == lsted::ROW_INV_SIM ? KK_ROW_INV_SIM
+                       : MODE == lsted::ROW_MID ? KK_ROW_MID : KK_ROW_FINAL;
+        before(kind);
+        row_kernel<MODE, T><<<grid, kRowThreads, smem, stream_>>>(a);
+        after();
+    }
+    template <int MODE, typename T> void launch_col(int grid, const lsted::ColArgs<T>& a) {
+        if (grid <= 0) return;
+        const size_t smem = lsted::col_smem_bytes(a.g, (int)sizeof(lsted::cplx<T>));
+        static size_t configured = 0;
+        if (smem > configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(col_kernel<MODE, T>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        const int kind = MODE == lsted::COL_OTF ? KK_COL_OTF : MODE == lsted::COL_H ? KK_COL_H : KK_COL_HT;
+        const int threads = sizeof(T) == 4 ? kColThreads32 : kColThreads64;
+        before(kind);
+        col_kernel<MODE, T><<<grid, threads, smem, stream_>>>(a);
+        after();
+    }
+    template <int OP, typename T> void ew(const lsted::EwArgs<T>& a) {
+        if (a.n == 0) return;
+        size_t blocks = (a.n + kEwThreads - 1) / kEwThreads;
+        const size_t cap = (size_t)num_sms_ * 16;
+        if (blocks > cap) blocks = cap;
+        before(KK_EW);
+        ew_kernel<OP, T><<<(int)blocks, kEwThreads, 0, stream_>>>(a);
+        after();
+    }
+    template <typename T> void cast_in(T* dst, const double* src, size_t n, double s) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = dst; a.d1 = src; a.s = s; a.n = n;
+        ew<lsted::EW_CAST_IN, T>(a);
+    }
+    template <typename T> void cast_out(double* dst, const T* src, size_t n) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.d0 = dst; a.t1 = src; a.n = n;
+        ew<lsted::EW_CAST_OUT, T>(a);
+    }
+    template <typename T> void fill(T* dst, size_t n, T v) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = dst; a.s = (double)v; a.n = n;
+        ew<lsted::EW_FILL, T>(a);
+    }
+    template <typename T> void divide(T* io, const T* den, size_t n) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = io; a.t1 = den; a.n = n;
+        ew<lsted::EW_DIVIDE, T>(a);
+    }
+    template <typename T> void rl_update(T* est, const T* num, const T* den, size_t n) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = est; a.t1 = num; a.t2 = den; a.n = n;
+        ew<lsted::EW_RL_UPDATE, T>(a);
+    }
+    double sum(const double* x, size_t n, double* partial) {
+        const int blocks = 1024;
+        before(KK_EW);
+        sum_partial_kernel<<<blocks, 256, 0, stream_>>>(x, n, partial);
+        sum_final_kernel<<<1, 256, 0, stream_>>>(partial, blocks);
+        after();
+        double s = 0;
+        download(&s, partial, sizeof(double));
+        return s;
+    }
+
+  private:
+    int device_;
+    cudaStream_t stream_;
+    size_t bytes_;
+    bool profile_;
+    cudaEvent_t t0_, t1_;
+    int num_sms_;
+    std::vector<cudaEvent_t> ev_pool_;
+    struct Span { int kind; size_t e0, e1; };
+    std::vector<Span> spans_;
+    size_t ev_used_ = 0;
+    double prof_ms_[LSTED_NUM_KERNEL_KINDS];
+    long long prof_n_[LSTED_NUM_KERNEL_KINDS];
+
+    size_t next_event() {
+        if (ev_used_ == ev_pool_.size()) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreate(&e));
+            ev_pool_.push_back(e);
+        }
+        return ev_used_++;
+    }
+    void before(int kind) {
+        if (!profile_) return;
+        Span s; s.kind = kind; s.e0 = next_event(); s.e1 = 0;
+        CUDA_CHECK(cudaEventRecord(ev_pool_[s.e0], stream_));
+        spans_.push_back(s);
+    }
+    void after() {
+        CUDA_CHECK(cudaGetLastError());
+        if (!profile_) return;
+        Span& s = spans_.back();
+        s.e1 = next_event();
+        CUDA_CHECK(cudaEventRecord(ev_pool_[s.e1], stream_));
+    }
+    void profile_drain() {
+        if (spans_.empty()) return;
+        sync();
+        for (size_t i = 0; i < spans_.size(); ++i) {
+            float ms = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ev_pool_[spans_[i].e0], ev_pool_[spans_[i].e1]));
+            prof_ms_[spans_[i].kind] += ms;
+            prof_n_[spans_[i].kind] += 1;
+        }
+        spans_.clear();
+        ev_used_ = 0;
+    }
+};
+
+#define LSTED_BACKEND CudaBackend
+#include "api_deconv.inl"
+
+// ---------------------------------------------------------------------------
+// Core entry points
+// ---------------------------------------------------------------------------
+extern "C" int lsted_version(void) { return 100; }
+extern "C" const char* lsted_last_error(void) { return g_error.c_str(); }
+
+extern "C" int lsted_device_count(int* count) {
+    if (!count) return set_error(LSTED_ERR_ARG, "null pointer");
+    cudaError_t err = cudaGetDeviceCount(count);
+    if (err != cudaSuccess) {
+        *count = 0;
+        return set_error(LSTED_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(err));
+    }
+    return LSTED_OK;
+}
+
+extern "C" int lsted_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return set_error(LSTED_ERR_ARG, "null pointer");
+    cudaError_t err = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (err != cudaSuccess)
+        return set_error(LSTED_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(err));
+    return LSTED_OK;
+}
+extern "C" int lsted_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+    return LSTED_OK;
+}
+
+// ---------------------------------------------------------------------------
+// PSF synthesis (fp64)
+// ---------------------------------------------------------------------------
+namespace {
+struct DeviceBuf {
+    void* p;
+    explicit DeviceBuf(size_t bytes) : p(0) { CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); }
+    ~DeviceBuf() { if (p) cudaFree(p); }
+    template <typename U> U* as() { return (U*)p; }
+};
+void select_device(int device) {
+    int count = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) {
+        lsted::ApiError e; e.code = LSTED_ERR_CUDA;
+        e.msg = "CUDA device " + std::to_string(device) + " not available; there is no CPU fallback";
+        throw e;
+    }
+    CUDA_CHECK(cudaSetDevice(device));
+}
+}  // namespace
+
+extern "C" int lsted_psf_illumination(int device, int psf_type, int batch, int n, const double* taps,
+                                      int radius, const double* excitation_brightness,
+                                      const double* depletion_brightness, double* excitation,
+                                      double* depletion, double* excitation_fraction,
+                                      double* depletion_fraction, double* sted) {
+    if (!taps || !excitation_brightness || !depletion_brightness || !excitation || !depletion ||
+        !excitation_fraction || !depletion_fraction || !sted)
+        return set_error(LSTED_ERR_ARG, "null pointer");
+    if (batch < 1 || n < 1 || radius < 0 || (psf_type != 0 && psf_type != 1))
+        return set_error(LSTED_ERR_ARG, "bad PSF arguments");
+    if (n > lsted::kPsfMaxN || 2 * radius + 1 > lsted::kPsfMaxTaps)
+        return set_error(LSTED_ERR_ARG, "PSF grid too large for the on-chip kernel");
+    try {
+        select_device(device);
+        const size_t img = (size_t)n * n, ntap = 2 * radius + 1;
+        DeviceBuf d_taps(sizeof(double) * ntap), d_eb(sizeof(double) * batch), d_db(sizeof(double) * batch);
+        DeviceBuf d_out(sizeof(double) * img * 5 * batch);
+        CUDA_CHECK(cudaMemcpy(d_taps.p, taps, sizeof(double) * ntap, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d_eb.p, excitation_brightness, sizeof(double) * batch, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d_db.p, depletion_brightness, sizeof(double) * batch, cudaMemcpyHostToDevice));
+        lsted::PsfIlluminationArgs a;
+        a.psf_type = psf_type; a.n = n; a.radius = radius;
+        a.taps = d_taps.as<double>();
+        a.exc_brightness = d_eb.as<double>(); a.dep_brightness = d_db.as<double>();
+        a.out = d_out.as<double>();
+        lsted::psf_illumination_kernel<<<batch, lsted::kPsfThreads>>>(a);
+        CUDA_CHECK(cudaGetLastError());
+        double* outs[5] = {excitation, depletion, excitation_fraction, depletion_fraction, sted};
+        for (int b = 0; b < batch; ++b)
+            for (int i = 0; i < 5; ++i)
+                CUDA_CHECK(cudaMemcpy(outs[i] + img * b, d_out.as<double>() + img * (5 * (size_t)b + i),
+                                      sizeof(double) * img, cudaMemcpyDeviceToHost));
+        return LSTED_OK;
+    } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
+}
+
+extern "C" int lsted_psf_rescan(int device, int batch, int n, const double* taps, int radius,
+                                const double* sted_rows, const int* ratios, double* emission,
+                                double* rescan, double* descan, double* wide) {
+    if (!taps || !sted_rows || !ratios || !emission || !rescan || !descan)
+        return set_error(LSTED_ERR_ARG, "null pointer");
+    if (batch < 1 || n < 1 || radius < 0) return set_error(LSTED_ERR_ARG, "bad PSF arguments");
+    if (n > lsted::kPsfMaxN || 2 * radius + 1 > lsted::kPsfMaxTaps)
+        return set_error(LSTED_ERR_ARG, "PSF grid too large for the on-chip kernel");
+    if (wide && batch != 1) return set_error(LSTED_ERR_ARG, "`wide` output needs batch == 1");
+    for (int b = 0; b < batch; ++b)
+        if (ratios[b] < 1 || (long long)ratios[b] * n > (1 << 24))
+            return set_error(LSTED_ERR_ARG, "rescan ratio out of range");
+    try {
+        select_device(device);
+        const size_t img = (size_t)n * n, ntap = 2 * radius + 1;
+        const size_t W = wide ? (size_t)ratios[0] * n : 0;
+        DeviceBuf d_taps(sizeof(double) * ntap), d_rows(sizeof(double) * n * batch);
+        DeviceBuf d_ratios(sizeof(int) * batch), d_out(sizeof(double) * img * 3 * batch);
+        DeviceBuf d_wide(sizeof(double) * (size_t)n * W);
+        CUDA_CHECK(cudaMemcpy(d_taps.p, taps, sizeof(double) * ntap, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d_rows.p, sted_rows, sizeof(double) * n * batch, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d_ratios.p, ratios, sizeof(int) * batch, cudaMemcpyHostToDevice));
+        lsted::PsfRescanArgs a;
+        a.n = n; a.radius = radius; a.taps = d_taps.as<double>();
+        a.sted_rows = d_rows.as<double>(); a.ratios = d_ratios.as<int>();
+        a.out = d_out.as<double>(); a.wide = wide ? d_wide.as<double>() : 0;
+        lsted::psf_rescan_kernel<<<batch, lsted::kPsfThreads>>>(a);
+        CUDA_CHECK(cudaGetLastError());
+        double* outs[3] = {emission, rescan, descan};
+        for (int b = 0; b < batch; ++b)
+            for (int i = 0; i < 3; ++i)
+                CUDA_CHECK(cudaMemcpy(outs[i] + img * b, d_out.as<double>() + img * (3 * (size_t)b + i),
+                                      sizeof(double) * img, cudaMemcpyDeviceToHost));
+        if (wide)
+            CUDA_CHECK(cudaMemcpy(wide, d_wide.p, sizeof(double) * (size_t)n * W, cudaMemcpyDeviceToHost));
+        return LSTED_OK;
+    } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
+}

@@ -1,0 +1,192 @@
+// TEST INFRASTRUCTURE ONLY -- CPU replay of the kernel bodies.
+//
+// Compiles the very same row/column/FFT bodies that lsted_api.cu launches
+// as sm_100a kernels, but runs every CTA serially (parallel_for = plain
+// loop, one "block" after another).  It lets the `-m "not gpu"` tests check
+// the numerics and the orchestration of the engine in the build container,
+// which has no GPU.  The product never loads this library: the package
+// binds liblsted.so only and fails loudly when that is missing.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <string>
+#include <vector>
+#include "../../include/lsted.h"
+#include "../../rescan_line_sted_b200/csrc/engine.h"
+#include "../../rescan_line_sted_b200/csrc/ew_bodies.cuh"
+#include "../../rescan_line_sted_b200/csrc/psf_kernels.cuh"
+
+namespace lsted {
+struct ApiError { int code; std::string msg; };
+}
+
+static thread_local std::string g_error;
+static int set_error(int code, const std::string& msg) { g_error = msg; return code; }
+extern "C" const char* lsted_last_error(void) { return g_error.c_str(); }
+
+struct HostCtx {
+    template <class F> void parallel_for(int n, F f) { for (int w = 0; w < n; ++w) f(w); }
+};
+
+class HostBackend {
+  public:
+    explicit HostBackend(int) : bytes_(0) {}
+    void activate() {}
+    void sync() {}
+    void* alloc(size_t bytes) { bytes_ += bytes; return malloc(bytes ? bytes : 1); }
+    void free(void* p) { ::free(p); }
+    size_t bytes_allocated() const { return bytes_; }
+    void upload(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+    void download(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+    void set_profile(bool) {}
+    void timer_start() {}
+    float timer_stop() { return 0.f; }
+    void profile_collect(double* ms, long long* n) {
+        for (int i = 0; i < LSTED_NUM_KERNEL_KINDS; ++i) { if (ms) ms[i] = 0; if (n) n[i] = 0; }
+    }
+    void profile_reset() {}
+
+    template <int MODE, typename T> void launch_row(int grid, const lsted::RowArgs<T>& a) {
+#pragma omp parallel
+        {
+            std::vector<lsted::cplx<T> > smem((size_t)2 * a.g.PR * a.g.Lpx);
+            HostCtx cx;
+#pragma omp for schedule(dynamic)
+            for (int b = 0; b < grid; ++b) lsted::row_body<MODE, T>(cx, b, a, smem.data());
+        }
+    }
+    template <int MODE, typename T> void launch_col(int grid, const lsted::ColArgs<T>& a) {
+#pragma omp parallel
+        {
+            std::vector<lsted::cplx<T> > smem((size_t)3 * a.g.C * a.g.Lpy);
+            HostCtx cx;
+#pragma omp for schedule(dynamic)
+            for (int b = 0; b < grid; ++b) lsted::col_body<MODE, T>(cx, b, a, smem.data());
+        }
+    }
+    template <int OP, typename T> void ew(const lsted::EwArgs<T>& a) {
+        for (size_t i = 0; i < a.n; ++i) lsted::ew_apply<OP, T>(a, i);
+    }
+    template <typename T> void cast_in(T* dst, const double* src, size_t n, double s) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = dst; a.d1 = src; a.s = s; a.n = n;
+        ew<lsted::EW_CAST_IN, T>(a);
+    }
+    template <typename T> void cast_out(double* dst, const T* src, size_t n) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.d0 = dst; a.t1 = src; a.n = n;
+        ew<lsted::EW_CAST_OUT, T>(a);
+    }
+    template <typename T> void fill(T* dst, size_t n, T v) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = dst; a.s = (double)v; a.n = n;
+        ew<lsted::EW_FILL, T>(a);
+    }
+    template <typename T> void divide(T* io, const T* den, size_t n) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = io; a.t1 = den; a.n = n;
+        ew<lsted::EW_DIVIDE, T>(a);
+    }
+    template <typename T> void rl_update(T* est, const T* num, const T* den, size_t n) {
+        lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = est; a.t1 = num; a.t2 = den; a.n = n;
+        ew<lsted::EW_RL_UPDATE, T>(a);
+    }
+    double sum(const double* x, size_t n, double*) {
+        long double s = 0;
+        for (size_t i = 0; i < n; ++i) s += x[i];
+        return (double)s;
+    }
+
+  private:
+    size_t bytes_;
+};
+
+#define LSTED_BACKEND HostBackend
+#include "../../rescan_line_sted_b200/csrc/api_deconv.inl"
+
+// Direct access to the batched shared-memory FFT for unit tests:
+// in/out are [nbatch][L] interleaved (re, im) float64.
+template <typename T>
+static void run_fft(int L, int dir, int nbatch, const double* in, double* out) {
+    lsted::FftPlan plan;
+    if (!lsted::make_fft_plan(L, &plan)) throw std::string("unsupported length");
+    const int Lp = lsted::smem_pitch(L, (int)sizeof(lsted::cplx<T>), 1);
+    std::vector<lsted::cplx<T> > a((size_t)nbatch * Lp), b((size_t)nbatch * Lp), tw(L);
+    lsted::fill_twiddles<T>(L, tw.data());
+    for (int f = 0; f < nbatch; ++f)
+        for (int i = 0; i < L; ++i)
+            a[(size_t)f * Lp + lsted::pad<T>(i)] =
+                lsted::mk<T>((T)in[2 * ((size_t)f * L + i)], (T)in[2 * ((size_t)f * L + i) + 1]);
+    HostCtx cx;
+    lsted::SmemSrc<T> s = {a.data(), Lp};
+    const lsted::cplx<T>* z = dir < 0
+        ? lsted::fft_batch<-1, T>(cx, plan, tw.data(), s, b.data(), a.data(), nbatch, Lp)
+        : lsted::fft_batch<+1, T>(cx, plan, tw.data(), s, b.data(), a.data(), nbatch, Lp);
+    for (int f = 0; f < nbatch; ++f)
+        for (int i = 0; i < L; ++i) {
+            out[2 * ((size_t)f * L + i)] = (double)z[(size_t)f * Lp + lsted::pad<T>(i)].x;
+            out[2 * ((size_t)f * L + i) + 1] = (double)z[(size_t)f * Lp + lsted::pad<T>(i)].y;
+        }
+}
+
+extern "C" int emul_fft(int L, int dir, int nbatch, int precision, const double* in, double* out) {
+    try {
+        if (precision == 32) run_fft<float>(L, dir, nbatch, in, out);
+        else run_fft<double>(L, dir, nbatch, in, out);
+    } catch (const std::string& s) { return set_error(LSTED_ERR_ARG, s); }
+    return 0;
+}
+
+extern "C" int emul_next_smooth_len(int n) { return lsted::next_smooth_len(n); }
+
+extern "C" int emul_fft_plan(int L, int* radices, int cap) {
+    lsted::FftPlan p;
+    if (!lsted::make_fft_plan(L, &p)) return -1;
+    for (int i = 0; i < p.npass && i < cap; ++i) radices[i] = p.radix[i];
+    return p.npass;
+}
+
+extern "C" int emul_poisson(double lam, uint64_t seed, uint64_t first_pixel, int n, double* out) {
+    for (int i = 0; i < n; ++i) out[i] = lsted::poisson_sample(lam, seed, first_pixel + i, 0);
+    return 0;
+}
+
+// PSF synthesis bodies, replayed one CTA after another.
+extern "C" int lsted_psf_illumination(int, int psf_type, int batch, int n, const double* taps,
+                                      int radius, const double* eb, const double* db,
+                                      double* excitation, double* depletion, double* exc_frac,
+                                      double* dep_frac, double* sted) {
+    if (n > lsted::kPsfMaxN || 2 * radius + 1 > lsted::kPsfMaxTaps)
+        return set_error(LSTED_ERR_ARG, "PSF grid too large for the on-chip kernel");
+    const size_t img = (size_t)n * n;
+    std::vector<double> out(img * 5 * batch);
+    lsted::PsfIlluminationArgs a;
+    a.psf_type = psf_type; a.n = n; a.radius = radius; a.taps = taps;
+    a.exc_brightness = eb; a.dep_brightness = db; a.out = out.data();
+    std::vector<lsted::PsfSmem> sm(1);
+    HostCtx cx;
+    for (int b = 0; b < batch; ++b) lsted::psf_illumination_body(cx, b, a, sm.data());
+    double* outs[5] = {excitation, depletion, exc_frac, dep_frac, sted};
+    for (int b = 0; b < batch; ++b)
+        for (int i = 0; i < 5; ++i)
+            memcpy(outs[i] + img * b, out.data() + img * (5 * (size_t)b + i), sizeof(double) * img);
+    return 0;
+}
+
+extern "C" int lsted_psf_rescan(int, int batch, int n, const double* taps, int radius,
+                                const double* sted_rows, const int* ratios, double* emission,
+                                double* rescan, double* descan, double* wide) {
+    if (n > lsted::kPsfMaxN || 2 * radius + 1 > lsted::kPsfMaxTaps)
+        return set_error(LSTED_ERR_ARG, "PSF grid too large for the on-chip kernel");
+    if (wide && batch != 1) return set_error(LSTED_ERR_ARG, "`wide` output needs batch == 1");
+    const size_t img = (size_t)n * n;
+    std::vector<double> out(img * 3 * batch);
+    lsted::PsfRescanArgs a;
+    a.n = n; a.radius = radius; a.taps = taps; a.sted_rows = sted_rows; a.ratios = ratios;
+    a.out = out.data(); a.wide = wide;
+    std::vector<lsted::PsfSmem> sm(1);
+    HostCtx cx;
+    for (int b = 0; b < batch; ++b) lsted::psf_rescan_body(cx, b, a, sm.data());
+    double* outs[3] = {emission, rescan, descan};
+    for (int b = 0; b < batch; ++b)
+        for (int i = 0; i < 3; ++i)
+            memcpy(outs[i] + img * b, out.data() + img * (3 * (size_t)b + i), sizeof(double) * img);
+    return 0;
+}
