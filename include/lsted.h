@@ -85,12 +85,18 @@ int lsted_deconv_create(lsted_deconv** out, int device, const double* psfs, int 
 int lsted_deconv_destroy(lsted_deconv* h);
 int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info);
 /* options: "exact_clip" (0|1: clip every H_t term before the sum, like :587),
- *          "profile" (0|1: per-kernel CUDA-event timing)                           */
+ *          "profile" (0|1: per-kernel CUDA-event timing),
+ *          "forget_normalization" (drop the cached H_t_normalization, :590)        */
 int lsted_deconv_set_option(lsted_deconv* h, const char* name, double value);
 /* create_data_from_object (:496-512).  rescale != 0 applies total_brightness.
  * Noise: in-kernel Philox4x32-10 Poisson, stream selected by `seed`.               */
 int lsted_deconv_create_data(lsted_deconv* h, const double* object, double total_brightness,
                              int rescale, uint64_t seed);
+/* The same in two asynchronous halves for pipelines that keep the object in HBM:
+ * stage the object (H2D on the handle's stream; pass pinned memory to overlap),
+ * then run the forward model + Poisson on whatever object is staged.              */
+int lsted_deconv_upload_object(lsted_deconv* h, const double* object);
+int lsted_deconv_simulate(lsted_deconv* h, double total_brightness, int rescale, uint64_t seed);
 /* iterate() n times (:520-531); no host transfers.                                 */
 int lsted_deconv_iterate(lsted_deconv* h, int n);
 /* attribute access; k is the PSF index for the per-PSF lists, else 0.

@@ -50,6 +50,9 @@ _DECONV_SIGNATURES = {
                                 ctypes.c_double],
     'lsted_deconv_create_data': [ctypes.c_void_p, c_double_p, ctypes.c_double,
                                  ctypes.c_int, ctypes.c_uint64],
+    'lsted_deconv_upload_object': [ctypes.c_void_p, c_double_p],
+    'lsted_deconv_simulate': [ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
+                              ctypes.c_uint64],
     'lsted_deconv_iterate': [ctypes.c_void_p, ctypes.c_int],
     'lsted_deconv_get': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                          c_double_p],
@@ -182,6 +185,19 @@ class DeconvHandle:
                       float(total_brightness or 0.0), int(rescale),
                       ctypes.c_uint64(seed))
 
+    def upload_object(self, obj):
+        """Stage an object (async H2D when `obj` lives in pinned memory)."""
+        assert obj.dtype == np.float64 and obj.flags.c_contiguous
+        assert obj.size == self.Ny * self.Nx
+        self.lib.call('lsted_deconv_upload_object', self._h,
+                      obj.ctypes.data_as(c_double_p))
+
+    def simulate(self, total_brightness, seed):
+        rescale = total_brightness is not None
+        self.lib.call('lsted_deconv_simulate', self._h,
+                      float(total_brightness or 0.0), int(rescale),
+                      ctypes.c_uint64(seed))
+
     def iterate(self, n=1):
         self.lib.call('lsted_deconv_iterate', self._h, int(n))
 
@@ -232,3 +248,25 @@ class DeconvHandle:
         n = (ctypes.c_longlong * NUM_KERNEL_KINDS)()
         self.lib.call('lsted_deconv_profile', self._h, int(reset), ms, n)
         return {kind: (ms[i], n[i]) for i, kind in enumerate(KERNEL_KINDS)}
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over page-locked host memory (cudaHostAlloc); keep the
+    returned array alive while transfers are in flight."""
+    lib = get()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = ctypes.c_void_p()
+    lib.call('lsted_host_alloc', ctypes.byref(ptr), n)
+    buf = (ctypes.c_char * n).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _pinned_keepalive[arr.ctypes.data] = ptr
+    return arr
+
+
+def pinned_free(arr):
+    ptr = _pinned_keepalive.pop(arr.ctypes.data, None)
+    if ptr is not None:
+        get().cdll.lsted_host_free(ptr)
+
+
+_pinned_keepalive = {}

@@ -91,6 +91,11 @@ extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double
         else h->e64->exact_clip = value != 0;
         return LSTED_OK;
     }
+    if (!strcmp(name, "forget_normalization")) {
+        if (h->precision == 32) h->e32->forget_normalization();
+        else h->e64->forget_normalization();
+        return LSTED_OK;
+    }
     if (!strcmp(name, "profile")) { h->bk->set_profile(value != 0); return LSTED_OK; }
     return set_error(LSTED_ERR_ARG, std::string("unknown option ") + name);
 }
@@ -101,6 +106,23 @@ extern "C" int lsted_deconv_create_data(lsted_deconv* h, const double* object, d
     LSTED_TRY
     LSTED_ENGINE(h, create_data(object, total_brightness, rescale != 0, seed));
     h->bk->sync();
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_upload_object(lsted_deconv* h, const double* object) {
+    if (!h || !object) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    LSTED_ENGINE(h, upload_object(object));
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_simulate(lsted_deconv* h, double total_brightness, int rescale,
+                                     uint64_t seed) {
+    if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    LSTED_ENGINE(h, simulate(total_brightness, rescale != 0, seed));
     return LSTED_OK;
     LSTED_CATCH
 }

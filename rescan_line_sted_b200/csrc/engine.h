@@ -53,11 +53,12 @@ template <typename T, class BK> class DeconvEngine {
         noiseless = (T*)bk.alloc(sizeof(T) * npix * K);
         noisy = (T*)bk.alloc(sizeof(T) * npix * K);
         stage64 = (double*)bk.alloc(sizeof(double) * npix * K);
+        object64 = (double*)bk.alloc(sizeof(double) * npix);
         partial = (double*)bk.alloc(sizeof(double) * kReduceBlocks);
     }
     ~DeconvEngine() {
         void* all[] = {tw_x, tw_y, otf, spec1, specK, true_object, estimate, norm,
-                       scratch, noiseless, noisy, stage64, partial};
+                       scratch, noiseless, noisy, stage64, object64, partial};
         for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) bk.free(all[i]);
     }
 
@@ -116,16 +117,24 @@ template <typename T, class BK> class DeconvEngine {
     }
 
     // ---- Deconvolver methods ---------------------------------------------
-    void create_data(const double* obj_host, double total_brightness, bool rescale,
-                     unsigned long long seed) {
-        bk.upload(stage64, obj_host, sizeof(double) * npix);
+    void upload_object(const double* obj_host) {
+        bk.upload(object64, obj_host, sizeof(double) * npix);
+    }
+    // Forward model + shot noise from the object staged by upload_object().
+    void simulate(double total_brightness, bool rescale, unsigned long long seed) {
         double s = 1.0;
-        if (rescale) s = total_brightness / bk.sum(stage64, npix, partial);
-        bk.cast_in(true_object, stage64, npix, s);
+        if (rescale) s = total_brightness / bk.sum(object64, npix, partial);
+        bk.cast_in(true_object, object64, npix, s);
         op_H(true_object, noiseless, noisy, seed);
         iterations_done = 0;
         have_estimate = false;
     }
+    void create_data(const double* obj_host, double total_brightness, bool rescale,
+                     unsigned long long seed) {
+        upload_object(obj_host);
+        simulate(total_brightness, rescale, seed);
+    }
+    void forget_normalization() { have_norm = false; }
 
     void iterate(int n) {
         for (int it = 0; it < n; ++it) {
@@ -225,7 +234,7 @@ template <typename T, class BK> class DeconvEngine {
     size_t npix;
     cplx<T>*tw_x, *tw_y, *otf, *spec1, *specK;
     T *true_object, *estimate, *norm, *scratch, *noiseless, *noisy;
-    double *stage64, *partial;
+    double *stage64, *object64, *partial;
 
     RowArgs<T> row_args(const ConvGeom& gg) {
         RowArgs<T> a;

@@ -1,0 +1,106 @@
+"""Parity of the CUDA PSF synthesis (K1/K2 kernels) with the oracle and the
+reference's golden vectors: arrays rel-L2 <= 1e-12 (fp64 kernels), doses and
+emissions rel <= 1e-12, fitted resolution factors rel <= 1e-6, integer grid
+sizes and rescan ratios exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import line_sted_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    den = np.linalg.norm(np.ravel(b))
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / (den if den > 0 else 1.0)
+
+
+@pytest.fixture(scope='module')
+def st():
+    from rescan_line_sted_b200 import line_sted_tools
+    return line_sted_tools
+
+
+def check_report(rep, gold_scalars, gold_arrays):
+    for k in ('excitation_dose', 'depletion_dose', 'expected_emission'):
+        assert rep[k] == pytest.approx(gold_scalars[k], rel=1e-12), k
+    for k in ('resolution_improvement_descanned', 'resolution_improvement_rescanned'):
+        if k in gold_scalars:
+            assert rep[k] == pytest.approx(gold_scalars[k], rel=1e-6), k
+    assert set(rep['psfs']) == set(gold_arrays)
+    for k, v in rep['psfs'].items():
+        assert v.shape == gold_arrays[k].shape and v.dtype == np.float64
+        assert rel_l2(v, gold_arrays[k]) < 1e-12, k
+
+
+def test_psf_report_golden(st, golden_dir):
+    with open(os.path.join(golden_dir, 'scalars.json')) as f:
+        scalars = json.load(f)
+    store = np.load(os.path.join(golden_dir, 'psf_reports.npz'))
+    for name, g in scalars['psf_report'].items():
+        rep = st.psf_report(*g['args'], verbose=False)
+        arrays = {k.split('/', 1)[1]: store[k] for k in store.files
+                  if k.startswith(name + '/')}
+        check_report(rep, g, arrays)
+    pub = scalars['published']['point_1_9_8_1']
+    rep = st.psf_report('point', 1, 9, 8, 1, verbose=False)
+    assert round(rep['excitation_dose'], 2) == pub['excitation_dose']
+    assert round(rep['depletion_dose'], 2) == pub['depletion_dose']
+    assert round(rep['expected_emission'], 2) == pub['expected_emission']
+
+
+@pytest.mark.parametrize('args', [('line', 0.05, 27, 8, 3), ('point', 4, 54, 6, 2),
+                                  ('line', 2, 0, 8, 1), ('line', 0.25, 108, 10, 1),
+                                  ('point', 8, 81, 12, 1), ('line', 0.5, 9, 25, 5)])
+def test_psf_report_vs_oracle(st, args):
+    rep = st.psf_report(*args, verbose=False)
+    ora = orc.psf_report(*args, use_closed_form=True)
+    ora.pop('_line_rescan_ratio', None)
+    check_report(rep, ora, ora['psfs'])
+
+
+def test_sweep_batch_equals_single_calls(st):
+    exc = [0.05, 0.1, 0.25, 0.5, 1, 2, 4, 8]
+    dep = [0, 1, 3, 9, 27, 54, 81, 108]
+    E, D = np.meshgrid(exc, dep, indexing='ij')
+    reps = st.psf_report_batch('line', E.ravel(), D.ravel(), 8, 1)
+    assert len(reps) == 64
+    for i in (0, 9, 37, 63):
+        one = st.psf_report('line', E.ravel()[i], D.ravel()[i], 8, 1, verbose=False)
+        for k, v in one['psfs'].items():
+            assert np.array_equal(v, reps[i]['psfs'][k]), k
+        assert one['expected_emission'] == reps[i]['expected_emission']
+
+
+def test_tune_psf_golden(st, golden_dir):
+    with open(os.path.join(golden_dir, 'scalars.json')) as f:
+        scalars = json.load(f)
+    for name in ('point_R2_E4', 'line_rescanned_R2p2_E3'):
+        g = scalars['tune_psf'][name]
+        res = st.tune_psf(**g['kwargs'])
+        for k, v in g.items():
+            if k == 'kwargs':
+                continue
+            assert res[k] == pytest.approx(v, rel=1e-5), (name, k)
+        assert 'psfs' in res and res['verbose'] is False
+    row = scalars['published']['fig2_point_rows']['2.0']
+    res = st.tune_psf(**scalars['tune_psf']['point_R2_E4']['kwargs'])
+    assert round(res['excitation_dose'], 1) == row[0]
+    assert round(res['depletion_dose'], 1) == row[1]
+
+
+def test_output_dir_tifs(st, tmp_path):
+    from rescan_line_sted_b200 import np_tif
+    out = str(tmp_path / 'psfs')
+    rep = st.psf_report('line', 1, 9, 8, 1, verbose=False, output_dir=out)
+    names = sorted(os.listdir(out))
+    assert 'sted_psf_line_rescan_unscaled.tif' in names and len(names) == 9
+    back = np_tif.tif_to_array(os.path.join(out, 'sted_psf_line_rescan.tif'))
+    assert np.allclose(back, rep['psfs']['rescan_sted'].astype(np.float32))
+    wide = np_tif.tif_to_array(os.path.join(out, 'sted_psf_line_rescan_unscaled.tif'))
+    ora = orc.psf_report('line', 1, 9, 8, 1)
+    ratio = ora['_line_rescan_ratio']
+    assert wide.shape == (1, 35, 35 * ratio)
