@@ -1,0 +1,152 @@
+"""CPU replay (tests/host_emul) of the very kernel bodies the sm_100a build
+launches: FFT passes, row/column convolution passes, fused RL iteration,
+PSF synthesis, Poisson sampler -- checked against numpy, the oracle and the
+reference's golden vectors.  Test infrastructure only; see emul.cpp."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+import emul_support
+from oracle import line_sted_oracle as orc
+from rescan_line_sted_b200 import _lib
+
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+def rel_l2(a, b):
+    den = np.linalg.norm(np.ravel(b))
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / (den if den > 0 else 1.0)
+
+
+@pytest.fixture(scope='module')
+def lib():
+    return emul_support.emulator_library()
+
+
+def emul_fft(lib, x, direction, precision):
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    out = np.empty_like(x)
+    assert lib.cdll.emul_fft(x.shape[1], direction, x.shape[0], precision,
+                             x.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+    return out
+
+
+@pytest.mark.parametrize('L', [8, 9, 10, 12, 15, 16, 18, 20, 24, 25, 27, 30, 36,
+                               45, 48, 60, 64, 75, 80, 81, 96, 100, 120, 125, 128,
+                               135, 144, 150, 160, 180, 192, 200, 216, 225, 240,
+                               243, 250, 256, 270, 288, 300, 320, 360, 375, 384,
+                               400, 405, 432, 450, 480, 486, 500, 512, 540, 576,
+                               600, 625, 640, 648, 675, 720, 729, 750, 768, 800,
+                               810, 864, 900, 960, 972, 1000, 1024, 1080, 2160])
+def test_stockham_fft_matches_numpy(lib, L):
+    rng = np.random.default_rng(L)
+    x = rng.standard_normal((2, L)) + 1j * rng.standard_normal((2, L))
+    ref = np.fft.fft(x, axis=1)
+    assert np.abs(emul_fft(lib, x, -1, 64) - ref).max() < 1e-13 * np.abs(ref).max() * np.log2(L)
+    assert np.abs(emul_fft(lib, x, -1, 32) - ref).max() < 3e-7 * np.abs(ref).max() * np.log2(L)
+    inv = np.fft.ifft(x, axis=1) * L
+    assert np.abs(emul_fft(lib, x, +1, 64) - inv).max() < 1e-13 * np.abs(inv).max() * np.log2(L)
+
+
+def test_fft_length_planner(lib):
+    for n, want in ((1, 8), (181, 192), (213, 216), (2101, 2160), (8245, 8640),
+                    (1025, 1080), (4097, 4320)):
+        assert lib.cdll.emul_next_smooth_len(n) == want
+    rad = (ctypes.c_int * 12)()
+    for L in (2160, 8640, 192, 8):
+        n = lib.cdll.emul_fft_plan(L, rad, 12)
+        assert n > 0 and int(np.prod(rad[:n])) == L
+    assert lib.cdll.emul_fft_plan(14, rad, 12) == -1     # 7 is not a supported radix
+
+
+@pytest.mark.parametrize('precision,tol', [(64, 1e-12), (32, 1e-5)])
+def test_engine_matches_reference_golden(lib, golden_dir, precision, tol):
+    g = np.load(os.path.join(golden_dir, 'fig2_2p0x_lr.npz'))
+    h = _lib.DeconvHandle(lib, g['psfs'], (128, 128), precision=precision)
+    h.create_data(g['object_u8'].astype(np.float64), 5e10, 0)
+    nl = np.concatenate([h.get(_lib.NOISELESS, k) for k in range(4)])
+    assert rel_l2(nl, g['noiseless']) < tol
+    for k in range(4):
+        h.set(_lib.NOISY, k, g['noisy'][k])
+    h.iterate(1)
+    assert rel_l2(h.get(_lib.ESTIMATE), g['estimate_1']) < tol
+    assert rel_l2(h.get(_lib.NORMALIZATION), g['H_t_normalization']) < tol
+    h.iterate(7)
+    assert rel_l2(h.get(_lib.ESTIMATE), g['estimate_8']) < 10 * tol
+    assert h.info().iterations_done == 8
+    # clip-per-term variant (reference order of operations)
+    h.set_option('exact_clip', 1)
+    h.create_data(g['object_u8'].astype(np.float64), 5e10, 0)
+    for k in range(4):
+        h.set(_lib.NOISY, k, g['noisy'][k])
+    h.iterate(8)
+    assert rel_l2(h.get(_lib.ESTIMATE), g['estimate_8']) < 10 * tol
+    h.close()
+
+
+@pytest.mark.parametrize('shape,pshape', [((33, 40), (9, 9)), ((7, 300), (11, 5)),
+                                          ((50, 31), (8, 6)), ((1, 64), (1, 9)),
+                                          ((5, 9), (11, 11)), ((2, 2), (1, 1))])
+def test_H_Ht_ragged_shapes(lib, shape, pshape):
+    rng = np.random.default_rng(3)
+    psfs = rng.random((3,) + pshape)
+    h = _lib.DeconvHandle(lib, psfs, shape, precision=64)
+    o = orc.Deconvolver([p[None] for p in psfs])
+    x = rng.random((1,) + shape)
+    assert rel_l2(h.H(x), np.concatenate(o.H(x))) < 1e-12
+    y = rng.random((3,) + shape)
+    ylist = [v[None] for v in y]
+    assert rel_l2(h.Ht(y, False), o.H_t(ylist, normalize=False)) < 1e-12
+    assert rel_l2(h.Ht(y, True), o.H_t(ylist)) < 1e-12
+    h.close()
+
+
+def test_error_paths(lib):
+    with pytest.raises(RuntimeError, match='precision'):
+        _lib.DeconvHandle(lib, np.ones((1, 3, 3)), (8, 8), precision=16)
+    h = _lib.DeconvHandle(lib, np.ones((1, 3, 3)), (8, 8), precision=64)
+    with pytest.raises(RuntimeError, match='selector'):
+        h.get(_lib.NOISY, 5)
+    with pytest.raises(RuntimeError, match='unknown option'):
+        h.set_option('nope', 1)
+    h.close()
+
+
+def poisson(lib, lam, n, seed=1, first=0):
+    out = np.empty(n)
+    lib.cdll.emul_poisson.argtypes = [ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64,
+                                      ctypes.c_int, dp]
+    lib.cdll.emul_poisson(lam, seed, first, n, out.ctypes.data_as(dp))
+    return out
+
+
+@pytest.mark.parametrize('lam', [0.1, 1.0, 5.0, 9.9, 10.0, 30.0])
+def test_poisson_small_lambda_pmf(lib, lam):
+    """Chi-square of the sampled histogram against the exact Poisson pmf."""
+    from scipy.stats import poisson as sp_poisson, chi2
+    n = 200000
+    x = poisson(lib, lam, n)
+    assert np.all(x == np.round(x)) and x.min() >= 0
+    kmax = int(sp_poisson.ppf(1 - 1e-5, lam)) + 1
+    obs = np.bincount(x.astype(int), minlength=kmax + 1)
+    obs = np.append(obs[:kmax], obs[kmax:].sum())
+    exp = np.append(sp_poisson.pmf(np.arange(kmax), lam), sp_poisson.sf(kmax - 1, lam)) * n
+    keep = exp > 5
+    stat = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    assert stat < chi2.ppf(1 - 1e-6, keep.sum() - 1)
+
+
+@pytest.mark.parametrize('lam', [100.0, 1e4, 1.8e7])
+def test_poisson_large_lambda_moments(lib, lam):
+    n = 100000
+    x = poisson(lib, lam, n, seed=3)
+    assert abs(x.mean() - lam) < 5 * np.sqrt(lam / n)
+    assert abs(x.var() / lam - 1) < 5 * np.sqrt(2.0 / n)
+    z = (x - lam) / np.sqrt(lam)
+    assert abs((z ** 3).mean() - 1 / np.sqrt(lam)) < 0.05      # skewness
+    assert poisson(lib, 0.0, 10).max() == 0
+    a, b = poisson(lib, lam, 100, seed=3), poisson(lib, lam, 100, seed=4)
+    assert np.array_equal(a, x[:100]) and not np.array_equal(a, b)
