@@ -86,7 +86,9 @@ int lsted_deconv_destroy(lsted_deconv* h);
 int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info);
 /* options: "exact_clip" (0|1: clip every H_t term before the sum, like :587),
  *          "profile" (0|1: per-kernel CUDA-event timing),
- *          "forget_normalization" (drop the cached H_t_normalization, :590)        */
+ *          "forget_normalization" (drop the cached H_t_normalization, :590),
+ *          "fast_path" (0|1, default 1: use the compile-time-planned kernels when
+ *          the transform length has one; 0 forces the generic mixed-radix kernels) */
 int lsted_deconv_set_option(lsted_deconv* h, const char* name, double value);
 /* create_data_from_object (:496-512).  rescale != 0 applies total_brightness.
  * Noise: in-kernel Philox4x32-10 Poisson, stream selected by `seed`.               */

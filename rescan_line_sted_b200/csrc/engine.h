@@ -33,7 +33,7 @@ template <typename T, class BK> class DeconvEngine {
     DeconvEngine(BK& backend, int K_, int ny_, int nx_, int Ny, int Nx)
         : K(K_), ny(ny_), nx(nx_), iterations_done(0), have_norm(false), have_estimate(false),
           exact_clip(false), bk(backend) {
-        const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g);
+        const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g, &BK::fast_cols);
         if (why[0]) throw std::string(why);
         npix = (size_t)Ny * Nx;
         std::vector<cplx<T> > tw;

@@ -1,0 +1,130 @@
+// Compile-time three-pass Stockham FFT with register-resident butterflies.
+//
+// L = RA*RB*RC.  NT threads cooperate on one sequence; thread t owns the
+// butterflies j = t + m*NT of every pass and keeps their operands in
+// registers, so a transform costs two shared-memory exchanges (after pass A
+// and after pass B) instead of one round trip per pass plus staging:
+//
+//   pass A: in  logical  j + q*NA          (caller fills registers: straight
+//           out position q*PA + j           from global memory, coalesced)
+//   pass B: in  position (j%RA)*PA + j/RA + q*RC,  twiddle w^(RC*(j%RA)*q)
+//           out position q*PB + j
+//   pass C: in  position (j/RA)*PB + q*RA + j%RA,  twiddle w^(q*j)
+//           out logical  j + q*NC           (stays in registers, natural order)
+//
+// The "[q][j]" exchange layouts make every shared-memory store unit-stride
+// and, with PA odd and PB = 0 (mod 16), the loads conflict-free for RA = 16
+// (odd pitches and at most 2-way conflicts otherwise).
+// The inverse transform uses the reversed radix order, so the registers a
+// forward pass C leaves (logical j + q*NC) are exactly the operands inverse
+// pass A wants: pointwise products with an OTF happen in registers.
+#pragma once
+#include "fft_core.cuh"
+
+namespace lsted {
+
+// Good-Thomas 15-point DFT (3 x 5, no twiddles): n = 5*n1 + 3*n2,
+// k = 10*k1 + 6*k2 (mod 15).
+template <int DIR, typename T> struct Dft<15, DIR, T> {
+    static LSTED_HD void run(cplx<T>* v) {
+        cplx<T> y[5][3];
+        LSTED_UNROLL
+        for (int n2 = 0; n2 < 5; ++n2) {
+            LSTED_UNROLL
+            for (int n1 = 0; n1 < 3; ++n1) y[n2][n1] = v[(5 * n1 + 3 * n2) % 15];
+            Dft<3, DIR, T>::run(y[n2]);
+        }
+        LSTED_UNROLL
+        for (int k1 = 0; k1 < 3; ++k1) {
+            cplx<T> z[5];
+            LSTED_UNROLL
+            for (int n2 = 0; n2 < 5; ++n2) z[n2] = y[n2][k1];
+            Dft<5, DIR, T>::run(z);
+            LSTED_UNROLL
+            for (int k2 = 0; k2 < 5; ++k2) v[(10 * k1 + 6 * k2) % 15] = z[k2];
+        }
+    }
+};
+
+constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+constexpr int imax(int a, int b) { return a > b ? a : b; }
+// smallest p >= n with p % 16 == r % 16
+constexpr int pitch_congruent(int n, int r) {
+    int p = n;
+    while ((p - r) % 16 != 0) ++p;
+    return p;
+}
+
+template <typename T, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3 {
+    enum {
+        RA = RA_, RB = RB_, RC = RC_, NT = NT_,
+        L = RA * RB * RC,
+        NA = RB * RC, NB = RA * RC, NC = RA * RB,   // butterflies per pass
+        MA = ceil_div(NA, NT), MB = ceil_div(NB, NT), MC = ceil_div(NC, NT),
+        PA = (NA % 2) ? NA : NA + 1,
+        PB = (RA % 16 == 0) ? pitch_congruent(NB, 0) : ((NB % 2) ? NB : NB + 1),
+        SEQ = imax(imax(RA * PA, RB * PB), L),      // shared elements per sequence
+        VREG = imax(imax(MA * RA, MB * RB), MC * RC)
+    };
+
+    // Pass A on registers v[m*RA + q] = x[j + q*NA], j = t + m*NT.
+    static LSTED_HD void pass_a(cplx<T>* v, int t, cplx<T>* sm) {
+        LSTED_UNROLL
+        for (int m = 0; m < MA; ++m) {
+            const int j = t + m * NT;
+            if (j < NA) {
+                Dft<RA, DIR, T>::run(v + m * RA);
+                LSTED_UNROLL
+                for (int q = 0; q < RA; ++q) sm[q * PA + j] = v[m * RA + q];
+            }
+        }
+    }
+    static LSTED_HD void load_b(cplx<T>* v, int t, const cplx<T>* sm, const cplx<T>* tw) {
+        LSTED_UNROLL
+        for (int m = 0; m < MB; ++m) {
+            const int j = t + m * NT;
+            if (j < NB) {
+                const int k = j % RA;
+                const int pos = k * PA + j / RA;
+                const int step = RC * k;
+                LSTED_UNROLL
+                for (int q = 0; q < RB; ++q) {
+                    cplx<T> x = sm[pos + q * RC];
+                    if (q > 0) x = mul_tw<DIR>(x, tw[q * step]);
+                    v[m * RB + q] = x;
+                }
+            }
+        }
+    }
+    static LSTED_HD void pass_b(cplx<T>* v, int t, cplx<T>* sm) {
+        LSTED_UNROLL
+        for (int m = 0; m < MB; ++m) {
+            const int j = t + m * NT;
+            if (j < NB) {
+                Dft<RB, DIR, T>::run(v + m * RB);
+                LSTED_UNROLL
+                for (int q = 0; q < RB; ++q) sm[q * PB + j] = v[m * RB + q];
+            }
+        }
+    }
+    // Loads pass-C operands, applies twiddles and the butterflies; on return
+    // v[m*RC + q] = X[j + q*NC].
+    static LSTED_HD void pass_c(cplx<T>* v, int t, const cplx<T>* sm, const cplx<T>* tw) {
+        LSTED_UNROLL
+        for (int m = 0; m < MC; ++m) {
+            const int j = t + m * NT;
+            if (j < NC) {
+                const int pos = (j / RA) * PB + (j % RA);
+                LSTED_UNROLL
+                for (int q = 0; q < RC; ++q) {
+                    cplx<T> x = sm[pos + q * RA];
+                    if (q > 0) x = mul_tw<DIR>(x, tw[q * j]);
+                    v[m * RC + q] = x;
+                }
+                Dft<RC, DIR, T>::run(v + m * RC);
+            }
+        }
+    }
+};
+
+}  // namespace lsted

@@ -12,6 +12,7 @@
 
 #include "../../include/lsted.h"
 #include "engine.h"
+#include "conv_fast.cuh"
 #include "ew_bodies.cuh"
 #include "psf_kernels.cuh"
 
@@ -41,7 +42,36 @@ struct DeviceCtx {
         for (int w = threadIdx.x; w < n; w += blockDim.x) f(w);
         __syncthreads();
     }
+    // one per-thread phase of a register-resident body, then a CTA barrier
+    template <class R, class F> __device__ __forceinline__ void phase(R* regs, F f) {
+        f((int)threadIdx.x, *regs);
+        __syncthreads();
+    }
 };
+
+// Compile-time plans of the fast path (conv_fast.cuh): 2160 = 16 * 9 * 15.
+typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 2> Plan2160f;
+typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
+
+template <int MODE, class P>
+__global__ void __launch_bounds__(P::ROW_THREADS)
+row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DeviceCtx cx;
+    lsted::RowRegs<P> r;
+    lsted::row_fast_body<MODE, P>(cx, blockIdx.x, a,
+                                  reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
+}
+
+template <int MODE, class P>
+__global__ void __launch_bounds__(P::COL_THREADS)
+col_fast_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DeviceCtx cx;
+    lsted::ColRegs<P> r;
+    lsted::col_fast_body<MODE, P>(cx, blockIdx.x, a,
+                                  reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
+}
 
 enum { kRowThreads = 256, kColThreads32 = 512, kColThreads64 = 256, kEwThreads = 256 };
 
@@ -104,7 +134,7 @@ enum KernelKind { KK_ROW_FWD = 0, KK_ROW_INV_STORE, KK_ROW_INV_SIM, KK_ROW_MID, 
 class CudaBackend {
   public:
     explicit CudaBackend(int device) : device_(device), stream_(0), bytes_(0), profile_(false),
-                                       t0_(0), t1_(0), num_sms_(148) {
+                                       use_fast_(true), t0_(0), t1_(0), num_sms_(148) {
         int count = 0;
         CUDA_CHECK(cudaGetDeviceCount(&count));
         if (device < 0 || device >= count) {
@@ -158,6 +188,7 @@ class CudaBackend {
         return ms;
     }
     void set_profile(bool on) { profile_ = on; }
+    void set_fast_path(bool on) { use_fast_ = on; }
     void profile_reset() {
         profile_drain();
         memset(prof_ms_, 0, sizeof(prof_ms_));
@@ -172,6 +203,64 @@ class CudaBackend {
     }
 
     // ---- launches ----
+    // ---- fast path (compile-time plans) ----
+    static int fast_cols(int L, int cplx_bytes) {
+        if (L == Plan2160f::L) return cplx_bytes == 8 ? (int)Plan2160f::C : (int)Plan2160d::C;
+        return 0;
+    }
+    template <class P> static bool plan_fits_rows(const lsted::ConvGeom& g) {
+        return g.Lx == P::L && g.C == P::C && g.PR == P::PR;
+    }
+    template <class P> static bool plan_fits_cols(const lsted::ConvGeom& g) {
+        return g.Ly == P::L && g.C == P::C;
+    }
+    template <int MODE, class P> void launch_row_fast(int grid, const lsted::RowArgs<typename P::T>& a,
+                                                      int kind) {
+        const size_t smem = lsted::fast_row_smem_bytes<P>();
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        before(kind);
+        row_fast_kernel<MODE, P><<<grid, P::ROW_THREADS, smem, stream_>>>(a);
+        after();
+    }
+    template <int MODE, class P> void launch_col_fast(int grid, const lsted::ColArgs<typename P::T>& a,
+                                                      int kind) {
+        const size_t smem = lsted::fast_col_smem_bytes<P>();
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        before(kind);
+        col_fast_kernel<MODE, P><<<grid, P::COL_THREADS, smem, stream_>>>(a);
+        after();
+    }
+    template <int MODE> bool try_fast_row(int grid, const lsted::RowArgs<float>& a, int kind) {
+        if (!plan_fits_rows<Plan2160f>(a.g)) return false;
+        launch_row_fast<MODE, Plan2160f>(grid, a, kind);
+        return true;
+    }
+    template <int MODE> bool try_fast_row(int grid, const lsted::RowArgs<double>& a, int kind) {
+        if (!plan_fits_rows<Plan2160d>(a.g)) return false;
+        launch_row_fast<MODE, Plan2160d>(grid, a, kind);
+        return true;
+    }
+    template <int MODE> bool try_fast_col(int grid, const lsted::ColArgs<float>& a, int kind) {
+        if (MODE == lsted::COL_OTF || !plan_fits_cols<Plan2160f>(a.g)) return false;
+        launch_col_fast<MODE == lsted::COL_OTF ? lsted::COL_H : MODE, Plan2160f>(grid, a, kind);
+        return true;
+    }
+    template <int MODE> bool try_fast_col(int grid, const lsted::ColArgs<double>& a, int kind) {
+        if (MODE == lsted::COL_OTF || !plan_fits_cols<Plan2160d>(a.g)) return false;
+        launch_col_fast<MODE == lsted::COL_OTF ? lsted::COL_H : MODE, Plan2160d>(grid, a, kind);
+        return true;
+    }
+
     template <int MODE, typename T> void launch_row(int grid, const lsted::RowArgs<T>& a) {
         if (grid <= 0) return;
         const size_t smem = lsted::row_smem_bytes(a.g, (int)sizeof(lsted::cplx<T>));
@@ -185,13 +274,20 @@ class CudaBackend {
                        : MODE == lsted::ROW_INV_STORE ? KK_ROW_INV_STORE
                        : MODE == lsted::ROW_INV_SIM ? KK_ROW_INV_SIM
                        : MODE == lsted::ROW_MID ? KK_ROW_MID : KK_ROW_FINAL;
+        if (use_fast_ && try_fast_row<MODE>(grid, a, kind)) return;
         before(kind);
         row_kernel<MODE, T><<<grid, kRowThreads, smem, stream_>>>(a);
         after();
     }
     template <int MODE, typename T> void launch_col(int grid, const lsted::ColArgs<T>& a) {
         if (grid <= 0) return;
-        const size_t smem = lsted::col_smem_bytes(a.g, (int)sizeof(lsted::cplx<T>));
+        const size_t smem = lsted::col_smem_bytes(a.g, (int)sizeof(lsted::cplx<T>),
+                                                  MODE == lsted::COL_OTF ? 2 : 3);
+        if (smem > lsted::kSmemLimit) {
+            lsted::ApiError e; e.code = LSTED_ERR_ARG;
+            e.msg = "generic column kernel does not fit in shared memory for this geometry";
+            throw e;
+        }
         static size_t configured = 0;
         if (smem > configured) {
             CUDA_CHECK(cudaFuncSetAttribute(col_kernel<MODE, T>,
@@ -200,6 +296,7 @@ class CudaBackend {
         }
         const int kind = MODE == lsted::COL_OTF ? KK_COL_OTF : MODE == lsted::COL_H ? KK_COL_H : KK_COL_HT;
         const int threads = sizeof(T) == 4 ? kColThreads32 : kColThreads64;
+        if (use_fast_ && try_fast_col<MODE>(grid, a, kind)) return;
         before(kind);
         col_kernel<MODE, T><<<grid, threads, smem, stream_>>>(a);
         after();
@@ -248,7 +345,7 @@ class CudaBackend {
     int device_;
     cudaStream_t stream_;
     size_t bytes_;
-    bool profile_;
+    bool profile_, use_fast_;
     cudaEvent_t t0_, t1_;
     int num_sms_;
     std::vector<cudaEvent_t> ev_pool_;

@@ -65,7 +65,11 @@ inline int smem_pitch(int L, int elem_bytes, int C) {
 
 // Geometry for an Ny x Nx image and ny x nx PSFs.  `cplx_bytes` = 8 (fp32)
 // or 16 (fp64).  Returns an empty string on success, else the reason.
-inline const char* make_geom(int Ny, int Nx, int ny, int nx, int cplx_bytes, ConvGeom* g) {
+// `fast_C(L)` > 0 means the backend has a compile-time plan for column length L
+// that wants C columns per block (it then needs only the generic OTF kernel to
+// fit: two buffers instead of three).
+inline const char* make_geom(int Ny, int Nx, int ny, int nx, int cplx_bytes, ConvGeom* g,
+                             int (*fast_C)(int L, int cplx_bytes) = 0) {
     memset(g, 0, sizeof(*g));
     if (Ny < 1 || Nx < 1 || ny < 1 || nx < 1) return "empty image or PSF";
     g->Ny = Ny; g->Nx = Nx;
@@ -79,10 +83,16 @@ inline const char* make_geom(int Ny, int Nx, int ny, int nx, int cplx_bytes, Con
     if (!make_fft_plan(g->Ly, &g->py) || !make_fft_plan(g->Lx, &g->px)) return "no FFT plan";
     g->Lxh = g->Lx / 2 + 1;
     g->C = cplx_bytes == 8 ? 4 : 2;
-    for (;; g->C /= 2) {
+    const int want = fast_C ? fast_C(g->Ly, cplx_bytes) : 0;
+    if (want > 0 && (size_t)2 * want * smem_pitch(g->Ly, cplx_bytes, want) * cplx_bytes <= kSmemLimit) {
+        g->C = want;
         g->Lpy = smem_pitch(g->Ly, cplx_bytes, g->C);
-        if ((size_t)3 * g->C * g->Lpy * cplx_bytes <= kSmemLimit) break;
-        if (g->C == 1) return "column transform does not fit in shared memory; tile the object";
+    } else {
+        for (;; g->C /= 2) {
+            g->Lpy = smem_pitch(g->Ly, cplx_bytes, g->C);
+            if ((size_t)3 * g->C * g->Lpy * cplx_bytes <= kSmemLimit) break;
+            if (g->C == 1) return "column transform does not fit in shared memory; tile the object";
+        }
     }
     g->nxb = (g->Lxh + g->C - 1) / g->C;
     g->PR = 2;
@@ -99,8 +109,8 @@ inline int row_blocks(const ConvGeom& g) { return (((g.Ny + 1) / 2) + g.PR - 1) 
 inline size_t row_smem_bytes(const ConvGeom& g, int cplx_bytes) {
     return (size_t)2 * g.PR * g.Lpx * cplx_bytes;
 }
-inline size_t col_smem_bytes(const ConvGeom& g, int cplx_bytes) {
-    return (size_t)3 * g.C * g.Lpy * cplx_bytes;
+inline size_t col_smem_bytes(const ConvGeom& g, int cplx_bytes, int nbuf = 3) {
+    return (size_t)nbuf * g.C * g.Lpy * cplx_bytes;
 }
 
 }  // namespace lsted

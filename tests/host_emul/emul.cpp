@@ -14,6 +14,7 @@
 #include <vector>
 #include "../../include/lsted.h"
 #include "../../rescan_line_sted_b200/csrc/engine.h"
+#include "../../rescan_line_sted_b200/csrc/conv_fast.cuh"
 #include "../../rescan_line_sted_b200/csrc/ew_bodies.cuh"
 #include "../../rescan_line_sted_b200/csrc/psf_kernels.cuh"
 
@@ -26,12 +27,29 @@ static int set_error(int code, const std::string& msg) { g_error = msg; return c
 extern "C" const char* lsted_last_error(void) { return g_error.c_str(); }
 
 struct HostCtx {
+    int nthreads;
+    HostCtx() : nthreads(1) {}
     template <class F> void parallel_for(int n, F f) { for (int w = 0; w < n; ++w) f(w); }
+    // register-resident bodies: every "thread" keeps its own Regs between phases
+    template <class R, class F> void phase(R* regs, F f) {
+        for (int t = 0; t < nthreads; ++t) f(t, regs[t]);
+    }
 };
+
+typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 2> Plan2160f;
+typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
+template <typename T> struct PlanFor;
+template <> struct PlanFor<float> { typedef Plan2160f type; };
+template <> struct PlanFor<double> { typedef Plan2160d type; };
 
 class HostBackend {
   public:
-    explicit HostBackend(int) : bytes_(0) {}
+    explicit HostBackend(int) : bytes_(0), use_fast_(true) {}
+    void set_fast_path(bool on) { use_fast_ = on; }
+    static int fast_cols(int L, int cplx_bytes) {
+        if (L == Plan2160f::L) return cplx_bytes == 8 ? (int)Plan2160f::C : (int)Plan2160d::C;
+        return 0;
+    }
     void activate() {}
     void sync() {}
     void* alloc(size_t bytes) { bytes_ += bytes; return malloc(bytes ? bytes : 1); }
@@ -48,6 +66,20 @@ class HostBackend {
     void profile_reset() {}
 
     template <int MODE, typename T> void launch_row(int grid, const lsted::RowArgs<T>& a) {
+        typedef typename PlanFor<T>::type P;
+        if (use_fast_ && a.g.Lx == P::L && a.g.C == P::C && a.g.PR == P::PR) {
+#pragma omp parallel
+            {
+                std::vector<lsted::cplx<T> > smem((size_t)P::PR * P::LSM_ROW);
+                std::vector<lsted::RowRegs<P> > regs(P::ROW_THREADS);
+                HostCtx cx;
+                cx.nthreads = P::ROW_THREADS;
+#pragma omp for schedule(dynamic)
+                for (int b = 0; b < grid; ++b)
+                    lsted::row_fast_body<MODE, P>(cx, b, a, smem.data(), regs.data());
+            }
+            return;
+        }
 #pragma omp parallel
         {
             std::vector<lsted::cplx<T> > smem((size_t)2 * a.g.PR * a.g.Lpx);
@@ -57,9 +89,24 @@ class HostBackend {
         }
     }
     template <int MODE, typename T> void launch_col(int grid, const lsted::ColArgs<T>& a) {
+        typedef typename PlanFor<T>::type P;
+        if (use_fast_ && MODE != lsted::COL_OTF && a.g.Ly == P::L && a.g.C == P::C) {
+#pragma omp parallel
+            {
+                std::vector<lsted::cplx<T> > smem((size_t)P::C * P::LSM_COL);
+                std::vector<lsted::ColRegs<P> > regs(P::COL_THREADS);
+                HostCtx cx;
+                cx.nthreads = P::COL_THREADS;
+#pragma omp for schedule(dynamic)
+                for (int b = 0; b < grid; ++b)
+                    lsted::col_fast_body<(MODE == lsted::COL_OTF ? lsted::COL_H : MODE), P>(
+                        cx, b, a, smem.data(), regs.data());
+            }
+            return;
+        }
 #pragma omp parallel
         {
-            std::vector<lsted::cplx<T> > smem((size_t)3 * a.g.C * a.g.Lpy);
+            std::vector<lsted::cplx<T> > smem((size_t)3 * a.g.C * a.g.Lpy);  // (no 227 KB limit here)
             HostCtx cx;
 #pragma omp for schedule(dynamic)
             for (int b = 0; b < grid; ++b) lsted::col_body<MODE, T>(cx, b, a, smem.data());
@@ -96,6 +143,7 @@ class HostBackend {
 
   private:
     size_t bytes_;
+    bool use_fast_;
 };
 
 #define LSTED_BACKEND HostBackend
