@@ -231,7 +231,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     typedef typename P::Fwd F;
     typedef typename P::Inv I;
     const ConvGeom& g = a.g;
-    const int Ny = g.Ny, Nx = g.Nx, Lx = g.Lx, Lxh = g.Lxh, C = g.C;
+    const int Ny = g.Ny, Nx = g.Nx;
+    const int Lx = P::L, Lxh = P::L / 2 + 1, C = P::C;  // == g.Lx, g.Lxh, g.C (checked at launch)
     const int Py = (Ny + 1) / 2;
     const int bpi = (Py + P::PR - 1) / P::PR;
     const int img = block / bpi;
@@ -316,6 +317,33 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             if (!live) return;
+            const bool two = y + 1 < Ny;
+            // Issue every global load of the pointwise step up front (they overlap
+            // pass C); divisions with their slow-path branches come afterwards.
+            cplx<T> pa[(MODE == ROW_MID || MODE == ROW_FINAL) ? I::MC * I::RC : 1];
+            cplx<T> pe[MODE == ROW_FINAL ? I::MC * I::RC : 1];
+            if (MODE == ROW_MID || MODE == ROW_FINAL) {
+                LSTED_UNROLL
+                for (int m = 0; m < I::MC; ++m) {
+                    const int j = t + m * P::NT;
+                    LSTED_UNROLL
+                    for (int q = 0; q < I::RC; ++q) {
+                        const int i = j + q * I::NC - shift;
+                        cplx<T> av = mk<T>(1, 1), ev = mk<T>(0, 0);
+                        if (j < I::NC && i >= 0 && i < Nx) {
+                            const size_t o = (size_t)y * Nx + i;
+                            av.x = aux[o];
+                            if (two) av.y = aux[o + Nx];
+                            if (MODE == ROW_FINAL) {
+                                ev.x = out[o];
+                                if (two) ev.y = out[o + Nx];
+                            }
+                        }
+                        pa[m * I::RC + q] = av;
+                        if (MODE == ROW_FINAL) pe[m * I::RC + q] = ev;
+                    }
+                }
+            }
             I::pass_c(r.v, t, sm, tw);
             LSTED_UNROLL
             for (int m = 0; m < I::MC; ++m) {
@@ -328,28 +356,23 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                         cplx<T> w = mk<T>(0, 0);
                         if (i >= 0 && i < Nx) {
                             const size_t o = (size_t)y * Nx + i;
-                            const bool two = y + 1 < Ny;
                             if (MODE == ROW_INV_STORE) {
                                 if (a.clip) { z.x = clip0(z.x); z.y = clip0(z.y); }
                                 out[o] = a.accumulate ? out[o] + z.x : z.x;
                                 if (two) out[o + Nx] = a.accumulate ? out[o + Nx] + z.y : z.y;
                             } else if (MODE == ROW_INV_SIM) {
-                                z.x = clip0(z.x); z.y = clip0(z.y);
-                                out[o] = z.x;
-                                out2[o] = (T)(poisson_sample((double)z.x, a.seed, o, a.img0 + img) + 1e-9);
-                                if (two) {
-                                    out[o + Nx] = z.y;
-                                    out2[o + Nx] = (T)(poisson_sample((double)z.y, a.seed, o + Nx,
-                                                                      a.img0 + img) + 1e-9);
-                                }
+                                out[o] = clip0(z.x);       // noisy image: second loop below
+                                if (two) out[o + Nx] = clip0(z.y);
                             } else if (MODE == ROW_MID) {
-                                w.x = aux[o] / clip0(z.x);
-                                if (two) w.y = aux[o + Nx] / clip0(z.y);
+                                const cplx<T> mv = pa[m * I::RC + q];
+                                w.x = fast_div(mv.x, clip0(z.x));
+                                if (two) w.y = fast_div(mv.y, clip0(z.y));
                             } else {  // ROW_FINAL
-                                w.x = out[o] * (clip0(z.x) / aux[o]);
+                                const cplx<T> nv = pa[m * I::RC + q], ev = pe[m * I::RC + q];
+                                w.x = ev.x * fast_div(clip0(z.x), nv.x);
                                 out[o] = w.x;
                                 if (two) {
-                                    w.y = out[o + Nx] * (clip0(z.y) / aux[o + Nx]);
+                                    w.y = ev.y * fast_div(clip0(z.y), nv.y);
                                     out[o + Nx] = w.y;
                                 }
                             }
@@ -359,6 +382,27 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 }
             }
         });
+        if (MODE == ROW_INV_SIM) {
+            // Shot noise.  A rolled loop over the pixels this thread just wrote (one
+            // copy of the sampler in the instruction stream, values re-read from L1/L2).
+            cx.phase(regs, [&](int tid, RowRegs<P>& r) {
+                LSTED_ROW_IDS
+                (void)r;
+                if (!live) return;
+                const int nr = (y + 1 < Ny) ? 2 : 1;
+                LSTED_NOUNROLL
+                for (int e = 0; e < I::MC * I::RC * 2; ++e) {
+                    const int rr = e & 1, mq = e >> 1;
+                    const int m = mq / I::RC, q = mq - m * I::RC;
+                    const int j = t + m * P::NT;
+                    const int i = j + q * I::NC - shift;
+                    if (j < I::NC && rr < nr && i >= 0 && i < Nx) {
+                        const size_t o = (size_t)(y + rr) * Nx + i;
+                        out2[o] = (T)(poisson_sample((double)out[o], a.seed, o, a.img0 + img) + 1e-9);
+                    }
+                }
+            });
+        }
         if (MODE == ROW_INV_STORE || MODE == ROW_INV_SIM) return;
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
@@ -411,7 +455,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 const cplx<T> z2 = sm[k == 0 ? 0 : Lx - k];
                 if (rr) o = mk<T>((T)0.5 * (z1.y + z2.y), (T)0.5 * (z2.x - z1.x));
                 else    o = mk<T>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y - z2.y));
-                if (shift) o = o * conj(tw[(int)(((long long)k * shift) % Lx)]);
+                if (shift) o = o * conj(tw[(k * shift) % Lx]);  // k*shift < L*L/2 fits an int
             }
             dst[((size_t)xb * Ny + y + rr) * C + c] = o;
         }

@@ -15,9 +15,11 @@
 #ifdef __CUDACC__
 #define LSTED_HD __host__ __device__ __forceinline__
 #define LSTED_UNROLL _Pragma("unroll")
+#define LSTED_NOUNROLL _Pragma("unroll 1")
 #else
 #define LSTED_HD inline
 #define LSTED_UNROLL
+#define LSTED_NOUNROLL
 #endif
 
 namespace lsted {
@@ -32,6 +34,16 @@ template <typename T> LSTED_HD cplx<T> operator*(cplx<T> a, cplx<T> b) {
 }
 template <typename T> LSTED_HD cplx<T> scale(cplx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
 template <typename T> LSTED_HD cplx<T> conj(cplx<T> a) { return mk<T>(a.x, -a.y); }
+// Branch-free fp32 division (MUFU.RCP based, <= 2 ulp) so the compiler can keep
+// many independent loads/divisions in flight; fp64 divides exactly.
+LSTED_HD float fast_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+LSTED_HD double fast_div(double a, double b) { return a / b; }
 // multiply by -i (DIR = -1, forward) or +i (DIR = +1, inverse)
 template <int DIR, typename T> LSTED_HD cplx<T> mul_dir_i(cplx<T> a) {
     return DIR < 0 ? mk<T>(a.y, -a.x) : mk<T>(-a.y, a.x);

@@ -263,6 +263,13 @@ class CudaBackend {
 
     template <int MODE, typename T> void launch_row(int grid, const lsted::RowArgs<T>& a) {
         if (grid <= 0) return;
+        {
+            const int kind0 = MODE == lsted::ROW_FWD ? KK_ROW_FWD
+                            : MODE == lsted::ROW_INV_STORE ? KK_ROW_INV_STORE
+                            : MODE == lsted::ROW_INV_SIM ? KK_ROW_INV_SIM
+                            : MODE == lsted::ROW_MID ? KK_ROW_MID : KK_ROW_FINAL;
+            if (use_fast_ && try_fast_row<MODE>(grid, a, kind0)) return;
+        }
         const size_t smem = lsted::row_smem_bytes(a.g, (int)sizeof(lsted::cplx<T>));
         static size_t configured = 0;  // per instantiation
         if (smem > configured) {
@@ -274,13 +281,16 @@ class CudaBackend {
                        : MODE == lsted::ROW_INV_STORE ? KK_ROW_INV_STORE
                        : MODE == lsted::ROW_INV_SIM ? KK_ROW_INV_SIM
                        : MODE == lsted::ROW_MID ? KK_ROW_MID : KK_ROW_FINAL;
-        if (use_fast_ && try_fast_row<MODE>(grid, a, kind)) return;
         before(kind);
         row_kernel<MODE, T><<<grid, kRowThreads, smem, stream_>>>(a);
         after();
     }
     template <int MODE, typename T> void launch_col(int grid, const lsted::ColArgs<T>& a) {
         if (grid <= 0) return;
+        {
+            const int kind0 = MODE == lsted::COL_OTF ? KK_COL_OTF : MODE == lsted::COL_H ? KK_COL_H : KK_COL_HT;
+            if (use_fast_ && try_fast_col<MODE>(grid, a, kind0)) return;
+        }
         const size_t smem = lsted::col_smem_bytes(a.g, (int)sizeof(lsted::cplx<T>),
                                                   MODE == lsted::COL_OTF ? 2 : 3);
         if (smem > lsted::kSmemLimit) {
@@ -296,7 +306,6 @@ class CudaBackend {
         }
         const int kind = MODE == lsted::COL_OTF ? KK_COL_OTF : MODE == lsted::COL_H ? KK_COL_H : KK_COL_HT;
         const int threads = sizeof(T) == 4 ? kColThreads32 : kColThreads64;
-        if (use_fast_ && try_fast_col<MODE>(grid, a, kind)) return;
         before(kind);
         col_kernel<MODE, T><<<grid, threads, smem, stream_>>>(a);
         after();
