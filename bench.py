@@ -84,53 +84,70 @@ def total_brightness(N):
 # Clock sampling during the timed region
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
-             'clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,'
-             'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled through NVML (same data as the
+    nvidia-smi clocks line of B200_PROFILING.md, without spawning a process
+    that stalls the driver) every 20 ms from a thread."""
+    REASONS = (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20),
+               ('hw_thermal_slowdown', 0x40), ('sw_power_cap', 0x4))
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.thread = device, [], None
+        self.running, self.error = False, None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            index = self.device
+            if visible:
+                ids = [v for v in visible.split(',') if v.strip()]
+                if all(v.strip().isdigit() for v in ids) and self.device < len(ids):
+                    index = int(ids[self.device])
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # noqa: BLE001
+            self.error = repr(exc)
+            return
+        self.running = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+    def _loop(self):
+        nv = self.nvml
+        while self.running:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:  # noqa: BLE001
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                except Exception:  # noqa: BLE001
+                    reasons = 0
+            self.rows.append((time.perf_counter(), float(mhz), int(reasons)))
+            time.sleep(0.02)
 
     def window(self, t0, t1):
         """Only samples taken inside [t0, t1] (the timed region) count."""
         self.t0, self.t1 = t0, t1
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        t0, t1 = getattr(self, 't0', None), getattr(self, 't1', None)
-        for stamp, r in self.rows:
-            if t0 is not None and not (t0 <= stamp <= t1 + 0.11):
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(names, r[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        if self.thread is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None,
+                    'reasons': ['NVML unavailable: %s' % self.error]}
+        self.running = False
+        self.thread.join(timeout=1.0)
+        rows = [r for r in self.rows
+                if self.t0 is None or self.t0 <= r[0] <= self.t1 + 0.03] or self.rows[-1:]
+        sm = [r[1] for r in rows]
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(n for n, b in self.REASONS if bits & b),
+                'samples': len(sm)}
 
 
 # ---------------------------------------------------------------------------

@@ -205,6 +205,7 @@ template <typename T> struct ColArgs {
     cplx<T>* dst;           // OTF: [K] XB(Ly); H: [K] XB(Ny); HT: XB(Ny)
     int K;
     int rows_in;            // valid input rows (zero padded up to Ly)
+    int src_same;           // HT: every k reads the same input spectrum (H_t of all-ones images)
     T scale;                // OTF: 1/(Lx*Ly)
 };
 
@@ -268,7 +269,7 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
     }
     // COL_HT: accumulate the products in the Fourier domain (b2).
     for (int k = 0; k < a.K; ++k) {
-        const cplx<T>* src = a.src + (size_t)k * img_ny + (size_t)xb * slab_ny;
+        const cplx<T>* src = a.src + (a.src_same ? 0 : (size_t)k * img_ny) + (size_t)xb * slab_ny;
         cx.parallel_for(C * Ly, [&](int w) {
             const int y = w / C, c = w - y * C;
             b0[c * Lp + pad<T>(y)] = (y < Ny) ? src[w] : mk<T>(0, 0);

@@ -3,15 +3,18 @@
 // geometry of BASELINE config 4).  Same operators, same HBM layout and same
 // argument structs as conv_bodies.cuh; what changes is the inside of a CTA:
 //
-//  * butterflies of all three passes live in registers (fft_static.cuh),
-//    two shared-memory exchanges per transform, no staging pass;
+//  * butterflies of all three passes live in registers (fft_static.cuh); a
+//    transform costs two shared-memory exchanges through two ping-pong
+//    buffers, i.e. two CTA barriers, and no staging pass;
 //  * operands of the first pass come straight from global memory (coalesced:
 //    consecutive threads own consecutive rows / pixels), results of the last
 //    pass go straight back;
 //  * the OTF product, the Fourier-domain sum over orientations, the 'same'
 //    crop, clip, RL ratio and RL update all happen on registers between an
-//    inverse and a forward transform (the crop offset becomes a phase ramp
-//    applied while the half spectra are split).
+//    inverse and a forward transform, inside one barrier-to-barrier phase
+//    (the crop offset becomes a phase ramp applied with the Hermitian split);
+//  * the Hermitian split of a packed row pair exchanges only the upper half
+//    of the spectrum with the "mirror" thread (NC - t).
 //
 // Bodies are written as per-thread phases separated by CTA barriers
 // (`cx.phase(regs, f)`), so tests/host_emul can replay them thread by thread.
@@ -28,18 +31,26 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
     enum {
         L = RA * RB * RC, NT = NT_, C = C_, PR = PR_,
         SEQ = imax(Fwd::SEQ, Inv::SEQ),
-        // column CTA: C interleaved sequences; the odd-ish offset spreads them over banks
+        // column CTA: C interleaved sequences; the small offset spreads them over banks
         LSM_COL = (SEQ + 15) / 16 * 16 + 16 / C_,
         COL_THREADS = NT_ * C_,
+        COL_SMEM_ELEMS = 2 * C_ * LSM_COL,          // two ping-pong buffers
         // row CTA: PR groups of NTG threads (whole warps), one row pair each
         NTG = (NT_ + 31) / 32 * 32,
         LSM_ROW = (SEQ + 15) / 16 * 16 + 8,
         ROW_THREADS = NTG * PR_,
+        ROW_SMEM_ELEMS = 2 * PR_ * LSM_ROW,
         VREG = imax(Fwd::VREG, Inv::VREG),
-        NKEEP = Fwd::MC * Fwd::RC
+        NKEEP = Fwd::MC * Fwd::RC,
+        // Hermitian split: thread t owns bins t + q*NC; its mirror bins live in thread NC - t
+        NC = Fwd::NC, RCF = RC, QH = (RC - 1) / 2, PX = Fwd::NC + 1
     };
     static_assert(Fwd::MC * Fwd::RC == Inv::MA * Inv::RA, "pass C / pass A operand sets must match");
     static_assert(Inv::MC * Inv::RC == Fwd::MA * Fwd::RA, "pass C / pass A operand sets must match");
+    static_assert(Fwd::MC == 1 && Fwd::NC == NT_, "row split assumes one pass-C butterfly per thread");
+    static_assert(Inv::MA == 1 && Inv::NA == NT_, "row unpack assumes one pass-A butterfly per thread");
+    static_assert(RC % 2 == 1, "row split assumes an odd last radix");
+    static_assert((RC - QH) * PX <= LSM_ROW, "mirror exchange must fit one row buffer");
 };
 
 template <class P> struct ColRegs {
@@ -51,10 +62,10 @@ template <class P> struct RowRegs {
 };
 
 template <class P> LSTED_HD size_t fast_col_smem_bytes() {
-    return sizeof(cplx<typename P::T>) * (size_t)P::C * P::LSM_COL;
+    return sizeof(cplx<typename P::T>) * (size_t)P::COL_SMEM_ELEMS;
 }
 template <class P> LSTED_HD size_t fast_row_smem_bytes() {
-    return sizeof(cplx<typename P::T>) * (size_t)P::PR * P::LSM_ROW;
+    return sizeof(cplx<typename P::T>) * (size_t)P::ROW_SMEM_ELEMS;
 }
 
 // ---------------------------------------------------------------------------
@@ -97,6 +108,29 @@ LSTED_HD void col_store_inv_c(const cplx<typename P::T>* v, int t, int c, cplx<t
     }
 }
 
+// v = keep (.) otf on the pass-C / pass-A operand set (rows j + q*NC of the OTF slab)
+template <class P, bool ACCUMULATE>
+LSTED_HD void col_otf_product(ColRegs<P>& r, int t, int c, const cplx<typename P::T>* otf, bool first) {
+    typedef typename P::Fwd F;
+    typedef typename P::T T;
+    LSTED_UNROLL
+    for (int m = 0; m < F::MC; ++m) {
+        const int j = t + m * P::NT;
+        if (j < F::NC) {
+            LSTED_UNROLL
+            for (int q = 0; q < F::RC; ++q) {
+                const cplx<T> o = otf[(size_t)(j + q * F::NC) * P::C + c];
+                if (ACCUMULATE) {
+                    const cplx<T> p = r.v[m * F::RC + q] * o;
+                    r.keep[m * F::RC + q] = first ? p : r.keep[m * F::RC + q] + p;
+                } else {
+                    r.v[m * F::RC + q] = r.keep[m * F::RC + q] * o;
+                }
+            }
+        }
+    }
+}
+
 template <int MODE, class P, class Ctx>
 LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                             cplx<typename P::T>* smem, ColRegs<P>* regs) {
@@ -104,121 +138,98 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     typedef typename P::Fwd F;
     typedef typename P::Inv I;
     const ConvGeom& g = a.g;
-    const int Ny = g.Ny, Ly = g.Ly;
+    const int Ny = g.Ny, Ly = P::L;  // == g.Ly (checked at launch)
     const int xb = block;
     const size_t slab_ly = (size_t)P::C * Ly, img_ly = (size_t)g.nxb * slab_ly;
     const size_t slab_ny = (size_t)P::C * Ny, img_ny = (size_t)g.nxb * slab_ny;
     const cplx<T>* tw = a.tw;
+    cplx<T>* const buf0 = smem;
+    cplx<T>* const buf1 = smem + (size_t)P::C * P::LSM_COL;
+    const int K = a.K;
+
+#define LSTED_COL_IDS                                          \
+    const int t = tid / P::C, c = tid - t * P::C;              \
+    cplx<T>* const s0 = buf0 + c * P::LSM_COL;                 \
+    cplx<T>* const s1 = buf1 + c * P::LSM_COL;
 
     if (MODE == COL_H) {
         const cplx<T>* src = a.src + (size_t)xb * slab_ny;
+        const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
+        cplx<T>* dst0 = a.dst + (size_t)xb * slab_ny;
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-            const int t = tid / P::C, c = tid - t * P::C;
+            LSTED_COL_IDS
             col_load_fwd_a<P>(r.v, t, c, src, Ny);
-            F::pass_a(r.v, t, smem + c * P::LSM_COL);
+            F::pass_a(r.v, t, s0);
         });
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-            const int t = tid / P::C, c = tid - t * P::C;
-            F::load_b(r.v, t, smem + c * P::LSM_COL, tw);
+            LSTED_COL_IDS
+            F::load_b(r.v, t, s0, tw);
+            F::pass_b(r.v, t, s1);
         });
-        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-            const int t = tid / P::C, c = tid - t * P::C;
-            F::pass_b(r.v, t, smem + c * P::LSM_COL);
-        });
-        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-            const int t = tid / P::C, c = tid - t * P::C;
-            F::pass_c(r.v, t, smem + c * P::LSM_COL, tw);
-            LSTED_UNROLL
-            for (int i = 0; i < P::NKEEP; ++i) r.keep[i] = r.v[i];
-        });
-        for (int k = 0; k < a.K; ++k) {
-            const cplx<T>* otf = a.otf + (size_t)k * img_ly + (size_t)xb * slab_ly;
-            cplx<T>* dst = a.dst + (size_t)k * img_ny + (size_t)xb * slab_ny;
+        // k-loop: [finish transform k-1 and store it | product k, inverse pass A] then pass B
+        for (int k = 0; k <= K; ++k) {
             cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-                const int t = tid / P::C, c = tid - t * P::C;
-                LSTED_UNROLL
-                for (int m = 0; m < F::MC; ++m) {
-                    const int j = t + m * P::NT;
-                    if (j < F::NC) {
-                        LSTED_UNROLL
-                        for (int q = 0; q < F::RC; ++q) {
-                            const int y = j + q * F::NC;
-                            r.v[m * F::RC + q] = r.keep[m * F::RC + q] * otf[(size_t)y * P::C + c];
-                        }
-                    }
+                LSTED_COL_IDS
+                if (k == 0) {
+                    F::pass_c(r.v, t, s1, tw);
+                    LSTED_UNROLL
+                    for (int i = 0; i < P::NKEEP; ++i) r.keep[i] = r.v[i];
+                } else {
+                    I::pass_c(r.v, t, s1, tw);
+                    col_store_inv_c<P>(r.v, t, c, dst0 + (size_t)(k - 1) * img_ny, g.sy, Ny);
                 }
-                I::pass_a(r.v, t, smem + c * P::LSM_COL);
+                if (k < K) {
+                    col_otf_product<P, false>(r, t, c, otf0 + (size_t)k * img_ly, false);
+                    I::pass_a(r.v, t, s0);
+                }
             });
+            if (k == K) break;
             cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-                const int t = tid / P::C, c = tid - t * P::C;
-                I::load_b(r.v, t, smem + c * P::LSM_COL, tw);
-            });
-            cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-                const int t = tid / P::C, c = tid - t * P::C;
-                I::pass_b(r.v, t, smem + c * P::LSM_COL);
-            });
-            cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-                const int t = tid / P::C, c = tid - t * P::C;
-                I::pass_c(r.v, t, smem + c * P::LSM_COL, tw);
-                col_store_inv_c<P>(r.v, t, c, dst, g.sy, Ny);
+                LSTED_COL_IDS
+                I::load_b(r.v, t, s0, tw);
+                I::pass_b(r.v, t, s1);
             });
         }
         return;
     }
-    // COL_HT
-    for (int k = 0; k < a.K; ++k) {
-        const cplx<T>* src = a.src + (size_t)k * img_ny + (size_t)xb * slab_ny;
-        const cplx<T>* otf = a.otf + (size_t)k * img_ly + (size_t)xb * slab_ly;
+    // COL_HT: per k [accumulate product k-1 | load k, forward pass A] then pass B
+    const cplx<T>* src0 = a.src + (size_t)xb * slab_ny;
+    const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
+    for (int k = 0; k <= K; ++k) {
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-            const int t = tid / P::C, c = tid - t * P::C;
-            col_load_fwd_a<P>(r.v, t, c, src, Ny);
-            F::pass_a(r.v, t, smem + c * P::LSM_COL);
-        });
-        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-            const int t = tid / P::C, c = tid - t * P::C;
-            F::load_b(r.v, t, smem + c * P::LSM_COL, tw);
-        });
-        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-            const int t = tid / P::C, c = tid - t * P::C;
-            F::pass_b(r.v, t, smem + c * P::LSM_COL);
-        });
-        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-            const int t = tid / P::C, c = tid - t * P::C;
-            F::pass_c(r.v, t, smem + c * P::LSM_COL, tw);
-            LSTED_UNROLL
-            for (int m = 0; m < F::MC; ++m) {
-                const int j = t + m * P::NT;
-                if (j < F::NC) {
-                    LSTED_UNROLL
-                    for (int q = 0; q < F::RC; ++q) {
-                        const int y = j + q * F::NC;
-                        const cplx<T> p = r.v[m * F::RC + q] * otf[(size_t)y * P::C + c];
-                        r.keep[m * F::RC + q] = (k == 0) ? p : r.keep[m * F::RC + q] + p;
-                    }
-                }
+            LSTED_COL_IDS
+            if (k > 0) {
+                F::pass_c(r.v, t, s1, tw);
+                col_otf_product<P, true>(r, t, c, otf0 + (size_t)(k - 1) * img_ly, k == 1);
             }
+            if (k < K) {
+                col_load_fwd_a<P>(r.v, t, c, src0 + (a.src_same ? 0 : (size_t)k * img_ny), Ny);
+                F::pass_a(r.v, t, s0);
+            } else {
+                LSTED_UNROLL
+                for (int i = 0; i < P::NKEEP; ++i) r.v[i] = r.keep[i];
+                I::pass_a(r.v, t, s0);
+            }
+        });
+        if (k == K) break;
+        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+            LSTED_COL_IDS
+            F::load_b(r.v, t, s0, tw);
+            F::pass_b(r.v, t, s1);
         });
     }
     cplx<T>* dst = a.dst + (size_t)xb * slab_ny;
     cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-        const int t = tid / P::C, c = tid - t * P::C;
-        LSTED_UNROLL
-        for (int i = 0; i < P::NKEEP; ++i) r.v[i] = r.keep[i];
-        I::pass_a(r.v, t, smem + c * P::LSM_COL);
+        LSTED_COL_IDS
+        I::load_b(r.v, t, s0, tw);
+        I::pass_b(r.v, t, s1);
     });
     cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-        const int t = tid / P::C, c = tid - t * P::C;
-        I::load_b(r.v, t, smem + c * P::LSM_COL, tw);
-    });
-    cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-        const int t = tid / P::C, c = tid - t * P::C;
-        I::pass_b(r.v, t, smem + c * P::LSM_COL);
-    });
-    cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-        const int t = tid / P::C, c = tid - t * P::C;
-        I::pass_c(r.v, t, smem + c * P::LSM_COL, tw);
+        LSTED_COL_IDS
+        I::pass_c(r.v, t, s1, tw);
         col_store_inv_c<P>(r.v, t, c, dst, g.sy, Ny);
     });
+#undef LSTED_COL_IDS
 }
 
 // ---------------------------------------------------------------------------
@@ -232,7 +243,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     typedef typename P::Inv I;
     const ConvGeom& g = a.g;
     const int Ny = g.Ny, Nx = g.Nx;
-    const int Lx = P::L, Lxh = P::L / 2 + 1, C = P::C;  // == g.Lx, g.Lxh, g.C (checked at launch)
+    const int Lx = P::L, C = P::C;  // == g.Lx, g.C (checked at launch)
     const int Py = (Ny + 1) / 2;
     const int bpi = (Py + P::PR - 1) / P::PR;
     const int img = block / bpi;
@@ -242,14 +253,17 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     const cplx<T>* tw = a.tw;
     // the data of a pair sit at logical positions shift + pixel during the transforms
     const int shift = (MODE == ROW_FWD) ? 0 : g.sx;
+    const size_t xb_stride = (size_t)Ny * C;  // elements between consecutive column blocks
 
 #define LSTED_ROW_IDS                                      \
     const int f = tid / P::NTG, t = tid - f * P::NTG;      \
     const int pair = pair0 + f;                            \
     const bool live = pair < Py && t < P::NT;              \
     const int y = 2 * pair;                                \
-    cplx<T>* sm = smem + f * P::LSM_ROW;                   \
-    (void)sm; (void)y; (void)live;
+    const bool two = y + 1 < Ny;                           \
+    cplx<T>* const s0 = smem + (size_t)(2 * f) * P::LSM_ROW;      \
+    cplx<T>* const s1 = smem + (size_t)(2 * f + 1) * P::LSM_ROW;  \
+    (void)s0; (void)s1; (void)y; (void)live; (void)two;
 
     if (MODE == ROW_FWD) {
         const T* src = a.real_in + real_off;
@@ -266,60 +280,62 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                         T va = 0, vb = 0;
                         if (i < Nx) {
                             va = src[(size_t)y * Nx + i];
-                            if (y + 1 < Ny) vb = src[(size_t)(y + 1) * Nx + i];
+                            if (two) vb = src[(size_t)(y + 1) * Nx + i];
                         }
                         r.v[m * F::RA + q] = mk<T>(va, vb);
                     }
                 }
             }
-            F::pass_a(r.v, t, sm);
+            F::pass_a(r.v, t, s0);
         });
     } else {
-        // Hermitian unpack straight into the inverse pass-A registers:
+        // Hermitian unpack straight into the inverse pass-A registers (bins t + q*NC):
         // Z[i] = A[i] + i B[i] (i <= L/2), conj(A[L-i]) + i conj(B[L-i]) otherwise.
+        // q < QH is always the lower half, q > QH always the upper half.
         const cplx<T>* src = a.spec_in + spec_off;
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             if (!live) return;
+            const cplx<T>* lo = src + ((size_t)(t / C) * Ny + y) * C + (t % C);
+            const int tm = Lx - t;  // mirror of bin t; (tm - q*NC) is the mirror of bin t + q*NC
             LSTED_UNROLL
-            for (int m = 0; m < I::MA; ++m) {
-                const int j = t + m * P::NT;
-                if (j < I::NA) {
-                    LSTED_UNROLL
-                    for (int q = 0; q < I::RA; ++q) {
-                        const int i = j + q * I::NA;
-                        const bool upper = 2 * i > Lx;
-                        const int k = upper ? Lx - i : i;
-                        const size_t ia = ((size_t)(k / C) * Ny + y) * C + (k % C);
-                        cplx<T> A = src[ia];
-                        cplx<T> B = (y + 1 < Ny) ? src[ia + C] : mk<T>(0, 0);
-                        if (k == 0 || 2 * k == Lx) { A.y = 0; B.y = 0; }
-                        r.v[m * I::RA + q] = upper ? mk<T>(A.x + B.y, B.x - A.y)
-                                                   : mk<T>(A.x - B.y, A.y + B.x);
-                    }
+            for (int q = 0; q < I::RA; ++q) {
+                const int i = t + q * P::NC;
+                bool upper = q > P::QH;
+                if (q == P::QH) upper = 2 * i > Lx;
+                cplx<T> A, B;
+                if (q < P::QH || (q == P::QH && !upper)) {
+                    const cplx<T>* p = lo + (size_t)(q * (P::NC / C)) * xb_stride;
+                    A = p[0];
+                    B = two ? p[C] : mk<T>(0, 0);
+                } else {
+                    const int k = tm - q * P::NC;
+                    const cplx<T>* p = src + ((size_t)(k / C) * Ny + y) * C + (k % C);
+                    A = p[0];
+                    B = two ? p[C] : mk<T>(0, 0);
                 }
+                if ((q == 0 && t == 0) || 2 * i == Lx) { A.y = 0; B.y = 0; }
+                r.v[q] = upper ? mk<T>(A.x + B.y, B.x - A.y) : mk<T>(A.x - B.y, A.y + B.x);
             }
-            I::pass_a(r.v, t, sm);
+            I::pass_a(r.v, t, s0);
         });
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
-            if (live) I::load_b(r.v, t, sm, tw);
+            if (!live) return;
+            I::load_b(r.v, t, s0, tw);
+            I::pass_b(r.v, t, s1);
         });
-        cx.phase(regs, [&](int tid, RowRegs<P>& r) {
-            LSTED_ROW_IDS
-            if (live) I::pass_b(r.v, t, sm);
-        });
-        // inverse pass C, then the pointwise step on registers: logical
-        // position idx = j + q*NC holds pixel idx - sx of rows y (re) and y+1 (im)
+        // inverse pass C, the pointwise step on registers (logical position
+        // idx = j + q*NC holds pixel idx - sx of rows y (re) and y+1 (im)) and the
+        // forward pass A of the result, all in one phase.
         T* out = (MODE == ROW_FINAL) ? a.real_out : a.real_out + real_off;
         T* out2 = (MODE == ROW_INV_SIM) ? a.real_out2 + real_off : 0;
         const T* aux = (MODE == ROW_MID) ? a.aux + real_off : a.aux;
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             if (!live) return;
-            const bool two = y + 1 < Ny;
             // Issue every global load of the pointwise step up front (they overlap
-            // pass C); divisions with their slow-path branches come afterwards.
+            // pass C); the arithmetic comes afterwards.
             cplx<T> pa[(MODE == ROW_MID || MODE == ROW_FINAL) ? I::MC * I::RC : 1];
             cplx<T> pe[MODE == ROW_FINAL ? I::MC * I::RC : 1];
             if (MODE == ROW_MID || MODE == ROW_FINAL) {
@@ -344,7 +360,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                     }
                 }
             }
-            I::pass_c(r.v, t, sm, tw);
+            I::pass_c(r.v, t, s1, tw);
             LSTED_UNROLL
             for (int m = 0; m < I::MC; ++m) {
                 const int j = t + m * P::NT;
@@ -381,6 +397,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                     }
                 }
             }
+            if (MODE == ROW_MID || MODE == ROW_FINAL) F::pass_a(r.v, t, s0);
         });
         if (MODE == ROW_INV_SIM) {
             // Shot noise.  A rolled loop over the pixels this thread just wrote (one
@@ -389,7 +406,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 LSTED_ROW_IDS
                 (void)r;
                 if (!live) return;
-                const int nr = (y + 1 < Ny) ? 2 : 1;
+                const int nr = two ? 2 : 1;
                 LSTED_NOUNROLL
                 for (int e = 0; e < I::MC * I::RC * 2; ++e) {
                     const int rr = e & 1, mq = e >> 1;
@@ -404,62 +421,60 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             });
         }
         if (MODE == ROW_INV_STORE || MODE == ROW_INV_SIM) return;
-        cx.phase(regs, [&](int tid, RowRegs<P>& r) {
-            LSTED_ROW_IDS
-            if (live) F::pass_a(r.v, t, sm);
-        });
     }
     cx.phase(regs, [&](int tid, RowRegs<P>& r) {
         LSTED_ROW_IDS
-        if (live) F::load_b(r.v, t, sm, tw);
+        if (!live) return;
+        F::load_b(r.v, t, s0, tw);
+        F::pass_b(r.v, t, s1);
     });
-    cx.phase(regs, [&](int tid, RowRegs<P>& r) {
-        LSTED_ROW_IDS
-        if (live) F::pass_b(r.v, t, sm);
-    });
-    cx.phase(regs, [&](int tid, RowRegs<P>& r) {
-        LSTED_ROW_IDS
-        if (live) F::pass_c(r.v, t, sm, tw);
-    });
-    // natural-order spectrum of (a + i b) to shared memory ...
+    // Forward pass C; the upper half of the spectrum goes to the mirror thread.
     cx.phase(regs, [&](int tid, RowRegs<P>& r) {
         LSTED_ROW_IDS
         if (!live) return;
+        F::pass_c(r.v, t, s1, tw);
         LSTED_UNROLL
-        for (int m = 0; m < F::MC; ++m) {
-            const int j = t + m * P::NT;
-            if (j < F::NC) {
-                LSTED_UNROLL
-                for (int q = 0; q < F::RC; ++q) sm[j + q * F::NC] = r.v[m * F::RC + q];
-            }
-        }
+        for (int q = P::QH; q < P::RCF; ++q) s0[(q - P::QH) * P::PX + t] = r.v[q];
     });
-    // ... then Hermitian split, crop-offset phase ramp, XB store.
+    // Hermitian split of the lower half, crop-offset phase ramp, XB store:
+    // bins k = t + q*NC with mirror L - k = (NC - t) + (RC - 1 - q)*NC.
     cplx<T>* dst = a.spec_out + spec_off;
     cx.phase(regs, [&](int tid, RowRegs<P>& r) {
-        const int f = tid / P::NTG, tl = tid - f * P::NTG;
-        const int pair = pair0 + f;
-        if (pair >= Py) return;
-        const int y = 2 * pair;
-        const int nr = (y + 1 < Ny) ? 2 : 1;
-        const cplx<T>* sm = smem + f * P::LSM_ROW;
-        const int per_xb = 2 * C;
-        for (int w = tl; w < g.nxb * per_xb; w += P::NTG) {
-            const int xb = w / per_xb, rem = w - xb * per_xb;
-            const int rr = rem / C, c = rem - rr * C;
-            if (rr >= nr) continue;
-            const int k = xb * C + c;
-            cplx<T> o = mk<T>(0, 0);
-            if (k < Lxh) {
-                const cplx<T> z1 = sm[k];
-                const cplx<T> z2 = sm[k == 0 ? 0 : Lx - k];
-                if (rr) o = mk<T>((T)0.5 * (z1.y + z2.y), (T)0.5 * (z2.x - z1.x));
-                else    o = mk<T>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y - z2.y));
-                if (shift) o = o * conj(tw[(k * shift) % Lx]);  // k*shift < L*L/2 fits an int
+        LSTED_ROW_IDS
+        if (!live) return;
+        const int tp = t == 0 ? 0 : P::NC - t;         // mirror thread
+        const int qoff = t == 0 ? 1 : 0;               // thread 0 mirrors onto itself, one q up
+        cplx<T>* pk = dst + ((size_t)(t / C) * Ny + y) * C + (t % C);
+        const int step = (t * shift) % Lx;             // twiddle index of the phase ramp at q = 0
+        const int qstep = (P::NC * shift) % Lx;
+        LSTED_UNROLL
+        for (int q = 0; q <= P::QH; ++q) {
+            const int k = t + q * P::NC;
+            if (q == P::QH && 2 * k > Lx) {
+                // past the Nyquist bin: only the zero padding of the last column block
+                if (k < g.nxb * C) {
+                    cplx<T>* p = pk + (size_t)(q * (P::NC / C)) * xb_stride;
+                    p[0] = mk<T>(0, 0);
+                    if (two) p[C] = mk<T>(0, 0);
+                }
+                continue;
             }
-            dst[((size_t)xb * Ny + y + rr) * C + c] = o;
+            const cplx<T> z1 = r.v[q];
+            cplx<T> z2;
+            const int qm = P::RCF - 1 - q + qoff;      // q of the mirror bin in thread tp
+            if (t == 0 && q == 0) z2 = z1;
+            else z2 = s0[(qm - P::QH) * P::PX + tp];
+            cplx<T> oa = mk<T>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y - z2.y));  // (z1 + conj z2)/2
+            cplx<T> ob = mk<T>((T)0.5 * (z1.y + z2.y), (T)0.5 * (z2.x - z1.x));  // (z1 - conj z2)/(2i)
+            if (shift) {
+                const cplx<T> ph = conj(tw[(step + q * qstep) % Lx]);
+                oa = oa * ph;
+                ob = ob * ph;
+            }
+            cplx<T>* p = pk + (size_t)(q * (P::NC / C)) * xb_stride;
+            p[0] = oa;
+            if (two) p[C] = ob;
         }
-        (void)r;
     });
 #undef LSTED_ROW_IDS
 }

@@ -32,7 +32,7 @@ template <typename T, class BK> class DeconvEngine {
 
     DeconvEngine(BK& backend, int K_, int ny_, int nx_, int Ny, int Nx)
         : K(K_), ny(ny_), nx(nx_), iterations_done(0), have_norm(false), have_estimate(false),
-          exact_clip(false), bk(backend) {
+          exact_clip(false), bk(backend), tmpK(0) {
         const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g, &BK::fast_cols);
         if (why[0]) throw std::string(why);
         npix = (size_t)Ny * Nx;
@@ -58,7 +58,7 @@ template <typename T, class BK> class DeconvEngine {
     }
     ~DeconvEngine() {
         void* all[] = {tw_x, tw_y, otf, spec1, specK, true_object, estimate, norm,
-                       scratch, noiseless, noisy, stage64, object64, partial};
+                       scratch, noiseless, noisy, stage64, object64, partial, tmpK};
         for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) bk.free(all[i]);
     }
 
@@ -208,15 +208,14 @@ template <typename T, class BK> class DeconvEngine {
     void H_host(const double* x, double* out) {
         bk.upload(stage64, x, sizeof(double) * npix);
         bk.cast_in(scratch, stage64, npix, 1.0);
-        T* tmp = (T*)bk.alloc(sizeof(T) * npix * K);
+        T* tmp = tmp_images();
         op_H(scratch, tmp, 0, 0);
         bk.cast_out(stage64, tmp, npix * K);
         bk.download(out, stage64, sizeof(double) * npix * K);
-        bk.free(tmp);
         invalidate_estimate_spectrum();
     }
     void Ht_host(const double* y, double* out, bool normalize) {
-        T* tmp = (T*)bk.alloc(sizeof(T) * npix * K);
+        T* tmp = tmp_images();
         if (normalize) ensure_norm();
         bk.upload(stage64, y, sizeof(double) * npix * K);
         bk.cast_in(tmp, stage64, npix * K, 1.0);
@@ -224,7 +223,6 @@ template <typename T, class BK> class DeconvEngine {
         if (normalize) bk.divide(scratch, norm, npix);
         bk.cast_out(stage64, scratch, npix);
         bk.download(out, stage64, sizeof(double) * npix);
-        bk.free(tmp);
         invalidate_estimate_spectrum();
     }
 
@@ -235,6 +233,11 @@ template <typename T, class BK> class DeconvEngine {
     cplx<T>*tw_x, *tw_y, *otf, *spec1, *specK;
     T *true_object, *estimate, *norm, *scratch, *noiseless, *noisy;
     double *stage64, *object64, *partial;
+    T* tmpK;  // K images, allocated on first use by the host-array forms of H / H_t
+    T* tmp_images() {
+        if (!tmpK) tmpK = (T*)bk.alloc(sizeof(T) * npix * K);
+        return tmpK;
+    }
 
     RowArgs<T> row_args(const ConvGeom& gg) {
         RowArgs<T> a;
@@ -249,10 +252,10 @@ template <typename T, class BK> class DeconvEngine {
         return a;
     }
     // specK holds K row-spectra -> out = sum_k conv_k (spec1 is clobbered)
-    void ht_from_specK(T* out) {
+    void ht_from_specK(T* out, bool same_input = false) {
         if (!exact_clip) {
             ColArgs<T> ct = col_args(g);
-            ct.src = specK; ct.dst = spec1; ct.K = K;
+            ct.src = specK; ct.dst = spec1; ct.K = K; ct.src_same = same_input;
             bk.template launch_col<COL_HT, T>(g.nxb, ct);
             RowArgs<T> rb = row_args(g);
             rb.nimg = 1; rb.spec_in = spec1; rb.real_out = out; rb.clip = 1;
@@ -261,7 +264,7 @@ template <typename T, class BK> class DeconvEngine {
             // one orientation at a time: product, inverse, clip, accumulate
             for (int k = 0; k < K; ++k) {
                 ColArgs<T> ct = col_args(g);
-                ct.src = specK + spec_elems(g, g.Ny) * k;
+                ct.src = specK + (same_input ? 0 : spec_elems(g, g.Ny) * k);
                 ct.otf = otf + spec_elems(g, g.Ly) * k;
                 ct.dst = spec1; ct.K = 1;
                 bk.template launch_col<COL_HT, T>(g.nxb, ct);
@@ -276,11 +279,13 @@ template <typename T, class BK> class DeconvEngine {
     // H_t_normalization = H_t(ones, normalize=False) (line_sted_tools.py:589-593)
     void ensure_norm() {
         if (have_norm) return;
-        T* ones = (T*)bk.alloc(sizeof(T) * npix * K);
-        bk.fill(ones, npix * K, (T)1);
-        op_Ht_raw(ones, norm);
-        bk.sync();
-        bk.free(ones);
+        // All K inputs are the same all-ones image: one row pass, shared by every k,
+        // and no temporary allocation (cudaMalloc/cudaFree would serialise the stream).
+        bk.fill(scratch, npix, (T)1);
+        RowArgs<T> ra = row_args(g);
+        ra.nimg = 1; ra.real_in = scratch; ra.spec_out = specK;
+        bk.template launch_row<ROW_FWD, T>(row_blocks(g), ra);
+        ht_from_specK(norm, true);
         have_norm = true;
         invalidate_estimate_spectrum();  // op_Ht_raw clobbered spec1
     }

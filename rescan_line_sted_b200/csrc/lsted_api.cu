@@ -54,7 +54,7 @@ typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 2> Plan2160f;
 typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 
 template <int MODE, class P>
-__global__ void __launch_bounds__(P::ROW_THREADS)
+__global__ void __launch_bounds__(P::ROW_THREADS, sizeof(typename P::T) == 4 ? 2 : 1)
 row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceCtx cx;

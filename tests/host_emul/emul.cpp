@@ -70,7 +70,7 @@ class HostBackend {
         if (use_fast_ && a.g.Lx == P::L && a.g.C == P::C && a.g.PR == P::PR) {
 #pragma omp parallel
             {
-                std::vector<lsted::cplx<T> > smem((size_t)P::PR * P::LSM_ROW);
+                std::vector<lsted::cplx<T> > smem((size_t)P::ROW_SMEM_ELEMS);
                 std::vector<lsted::RowRegs<P> > regs(P::ROW_THREADS);
                 HostCtx cx;
                 cx.nthreads = P::ROW_THREADS;
@@ -93,7 +93,7 @@ class HostBackend {
         if (use_fast_ && MODE != lsted::COL_OTF && a.g.Ly == P::L && a.g.C == P::C) {
 #pragma omp parallel
             {
-                std::vector<lsted::cplx<T> > smem((size_t)P::C * P::LSM_COL);
+                std::vector<lsted::cplx<T> > smem((size_t)P::COL_SMEM_ELEMS);
                 std::vector<lsted::ColRegs<P> > regs(P::COL_THREADS);
                 HostCtx cx;
                 cx.nthreads = P::COL_THREADS;
