@@ -33,6 +33,33 @@ template <typename T> LSTED_HD cplx<T> operator*(cplx<T> a, cplx<T> b) {
     return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 template <typename T> LSTED_HD cplx<T> scale(cplx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
+// a * s + b with a real factor s
+template <typename T> LSTED_HD cplx<T> fma_real(cplx<T> a, T s, cplx<T> b) {
+    return mk<T>(a.x * s + b.x, a.y * s + b.y);
+}
+#ifndef LSTED_NO_PACKED_F32X2
+#define LSTED_PACKED_F32X2 1
+#endif
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && defined(LSTED_PACKED_F32X2)
+// Blackwell packed fp32 pairs (FADD2 / FMUL2 / FFMA2): a complex add, subtract or
+// real scaling is one instruction on a 64-bit register pair.
+LSTED_HD cplx<float> operator+(cplx<float> a, cplx<float> b) {
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return mk<float>(r.x, r.y);
+}
+LSTED_HD cplx<float> operator-(cplx<float> a, cplx<float> b) {
+    const float2 r = __ffma2_rn(make_float2(b.x, b.y), make_float2(-1.f, -1.f), make_float2(a.x, a.y));
+    return mk<float>(r.x, r.y);
+}
+LSTED_HD cplx<float> scale(cplx<float> a, float s) {
+    const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(s, s));
+    return mk<float>(r.x, r.y);
+}
+LSTED_HD cplx<float> fma_real(cplx<float> a, float s, cplx<float> b) {
+    const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(s, s), make_float2(b.x, b.y));
+    return mk<float>(r.x, r.y);
+}
+#endif
 template <typename T> LSTED_HD cplx<T> conj(cplx<T> a) { return mk<T>(a.x, -a.y); }
 // Branch-free fp32 division (MUFU.RCP based, <= 2 ulp) so the compiler can keep
 // many independent loads/divisions in flight; fp64 divides exactly.
@@ -76,7 +103,7 @@ template <int DIR, typename T> struct Dft<3, DIR, T> {
         const T s3 = (T)0.86602540378443864676;
         cplx<T> t = v[1] + v[2];
         cplx<T> d = mul_dir_i<DIR>(scale(v[1] - v[2], s3));
-        cplx<T> m = mk<T>(v[0].x - (T)0.5 * t.x, v[0].y - (T)0.5 * t.y);
+        cplx<T> m = fma_real(t, (T)-0.5, v[0]);
         v[0] = v[0] + t;
         v[1] = m + d;
         v[2] = m - d;
@@ -100,10 +127,10 @@ template <int DIR, typename T> struct Dft<5, DIR, T> {
         const T s1 = (T)0.95105651629515357212, s2 = (T)0.58778525229247312917;
         cplx<T> t1 = v[1] + v[4], t2 = v[2] + v[3];
         cplx<T> t3 = v[1] - v[4], t4 = v[2] - v[3];
-        cplx<T> a1 = mk<T>(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
-        cplx<T> a2 = mk<T>(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
-        cplx<T> b1 = mul_dir_i<DIR>(mk<T>(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
-        cplx<T> b2 = mul_dir_i<DIR>(mk<T>(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+        cplx<T> a1 = fma_real(t2, c2, fma_real(t1, c1, v[0]));
+        cplx<T> a2 = fma_real(t2, c1, fma_real(t1, c2, v[0]));
+        cplx<T> b1 = mul_dir_i<DIR>(fma_real(t4, s2, scale(t3, s1)));
+        cplx<T> b2 = mul_dir_i<DIR>(fma_real(t4, -s1, scale(t3, s2)));
         v[0] = v[0] + t1 + t2;
         v[1] = a1 + b1;
         v[4] = a1 - b1;

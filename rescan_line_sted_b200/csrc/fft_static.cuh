@@ -79,18 +79,29 @@ template <typename T, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3 {
             }
         }
     }
+    // w[q] = w1^q for q = 1..N by binary splitting (product depth <= log2 N, so the
+    // rounding error stays at a few ulp); replaces N-1 scattered table look-ups,
+    // which cost up to 32 L1 wavefronts each, by one coalesced load + N-1 products.
+    template <int N> static LSTED_HD void twiddle_powers(cplx<T> w1, cplx<T>* w) {
+        w[1] = w1;
+        LSTED_UNROLL
+        for (int q = 2; q <= N; ++q) w[q] = w[q / 2] * w[q - q / 2];
+    }
     static LSTED_HD void load_b(cplx<T>* v, int t, const cplx<T>* sm, const cplx<T>* tw) {
+        // every butterfly of this thread has the same k = j % RA when NT % RA == 0
+        cplx<T> w[RB];
+        if (NT % RA == 0) twiddle_powers<RB - 1>(tw[RC * (t % RA)], w);
         LSTED_UNROLL
         for (int m = 0; m < MB; ++m) {
             const int j = t + m * NT;
             if (j < NB) {
                 const int k = j % RA;
                 const int pos = k * PA + j / RA;
-                const int step = RC * k;
+                if (NT % RA != 0) twiddle_powers<RB - 1>(tw[RC * k], w);
                 LSTED_UNROLL
                 for (int q = 0; q < RB; ++q) {
                     cplx<T> x = sm[pos + q * RC];
-                    if (q > 0) x = mul_tw<DIR>(x, tw[q * step]);
+                    if (q > 0) x = mul_tw<DIR>(x, w[q]);
                     v[m * RB + q] = x;
                 }
             }
@@ -115,10 +126,12 @@ template <typename T, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3 {
             const int j = t + m * NT;
             if (j < NC) {
                 const int pos = (j / RA) * PB + (j % RA);
+                cplx<T> w[RC];
+                twiddle_powers<RC - 1>(tw[j], w);
                 LSTED_UNROLL
                 for (int q = 0; q < RC; ++q) {
                     cplx<T> x = sm[pos + q * RA];
-                    if (q > 0) x = mul_tw<DIR>(x, tw[q * j]);
+                    if (q > 0) x = mul_tw<DIR>(x, w[q]);
                     v[m * RC + q] = x;
                 }
                 Dft<RC, DIR, T>::run(v + m * RC);

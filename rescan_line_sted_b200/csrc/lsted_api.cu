@@ -50,11 +50,14 @@ struct DeviceCtx {
 };
 
 // Compile-time plans of the fast path (conv_fast.cuh): 2160 = 16 * 9 * 15.
-typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 2> Plan2160f;
+#ifndef LSTED_FAST_PR
+#define LSTED_FAST_PR 1
+#endif
+typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, LSTED_FAST_PR> Plan2160f;
 typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 
 template <int MODE, class P>
-__global__ void __launch_bounds__(P::ROW_THREADS, sizeof(typename P::T) == 4 ? 2 : 1)
+__global__ void __launch_bounds__(P::ROW_THREADS, sizeof(typename P::T) == 4 ? (640 / P::ROW_THREADS) : 1)
 row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceCtx cx;
@@ -209,7 +212,7 @@ class CudaBackend {
         return 0;
     }
     template <class P> static bool plan_fits_rows(const lsted::ConvGeom& g) {
-        return g.Lx == P::L && g.C == P::C && g.PR == P::PR;
+        return g.Lx == P::L && g.C == P::C;
     }
     template <class P> static bool plan_fits_cols(const lsted::ConvGeom& g) {
         return g.Ly == P::L && g.C == P::C;
@@ -224,7 +227,10 @@ class CudaBackend {
             configured = true;
         }
         before(kind);
-        row_fast_kernel<MODE, P><<<grid, P::ROW_THREADS, smem, stream_>>>(a);
+        // the plan's own pairs-per-CTA decides the grid (the generic geometry may differ)
+        const int fast_grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
+        (void)grid;
+        row_fast_kernel<MODE, P><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
         after();
     }
     template <int MODE, class P> void launch_col_fast(int grid, const lsted::ColArgs<typename P::T>& a,

@@ -36,7 +36,7 @@ struct HostCtx {
     }
 };
 
-typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 2> Plan2160f;
+typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 1> Plan2160f;
 typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 template <typename T> struct PlanFor;
 template <> struct PlanFor<float> { typedef Plan2160f type; };
@@ -67,7 +67,8 @@ class HostBackend {
 
     template <int MODE, typename T> void launch_row(int grid, const lsted::RowArgs<T>& a) {
         typedef typename PlanFor<T>::type P;
-        if (use_fast_ && a.g.Lx == P::L && a.g.C == P::C && a.g.PR == P::PR) {
+        if (use_fast_ && a.g.Lx == P::L && a.g.C == P::C) {
+            grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
 #pragma omp parallel
             {
                 std::vector<lsted::cplx<T> > smem((size_t)P::ROW_SMEM_ELEMS);
