@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument('--iterations', type=int, default=64)
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp64'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--shard', default='frames', choices=['frames', 'orientations'],
+                    help='N>1: independent frames per GPU (weak scaling, no collective) or the '
+                         'K orientations of every frame split over the GPUs (strong scaling, one '
+                         'NCCL all-reduce per RL iteration)')
     return ap.parse_args()
 
 
@@ -230,7 +234,9 @@ def workload_config(args):
                                          args.iterations),
             'size': args.size, 'orientations': args.orientations,
             'rl_iterations': args.iterations, 'psf_side': 107,
-            'sharding': 'independent frames per GPU (no collective)',
+            'sharding': ('independent frames per GPU (no collective)' if args.shard == 'frames'
+                         else 'orientations of each frame split over the GPUs, one NCCL all-reduce '
+                              'of the Fourier-domain partial H_t sum per RL iteration'),
             'cache': 'working set (K measurements + K spectra + K OTFs, >1 GB) exceeds the '
                      '126 MB L2; no explicit flush'}
 
@@ -270,8 +276,17 @@ def main():
     brightness = total_brightness(N)
 
     lib = _lib.get()
-    h = _lib.DeconvHandle(lib, st._stack_psfs(psfs), (N, N),
-                          precision=32 if args.precision == 'fp32' else 64, device=local_rank)
+    by_orientation = args.shard == 'orientations' and world > 1
+    if by_orientation:
+        from rescan_line_sted_b200 import sharded
+        sd = sharded.OrientationShardedDeconvolver(
+            st._stack_psfs(psfs), (N, N), precision=32 if args.precision == 'fp32' else 64,
+            device=local_rank)
+        h = sd.handle
+    else:
+        h = _lib.DeconvHandle(lib, st._stack_psfs(psfs), (N, N),
+                              precision=32 if args.precision == 'fp32' else 64, device=local_rank)
+    jobs = 1 if by_orientation else world   # frames in flight across the node
     info = h.info()
     pinned_in = _lib.pinned_empty((1, N, N))
     pinned_in[...] = obj_host
@@ -312,7 +327,7 @@ def main():
     t_begin = time.perf_counter()
     h.timer_start()
     for s in range(args.steps):
-        frame_resident(s + 1 + 7919 * rank)
+        frame_resident(s + 1 + (0 if by_orientation else 7919 * rank))
     ms_total = h.timer_stop()
     sampler.window(t_begin, time.perf_counter())
     barrier()
@@ -322,13 +337,13 @@ def main():
     h.set_option('profile', 1)
     h.profile(reset=True)
     for s in range(args.steps):
-        frame_resident(s + 1 + 7919 * rank)
+        frame_resident(s + 1 + (0 if by_orientation else 7919 * rank))
     prof = h.profile(reset=True)
     h.set_option('profile', 0)
     clocks = sampler.stop()
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
-    value = world * 1000.0 / ms_step
+    value = jobs * 1000.0 / ms_step
 
     # ---- end-to-end timing through host buffers ----
     for w in range(min(2, args.warmup)):
@@ -361,6 +376,9 @@ def main():
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     elem = 4 if args.precision == 'fp32' else 8
     A = elem * N * N
+    K_total = K
+    if by_orientation:
+        K = sd.k1 - sd.k0       # per-GPU accounting: this rank's orientations
     # algorithmic bytes charged to each launch (DESIGN.md "Roofline accounting")
     alg = {'row_mid': K * A,        # streams the K measurements once
            'row_final': 4 * A,      # norm + estimate read, estimate write (+ estimate for H)
@@ -395,14 +413,15 @@ def main():
     line = {
         'metric': 'frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'higher_is_better': True, 'scaling': 'strong' if by_orientation else 'weak',
+        'vs_baseline': None,
         'dtype': 'f32' if args.precision == 'fp32' else 'f64', 'data': 'synthetic',
         'config': workload_config(args),
-        'e2e': {'value': world * 1000.0 / ms_e2e, 'unit': 'frames/s',
+        'e2e': {'value': jobs * 1000.0 / ms_e2e, 'unit': 'frames/s',
                 'h2d_bytes_per_step': int(pinned_in.nbytes),
                 'd2h_bytes_per_step': int(pinned_out.nbytes), 'ms_per_step': ms_e2e},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'kernels': kernels,
-        'rl_iterations_per_sec': world * n_iter * 1000.0 / ms_step,
+        'rl_iterations_per_sec': jobs * n_iter * 1000.0 / ms_step,
         'geometry': {'Ly': info.Ly, 'Lx': info.Lx, 'cols_per_cta': info.cols_per_cta,
                      'row_pairs_per_cta': info.row_pairs_per_cta,
                      'device_bytes': int(info.device_bytes)},

@@ -99,6 +99,16 @@ int lsted_deconv_create_data(lsted_deconv* h, const double* object, double total
  * then run the forward model + Poisson on whatever object is staged.              */
 int lsted_deconv_upload_object(lsted_deconv* h, const double* object);
 int lsted_deconv_simulate(lsted_deconv* h, double total_brightness, int rescale, uint64_t seed);
+/* Orientation sharding over the GPUs of one node: the handle was created
+ * with this rank's subset of the PSFs (global orientation indices k_offset ...); every
+ * rank keeps a replica of the estimate and of the normalisation, and the partial H_t sums
+ * are combined by ONE ncclAllReduce per RL iteration (of the Fourier-domain partial sum)
+ * on the handle's stream.  `unique_id` = the 128 bytes lsted_nccl_unique_id() produced
+ * on rank 0, distributed by the caller (e.g. torch.distributed broadcast).  NCCL is
+ * dlopen()ed on first use; single-GPU users do not need it.                          */
+enum { LSTED_NCCL_UNIQUE_ID_BYTES = 128 };
+int lsted_nccl_unique_id(char* out);
+int lsted_deconv_shard(lsted_deconv* h, int rank, int world, int k_offset, const char* unique_id);
 /* iterate() n times (:520-531); no host transfers.                                 */
 int lsted_deconv_iterate(lsted_deconv* h, int n);
 /* attribute access; k is the PSF index for the per-PSF lists, else 0.

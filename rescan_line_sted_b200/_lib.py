@@ -53,6 +53,8 @@ _DECONV_SIGNATURES = {
     'lsted_deconv_upload_object': [ctypes.c_void_p, c_double_p],
     'lsted_deconv_simulate': [ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
                               ctypes.c_uint64],
+    'lsted_deconv_shard': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                           ctypes.c_int, ctypes.c_char_p],
     'lsted_deconv_iterate': [ctypes.c_void_p, ctypes.c_int],
     'lsted_deconv_get': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                          c_double_p],
@@ -73,6 +75,7 @@ _CORE_SIGNATURES = {
     'lsted_device_count': [c_int_p],
     'lsted_host_alloc': [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t],
     'lsted_host_free': [ctypes.c_void_p],
+    'lsted_nccl_unique_id': [ctypes.c_char_p],
     'lsted_psf_illumination': [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                ctypes.c_int, c_double_p, ctypes.c_int,
                                c_double_p, c_double_p, c_double_p, c_double_p,
@@ -198,6 +201,11 @@ class DeconvHandle:
                       float(total_brightness or 0.0), int(rescale),
                       ctypes.c_uint64(seed))
 
+    def shard(self, rank, world, k_offset, unique_id):
+        """Orientation sharding: this handle holds PSFs k_offset..k_offset+K-1."""
+        self.lib.call('lsted_deconv_shard', self._h, int(rank), int(world),
+                      int(k_offset), unique_id)
+
     def iterate(self, n=1):
         self.lib.call('lsted_deconv_iterate', self._h, int(n))
 
@@ -270,3 +278,16 @@ def pinned_free(arr):
 
 
 _pinned_keepalive = {}
+
+
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+def nccl_unique_id(lib=None):
+    """128-byte NCCL id (call on rank 0, broadcast to the other ranks).  A
+    library without NCCL (the CPU replay used by the gloo tests) gets zeros."""
+    lib = lib or get()
+    buf = ctypes.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
+    if hasattr(lib.cdll, 'lsted_nccl_unique_id'):
+        lib.call('lsted_nccl_unique_id', buf)
+    return buf.raw

@@ -128,6 +128,20 @@ extern "C" int lsted_deconv_simulate(lsted_deconv* h, double total_brightness, i
     LSTED_CATCH
 }
 
+extern "C" int lsted_deconv_shard(lsted_deconv* h, int rank, int world, int k_offset,
+                                  const char* unique_id) {
+    if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
+    if (world < 1 || rank < 0 || rank >= world || k_offset < 0)
+        return set_error(LSTED_ERR_ARG, "bad rank / world / k_offset");
+    LSTED_TRY
+    h->bk->activate();
+    if (world > 1) h->bk->comm_init(unique_id, rank, world);
+    if (h->precision == 32) h->e32->set_sharding(rank, world, k_offset);
+    else h->e64->set_sharding(rank, world, k_offset);
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
 extern "C" int lsted_deconv_iterate(lsted_deconv* h, int n) {
     if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
     LSTED_TRY

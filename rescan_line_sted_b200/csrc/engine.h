@@ -29,10 +29,11 @@ template <typename T, class BK> class DeconvEngine {
     int K, ny, nx;
     int iterations_done;
     bool have_norm, have_estimate, exact_clip;
+    int rank, world, k_offset;
 
     DeconvEngine(BK& backend, int K_, int ny_, int nx_, int Ny, int Nx)
         : K(K_), ny(ny_), nx(nx_), iterations_done(0), have_norm(false), have_estimate(false),
-          exact_clip(false), bk(backend), tmpK(0) {
+          exact_clip(false), rank(0), world(1), k_offset(0), bk(backend), tmpK(0) {
         const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g, &BK::fast_cols);
         if (why[0]) throw std::string(why);
         npix = (size_t)Ny * Nx;
@@ -98,7 +99,7 @@ template <typename T, class BK> class DeconvEngine {
         RowArgs<T> rb = row_args(g);
         rb.nimg = K; rb.spec_in = specK; rb.real_out = out; rb.clip = 1;
         if (out_noisy) {
-            rb.real_out2 = out_noisy; rb.seed = seed; rb.img0 = 0;
+            rb.real_out2 = out_noisy; rb.seed = seed; rb.img0 = (unsigned)k_offset;
             bk.template launch_row<ROW_INV_SIM, T>(row_blocks(g) * K, rb);
         } else {
             bk.template launch_row<ROW_INV_STORE, T>(row_blocks(g) * K, rb);
@@ -136,6 +137,19 @@ template <typename T, class BK> class DeconvEngine {
     }
     void forget_normalization() { have_norm = false; }
 
+    // Orientation sharding: this handle owns `K` of the orientations
+    // (global indices k_offset .. k_offset+K-1) plus replicas of the estimate and
+    // the normalisation; the Fourier-domain partial sums of H_t are all-reduced
+    // over `world` ranks once per iteration (the transforms are linear, so summing
+    // spectra equals summing images) and everything else stays local.
+    void set_sharding(int rank_, int world_, int k_offset_) {
+        rank = rank_; world = world_; k_offset = k_offset_;
+        have_norm = false;
+    }
+    void reduce_over_ranks(cplx<T>* spec) {
+        if (world > 1) bk.all_reduce_sum((T*)spec, 2 * spec_elems(g, g.Ny));
+    }
+
     void iterate(int n) {
         for (int it = 0; it < n; ++it) {
             ensure_norm();
@@ -157,6 +171,7 @@ template <typename T, class BK> class DeconvEngine {
                 ColArgs<T> ct = col_args(g);
                 ct.src = specK; ct.dst = spec1; ct.K = K;
                 bk.template launch_col<COL_HT, T>(g.nxb, ct);
+                reduce_over_ranks(spec1);   // orientation shards: sum of partial spectra
                 RowArgs<T> rf = row_args(g);
                 rf.nimg = 1; rf.spec_in = spec1; rf.spec_out = spec1;
                 rf.real_out = estimate; rf.aux = norm;
@@ -257,6 +272,7 @@ template <typename T, class BK> class DeconvEngine {
             ColArgs<T> ct = col_args(g);
             ct.src = specK; ct.dst = spec1; ct.K = K; ct.src_same = same_input;
             bk.template launch_col<COL_HT, T>(g.nxb, ct);
+            reduce_over_ranks(spec1);
             RowArgs<T> rb = row_args(g);
             rb.nimg = 1; rb.spec_in = spec1; rb.real_out = out; rb.clip = 1;
             bk.template launch_row<ROW_INV_STORE, T>(row_blocks(g), rb);
@@ -273,6 +289,8 @@ template <typename T, class BK> class DeconvEngine {
                 rb.accumulate = (k > 0);
                 bk.template launch_row<ROW_INV_STORE, T>(row_blocks(g), rb);
             }
+            // every term was clipped locally; the sum over ranks is a plain image sum
+            if (world > 1) bk.all_reduce_sum(out, npix);
         }
     }
   public:

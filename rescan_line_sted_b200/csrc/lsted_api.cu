@@ -4,6 +4,8 @@
 // The kernels are thin __global__ shells around the bodies in
 // conv_bodies.cuh / psf_kernels.cuh; orchestration lives in engine.h.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <stdio.h>
 #include <string.h>
 #include <new>
@@ -129,6 +131,52 @@ __global__ void __launch_bounds__(256) sum_final_kernel(double* partial, int nbl
 }
 
 // ---------------------------------------------------------------------------
+// NCCL, resolved at run time (dlopen) so that single-GPU use has no NCCL dependency
+// ---------------------------------------------------------------------------
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    const char* (*GetErrorString)(ncclResult_t);
+    bool ok;
+};
+static NcclApi& nccl_api() {
+    static NcclApi api = {0, 0, 0, 0, 0, false};
+    if (api.ok) return api;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+        lsted::ApiError e; e.code = LSTED_ERR_NCCL;
+        e.msg = std::string("cannot load libnccl.so.2: ") + dlerror();
+        throw e;
+    }
+    api.GetUniqueId = (ncclResult_t(*)(ncclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+    api.CommInitRank = (ncclResult_t(*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+    api.AllReduce = (ncclResult_t(*)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                                     cudaStream_t))dlsym(lib, "ncclAllReduce");
+    api.CommDestroy = (ncclResult_t(*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(ncclResult_t))dlsym(lib, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString) {
+        lsted::ApiError e; e.code = LSTED_ERR_NCCL; e.msg = "libnccl lacks a required symbol";
+        throw e;
+    }
+    api.ok = true;
+    return api;
+}
+#define NCCL_CHECK(expr)                                                                  \
+    do {                                                                                  \
+        ncclResult_t res__ = (expr);                                                      \
+        if (res__ != ncclSuccess) {                                                       \
+            lsted::ApiError e__;                                                          \
+            e__.code = LSTED_ERR_NCCL;                                                    \
+            e__.msg = std::string(#expr) + ": " + nccl_api().GetErrorString(res__);       \
+            throw e__;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------
 // CUDA backend of the engine
 // ---------------------------------------------------------------------------
 enum KernelKind { KK_ROW_FWD = 0, KK_ROW_INV_STORE, KK_ROW_INV_SIM, KK_ROW_MID, KK_ROW_FINAL,
@@ -156,6 +204,7 @@ class CudaBackend {
     }
     ~CudaBackend() {
         cudaSetDevice(device_);
+        if (comm_) nccl_api().CommDestroy(comm_);
         for (size_t i = 0; i < ev_pool_.size(); ++i) cudaEventDestroy(ev_pool_[i]);
         if (t0_) cudaEventDestroy(t0_);
         if (t1_) cudaEventDestroy(t1_);
@@ -163,6 +212,25 @@ class CudaBackend {
     }
     void activate() { CUDA_CHECK(cudaSetDevice(device_)); }
     void sync() { CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+
+    // ---- collectives (orientation sharding) ----
+    void comm_init(const char* unique_id, int rank, int world) {
+        if (!unique_id) { lsted::ApiError e; e.code = LSTED_ERR_ARG; e.msg = "null NCCL id"; throw e; }
+        if (comm_) { nccl_api().CommDestroy(comm_); comm_ = 0; }
+        ncclUniqueId id;
+        memcpy(id.internal, unique_id, sizeof(id.internal));
+        NCCL_CHECK(nccl_api().CommInitRank(&comm_, world, id, rank));
+    }
+    void all_reduce_sum(float* p, size_t n) {
+        before(KK_EW);
+        NCCL_CHECK(nccl_api().AllReduce(p, p, n, ncclFloat, ncclSum, comm_, stream_));
+        after();
+    }
+    void all_reduce_sum(double* p, size_t n) {
+        before(KK_EW);
+        NCCL_CHECK(nccl_api().AllReduce(p, p, n, ncclDouble, ncclSum, comm_, stream_));
+        after();
+    }
     cudaStream_t stream() const { return stream_; }
 
     void* alloc(size_t bytes) {
@@ -361,6 +429,7 @@ class CudaBackend {
     cudaStream_t stream_;
     size_t bytes_;
     bool profile_, use_fast_;
+    ncclComm_t comm_ = 0;
     cudaEvent_t t0_, t1_;
     int num_sms_;
     std::vector<cudaEvent_t> ev_pool_;
@@ -422,6 +491,17 @@ extern "C" int lsted_device_count(int* count) {
         return set_error(LSTED_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(err));
     }
     return LSTED_OK;
+}
+
+extern "C" int lsted_nccl_unique_id(char* out) {
+    if (!out) return set_error(LSTED_ERR_ARG, "null pointer");
+    try {
+        static_assert(sizeof(ncclUniqueId) == LSTED_NCCL_UNIQUE_ID_BYTES, "NCCL id size");
+        ncclUniqueId id;
+        NCCL_CHECK(nccl_api().GetUniqueId(&id));
+        memcpy(out, id.internal, sizeof(id.internal));
+        return LSTED_OK;
+    } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
 }
 
 extern "C" int lsted_host_alloc(void** ptr, size_t bytes) {

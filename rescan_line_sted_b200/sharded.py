@@ -1,0 +1,97 @@
+"""Multi-GPU sharding of the hot path along its independent axes
+(SURVEY.md section 8e), one process per GPU with torch.distributed as the
+plumbing:
+
+* `OrientationShardedDeconvolver` -- the K line orientations of ONE frame
+  are split over the ranks; every rank keeps a replica of the estimate and
+  one NCCL all-reduce per RL iteration (inside liblsted, on the handle's
+  stream, over NVLink) sums the Fourier-domain partial H_t.
+* `shard_items` / `gather_reports` -- independent units (frames, sweep
+  points of `psf_report_batch`) dealt round-robin, results gathered once.
+"""
+import numpy as np
+
+from . import _lib
+
+
+def orientation_slice(K, rank, world):
+    """Contiguous block of orientation indices owned by `rank`."""
+    if world > K:
+        raise ValueError('more ranks (%d) than orientations (%d)' % (world, K))
+    base, extra = divmod(K, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_items(n_items, rank, world):
+    """Indices of the independent work items (frames, sweep points) of `rank`."""
+    return list(range(rank, n_items, world))
+
+
+def gather_reports(local, n_items, group=None):
+    """Inverse of `shard_items`: every rank gets the full, ordered list."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    dist.all_gather_object(parts, local, group=group)
+    out = [None] * n_items
+    for r, part in enumerate(parts):
+        for i, item in zip(range(r, n_items, world), part):
+            out[i] = item
+    return out
+
+
+class OrientationShardedDeconvolver:
+    """Forward model + multi-view Richardson-Lucy with the orientations of one
+    frame sharded over the ranks of a torch.distributed process group.
+
+    Every rank passes the FULL list of PSFs and the same object / seed; each
+    keeps only its slice on its GPU.  Results (`estimate`) are identical on
+    all ranks and equal to the single-GPU result up to summation order.
+    """
+
+    def __init__(self, psfs, image_shape, precision=32, device=0, group=None,
+                 lib=None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        psfs = np.ascontiguousarray(psfs, dtype=np.float64)
+        self.K_total = psfs.shape[0]
+        self.k0, self.k1 = orientation_slice(self.K_total, self.rank, self.world)
+        lib = lib or _lib.get()
+        self.handle = _lib.DeconvHandle(lib, psfs[self.k0:self.k1], image_shape,
+                                        precision=precision, device=device)
+        unique_id = [None]
+        if self.world > 1:
+            if self.rank == 0:
+                unique_id[0] = _lib.nccl_unique_id(lib)
+            dist.broadcast_object_list(unique_id, src=0, group=group)
+        self.handle.shard(self.rank, self.world, self.k0, unique_id[0])
+
+    def create_data(self, obj, total_brightness, seed):
+        """Each rank simulates only its orientations; the Poisson streams are
+        keyed by the global orientation index, so the noise field does not
+        depend on the number of GPUs."""
+        self.handle.create_data(obj, total_brightness, seed)
+
+    def set_noisy(self, k_global, image):
+        if self.k0 <= k_global < self.k1:
+            self.handle.set(_lib.NOISY, k_global - self.k0, image)
+
+    def local_measurements(self, which=_lib.NOISY):
+        return {k: self.handle.get(which, k - self.k0) for k in range(self.k0, self.k1)}
+
+    def iterate(self, n=1):
+        self.handle.iterate(n)
+
+    @property
+    def estimate(self):
+        return self.handle.get(_lib.ESTIMATE)
+
+    @property
+    def H_t_normalization(self):
+        return self.handle.get(_lib.NORMALIZATION)
+
+    def close(self):
+        self.handle.close()

@@ -1,0 +1,55 @@
+"""Worker of tests/test_gpu_multi.py: one rank (one GPU) of an NCCL group."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from rescan_line_sted_b200 import _lib, sharded
+    local = int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'fig2_2p0x_lr.npz'))
+    out = {}
+    for precision, tag in ((64, 'fp64'), (32, 'fp32')):
+        d = sharded.OrientationShardedDeconvolver(g['psfs'], (128, 128), precision=precision,
+                                                  device=local)
+        d.create_data(g['object_u8'].astype(np.float64), 5e10, 0)
+        for k in range(4):
+            d.set_noisy(k, g['noisy'][k])
+        d.iterate(1)
+        e1 = np.linalg.norm(d.estimate - g['estimate_1']) / np.linalg.norm(g['estimate_1'])
+        d.iterate(7)
+        est = d.estimate
+        e8 = np.linalg.norm(est - g['estimate_8']) / np.linalg.norm(g['estimate_8'])
+        t = torch.from_numpy(est.copy()).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        out[tag] = {'est1': e1, 'est8': e8, 'replica_diff': float((t - ref).abs().max())}
+        # in-kernel Poisson field must not depend on the GPU count
+        d.create_data(g['object_u8'].astype(np.float64), 5e10, 123)
+        noisy = d.local_measurements(_lib.NOISY)
+        single = _lib.DeconvHandle(_lib.get(), g['psfs'], (128, 128), precision=precision,
+                                   device=local)
+        single.create_data(g['object_u8'].astype(np.float64), 5e10, 123)
+        same = all(np.array_equal(v, single.get(_lib.NOISY, k)) for k, v in noisy.items())
+        out[tag]['noise_independent_of_world'] = bool(same)
+        single.close()
+        d.close()
+    if rank == 0:
+        with open(sys.argv[1], 'w') as f:
+            json.dump(out, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

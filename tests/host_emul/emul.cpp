@@ -42,6 +42,10 @@ template <typename T> struct PlanFor;
 template <> struct PlanFor<float> { typedef Plan2160f type; };
 template <> struct PlanFor<double> { typedef Plan2160d type; };
 
+typedef void (*allreduce_cb)(double* buf, size_t n);
+static allreduce_cb g_allreduce = 0;
+extern "C" void emul_set_allreduce(allreduce_cb cb) { g_allreduce = cb; }
+
 class HostBackend {
   public:
     explicit HostBackend(int) : bytes_(0), use_fast_(true) {}
@@ -57,6 +61,17 @@ class HostBackend {
     size_t bytes_allocated() const { return bytes_; }
     void upload(void* d, const void* s, size_t n) { memcpy(d, s, n); }
     void download(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+    // collectives: a callback installed by the test (torch.distributed over gloo)
+    void comm_init(const char*, int, int) {}
+    void all_reduce_sum(double* p, size_t n) {
+        if (!g_allreduce) throw std::string("no all-reduce callback installed");
+        g_allreduce(p, n);
+    }
+    void all_reduce_sum(float* p, size_t n) {
+        std::vector<double> tmp(p, p + n);
+        all_reduce_sum(tmp.data(), n);
+        for (size_t i = 0; i < n; ++i) p[i] = (float)tmp[i];
+    }
     void set_profile(bool) {}
     void timer_start() {}
     float timer_stop() { return 0.f; }

@@ -1,0 +1,39 @@
+"""Orientation sharding over NCCL on 2 GPUs (skipped on a 1-GPU box): same
+golden vectors as the single-GPU tests, identical replicas on every rank, and
+a noise field that does not depend on the number of GPUs."""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def device_count():
+    from rescan_line_sted_b200 import _lib
+    n = ctypes.c_int(0)
+    _lib.get().cdll.lsted_device_count(ctypes.byref(n))
+    return n.value
+
+
+def test_orientation_sharding_nccl(tmp_path):
+    if device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    out = str(tmp_path / 'result.json')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+           '--master-addr', '127.0.0.1', '--master-port', '29519',
+           os.path.join(ROOT, 'tests', '_nccl_worker.py'), out]
+    res = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR='127.0.0.1'),
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    with open(out) as f:
+        r = json.load(f)
+    assert r['fp64']['est1'] < 1e-12 and r['fp64']['est8'] < 1e-11
+    assert r['fp32']['est1'] < 1e-5 and r['fp32']['est8'] < 1e-4
+    for tag in ('fp64', 'fp32'):
+        assert r[tag]['replica_diff'] == 0.0
+        assert r[tag]['noise_independent_of_world']
