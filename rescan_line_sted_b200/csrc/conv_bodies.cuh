@@ -66,6 +66,7 @@ template <typename T> struct RowArgs {
     int accumulate;          // STORE: real_out += result (used by the exact-clip H_t)
     unsigned long long seed; // SIM
     unsigned int img0;       // SIM: global index of image 0 (RNG stream id)
+    int prefetch_ahead;      // fast path: L2-prefetch the operands of CTA (blockIdx + this); 0 = off
 };
 
 template <typename T> LSTED_HD T clip0(T v) { return v < (T)0 ? (T)0 : v; }

@@ -170,6 +170,9 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
         for (int k = 0; k <= K; ++k) {
             cx.phase(regs, [&](int tid, ColRegs<P>& r) {
                 LSTED_COL_IDS
+                if (k + 1 < K)   // the OTF slab of the next orientation streams in from HBM
+                    prefetch_l2_range(otf0 + (size_t)(k + 1) * img_ly, slab_ly * sizeof(cplx<T>), tid,
+                                      P::COL_THREADS);
                 if (k == 0) {
                     F::pass_c(r.v, t, s1, tw);
                     LSTED_UNROLL
@@ -198,6 +201,12 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     for (int k = 0; k <= K; ++k) {
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
             LSTED_COL_IDS
+            if (k + 1 < K && !a.src_same)
+                prefetch_l2_range(src0 + (size_t)(k + 1) * img_ny, slab_ny * sizeof(cplx<T>), tid,
+                                  P::COL_THREADS);
+            if (k < K)   // product k happens at the start of the next phase
+                prefetch_l2_range(otf0 + (size_t)k * img_ly, slab_ly * sizeof(cplx<T>), tid,
+                                  P::COL_THREADS);
             if (k > 0) {
                 F::pass_c(r.v, t, s1, tw);
                 col_otf_product<P, true>(r, t, c, otf0 + (size_t)(k - 1) * img_ly, k == 1);
@@ -265,6 +274,28 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     cplx<T>* const s1 = smem + (size_t)(2 * f + 1) * P::LSM_ROW;  \
     (void)s0; (void)s1; (void)y; (void)live; (void)two;
 
+    // Software prefetch across CTAs: the operands of the row pairs that will be
+    // scheduled roughly one wave later are pulled into L2 now (spectra: one
+    // 2-row chunk per column block; measurement / normalisation rows: contiguous).
+    if (MODE == ROW_MID || MODE == ROW_FINAL) {
+        const int ahead = block + a.prefetch_ahead;
+        const int img2 = ahead / bpi;
+        const int pair2 = (ahead - img2 * bpi) * P::PR;
+        if (a.prefetch_ahead > 0 && img2 < a.nimg && pair2 < Py) {
+            const int y2 = 2 * pair2;
+            const int rows2 = (Ny - y2) < 2 * P::PR ? (Ny - y2) : 2 * P::PR;
+            const cplx<T>* sp = a.spec_in + (size_t)img2 * g.nxb * C * Ny + (size_t)y2 * C;
+            const T* ax = (MODE == ROW_MID ? a.aux + (size_t)img2 * Ny * Nx : a.aux) + (size_t)y2 * Nx;
+            cx.phase(regs, [&](int tid, RowRegs<P>& r) {
+                (void)r;
+                for (int xb = tid; xb < g.nxb; xb += P::ROW_THREADS) prefetch_l2(sp + (size_t)xb * xb_stride);
+                prefetch_l2_range(ax, (size_t)rows2 * Nx * sizeof(T), tid, P::ROW_THREADS);
+                if (MODE == ROW_FINAL)
+                    prefetch_l2_range(a.real_out + (size_t)y2 * Nx, (size_t)rows2 * Nx * sizeof(T), tid,
+                                      P::ROW_THREADS);
+            });
+        }
+    }
     if (MODE == ROW_FWD) {
         const T* src = a.real_in + real_off;
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {

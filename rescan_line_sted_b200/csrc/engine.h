@@ -258,6 +258,7 @@ template <typename T, class BK> class DeconvEngine {
         RowArgs<T> a;
         memset(&a, 0, sizeof(a));
         a.g = gg; a.tw = tw_x;
+        a.prefetch_ahead = bk.row_prefetch_distance();
         return a;
     }
     ColArgs<T> col_args(const ConvGeom& gg) {

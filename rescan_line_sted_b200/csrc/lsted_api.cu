@@ -260,6 +260,9 @@ class CudaBackend {
     }
     void set_profile(bool on) { profile_ = on; }
     void set_fast_path(bool on) { use_fast_ = on; }
+    // row CTAs resident at once (4 per SM): prefetch for the CTA one wave ahead
+    int row_prefetch_distance() const { return prefetch_ ? num_sms_ * 4 : 0; }
+    void set_prefetch(bool on) { prefetch_ = on; }
     void profile_reset() {
         profile_drain();
         memset(prof_ms_, 0, sizeof(prof_ms_));
@@ -429,6 +432,7 @@ class CudaBackend {
     cudaStream_t stream_;
     size_t bytes_;
     bool profile_, use_fast_;
+    bool prefetch_ = true;
     ncclComm_t comm_ = 0;
     cudaEvent_t t0_, t1_;
     int num_sms_;

@@ -50,6 +50,8 @@ class HostBackend {
   public:
     explicit HostBackend(int) : bytes_(0), use_fast_(true) {}
     void set_fast_path(bool on) { use_fast_ = on; }
+    int row_prefetch_distance() const { return 3; }
+    void set_prefetch(bool) {}
     static int fast_cols(int L, int cplx_bytes) {
         if (L == Plan2160f::L) return cplx_bytes == 8 ? (int)Plan2160f::C : (int)Plan2160d::C;
         return 0;
