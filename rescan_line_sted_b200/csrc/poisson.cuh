@@ -67,10 +67,11 @@ LSTED_HD double poisson_sample(double lam, unsigned long long seed, unsigned lon
             x += 1.0;
         }
     }
-    const double slam = sqrt(lam), loglam = log(lam);
+    // PTRS.  The squeeze `us >= 0.07 && V <= vr` accepts ~90 % of the attempts, so
+    // the logarithms (and invalpha) are evaluated only on the slow path.
+    const double slam = sqrt(lam);
     const double b = 0.931 + 2.53 * slam;
     const double aa = -0.059 + 0.02483 * b;
-    const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
     const double vr = 0.9277 - 3.6224 / (b - 2.0);
     for (uint32_t att = 0;; ++att) {
         const Philox4 r = philox4x32_10(c0, c1, image, att, k0, k1);
@@ -80,8 +81,9 @@ LSTED_HD double poisson_sample(double lam, unsigned long long seed, unsigned lon
         const double k = floor((2.0 * aa / us + b) * U + lam + 0.43);
         if (us >= 0.07 && V <= vr) return k;
         if (k < 0.0 || (us < 0.013 && V > us)) continue;
+        const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
         if (log(V) + log(invalpha) - log(aa / (us * us) + b) <=
-            -lam + k * loglam - lgamma(k + 1.0))
+            -lam + k * log(lam) - lgamma(k + 1.0))
             return k;
     }
 }
