@@ -52,6 +52,9 @@ struct DeviceCtx {
 };
 
 // Compile-time plans of the fast path (conv_fast.cuh): 2160 = 16 * 9 * 15.
+#ifndef LSTED_ROW_RESIDENT_THREADS
+#define LSTED_ROW_RESIDENT_THREADS 480
+#endif
 #ifndef LSTED_FAST_PR
 #define LSTED_FAST_PR 1
 #endif
@@ -59,7 +62,7 @@ typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, LSTED_FAST_PR> Plan2160f;
 typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 
 template <int MODE, class P>
-__global__ void __launch_bounds__(P::ROW_THREADS, sizeof(typename P::T) == 4 ? (640 / P::ROW_THREADS) : 1)
+__global__ void __launch_bounds__(P::ROW_THREADS, sizeof(typename P::T) == 4 ? (LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
 row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceCtx cx;
@@ -69,7 +72,7 @@ row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
 }
 
 template <int MODE, class P>
-__global__ void __launch_bounds__(P::COL_THREADS)
+__global__ void __launch_bounds__(P::COL_THREADS, 1)
 col_fast_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceCtx cx;
