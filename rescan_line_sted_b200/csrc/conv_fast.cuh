@@ -39,7 +39,8 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
         NTG = (NT_ + 31) / 32 * 32,
         LSM_ROW = (SEQ + 15) / 16 * 16 + 8,
         ROW_THREADS = NTG * PR_,
-        ROW_SMEM_ELEMS = 2 * PR_ * LSM_ROW,
+        // two ping-pong buffers + one staging buffer (2 measurement rows of <= L pixels) per pair
+        ROW_SMEM_ELEMS = 3 * PR_ * LSM_ROW,
         VREG = imax(Fwd::VREG, Inv::VREG),
         NKEEP = Fwd::MC * Fwd::RC,
         // Hermitian split: thread t owns bins t + q*NC; its mirror bins live in thread NC - t
@@ -270,9 +271,10 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     const bool live = pair < Py && t < P::NT;              \
     const int y = 2 * pair;                                \
     const bool two = y + 1 < Ny;                           \
-    cplx<T>* const s0 = smem + (size_t)(2 * f) * P::LSM_ROW;      \
-    cplx<T>* const s1 = smem + (size_t)(2 * f + 1) * P::LSM_ROW;  \
-    (void)s0; (void)s1; (void)y; (void)live; (void)two;
+    cplx<T>* const s0 = smem + (size_t)(3 * f) * P::LSM_ROW;      \
+    cplx<T>* const s1 = smem + (size_t)(3 * f + 1) * P::LSM_ROW;  \
+    T* const stage = (T*)(smem + (size_t)(3 * f + 2) * P::LSM_ROW); \
+    (void)s0; (void)s1; (void)stage; (void)y; (void)live; (void)two;
 
     // Software prefetch across CTAs: the operands of the row pairs that will be
     // scheduled roughly one wave later are pulled into L2 now (spectra: one
@@ -326,6 +328,13 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         const cplx<T>* src = a.spec_in + spec_off;
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
+            if (MODE == ROW_MID && pair < Py) {
+                // measurement rows y, y+1 -> shared memory, asynchronously (used after
+                // the inverse transform, two barriers from here)
+                const T* m0 = a.aux + real_off + (size_t)y * Nx;
+                async_copy_row(stage, m0, Nx, t, P::NTG);
+                if (two) async_copy_row(stage + P::L, m0 + Nx, Nx, t, P::NTG);
+            }
             if (!live) return;
             const cplx<T>* lo = src + ((size_t)(t / C) * Ny + y) * C + (t % C);
             const int tm = Lx - t;  // mirror of bin t; (tm - q*NC) is the mirror of bin t + q*NC
@@ -352,9 +361,11 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         });
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
-            if (!live) return;
-            I::load_b(r.v, t, s0, tw);
-            I::pass_b(r.v, t, s1);
+            if (live) {
+                I::load_b(r.v, t, s0, tw);
+                I::pass_b(r.v, t, s1);
+            }
+            if (MODE == ROW_MID) async_copy_wait_all();   // visible to the group after the barrier
         });
         // inverse pass C, the pointwise step on registers (logical position
         // idx = j + q*NC holds pixel idx - sx of rows y (re) and y+1 (im)) and the
@@ -367,9 +378,9 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             if (!live) return;
             // Issue every global load of the pointwise step up front (they overlap
             // pass C); the arithmetic comes afterwards.
-            cplx<T> pa[(MODE == ROW_MID || MODE == ROW_FINAL) ? I::MC * I::RC : 1];
+            cplx<T> pa[MODE == ROW_FINAL ? I::MC * I::RC : 1];
             cplx<T> pe[MODE == ROW_FINAL ? I::MC * I::RC : 1];
-            if (MODE == ROW_MID || MODE == ROW_FINAL) {
+            if (MODE == ROW_FINAL) {
                 LSTED_UNROLL
                 for (int m = 0; m < I::MC; ++m) {
                     const int j = t + m * P::NT;
@@ -411,9 +422,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                                 out[o] = clip0(z.x);       // noisy image: second loop below
                                 if (two) out[o + Nx] = clip0(z.y);
                             } else if (MODE == ROW_MID) {
-                                const cplx<T> mv = pa[m * I::RC + q];
-                                w.x = fast_div(mv.x, clip0(z.x));
-                                if (two) w.y = fast_div(mv.y, clip0(z.y));
+                                w.x = fast_div(stage[i], clip0(z.x));
+                                if (two) w.y = fast_div(stage[P::L + i], clip0(z.y));
                             } else {  // ROW_FINAL
                                 const cplx<T> nv = pa[m * I::RC + q], ev = pe[m * I::RC + q];
                                 w.x = ev.x * fast_div(clip0(z.x), nv.x);

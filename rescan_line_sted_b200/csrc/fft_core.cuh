@@ -79,6 +79,36 @@ LSTED_HD void prefetch_l2(const void* p) {
     (void)p;
 #endif
 }
+// Asynchronous global -> shared copies (LDGSTS / cp.async): no registers held while
+// the data is in flight.  `async_copy_row` spreads n elements over the threads of a
+// group, 16 bytes per request when source and destination allow it.
+template <typename T>
+LSTED_HD void async_copy_row(T* dst_smem, const T* src, int n, int tid, int nthreads) {
+#ifdef __CUDA_ARCH__
+    const int per16 = 16 / (int)sizeof(T);
+    const bool wide = ((((size_t)src) | ((size_t)dst_smem)) & 15) == 0 && (n % per16) == 0;
+    if (wide) {
+        for (int i = tid * per16; i < n; i += nthreads * per16) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem + i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i));
+        }
+    } else {
+        for (int i = tid; i < n; i += nthreads) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem + i);
+            if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src + i));
+            else                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + i));
+        }
+    }
+    asm volatile("cp.async.commit_group;");
+#else
+    for (int i = tid; i < n; i += nthreads) dst_smem[i] = src[i];
+#endif
+}
+LSTED_HD void async_copy_wait_all() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
 // `nthreads` threads sweep [p, p + bytes) in 128-byte lines
 LSTED_HD void prefetch_l2_range(const void* p, size_t bytes, int tid, int nthreads) {
     const char* c = (const char*)p;

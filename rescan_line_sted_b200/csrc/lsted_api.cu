@@ -53,7 +53,7 @@ struct DeviceCtx {
 
 // Compile-time plans of the fast path (conv_fast.cuh): 2160 = 16 * 9 * 15.
 #ifndef LSTED_ROW_RESIDENT_THREADS
-#define LSTED_ROW_RESIDENT_THREADS 480
+#define LSTED_ROW_RESIDENT_THREADS 480  // 3 row CTAs per SM: no register spills
 #endif
 #ifndef LSTED_FAST_PR
 #define LSTED_FAST_PR 1
