@@ -406,6 +406,16 @@ def main():
                 'durations of its 4 launches (col_h,row_mid,col_ht,row_final); the path is '
                 'FFT (FP32/SMEM) bound, not HBM bound: see DESIGN.md',
     }
+    # DRAM traffic of the same four launches from the committed ncu --set full capture
+    traffic_file = os.path.join(ROOT, 'profiles', 'r01_dram_traffic.json')
+    if (os.path.isfile(traffic_file) and args.precision == 'fp32' and N == 2048 and K_total == 16
+            and not by_orientation):
+        with open(traffic_file) as f:
+            t = json.load(f)
+        roofline['traffic'] = sum(t[k]['dram_bytes_read'] + t[k]['dram_bytes_write']
+                                  for k in ('col_h', 'row_mid', 'col_ht', 'row_final'))
+        roofline['traffic_source'] = t['_source']
+        roofline['algorithmic_bytes'] = (K + 4) * A
     roofline['frac'] = roofline['achieved'] / peak
     roofline['step_achieved'] = step_bytes / (ms_step * 1e-3) / 1e9
     roofline['step_frac'] = roofline['step_achieved'] / peak
