@@ -77,11 +77,19 @@ typedef struct {
     double bytes_forward;        /* (2K+1) A                                         */
     double bytes_normalization;  /* A                                                */
     double bytes_iteration;      /* (K+4) A                                          */
+    int tiles_y, tiles_x;        /* overlap-save tiling of large objects (1 x 1: none) */
+    int tile_out_y, tile_out_x;  /* pixels of the object each tile produces            */
 } lsted_deconv_info_t;
 
 /* Deconvolver.__init__ (:479-494): psfs = [K][ny][nx].  precision 32 | 64.          */
 int lsted_deconv_create(lsted_deconv** out, int device, const double* psfs, int K, int ny, int nx,
                         int Ny, int Nx, int precision);
+/* Same, with overlap-save tiling: the object is processed through windows of
+ * tile_fft_len^2 pixels (halo included) and may be arbitrarily large.  0 = decide
+ * automatically (lsted_deconv_create tiles with 2160 when one transform of the padded
+ * object does not fit a CTA's shared memory, e.g. 8192^2).                            */
+int lsted_deconv_create_tiled(lsted_deconv** out, int device, const double* psfs, int K, int ny,
+                              int nx, int Ny, int Nx, int precision, int tile_fft_len);
 int lsted_deconv_destroy(lsted_deconv* h);
 int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info);
 /* options: "exact_clip" (0|1: clip every H_t term before the sum, like :587),

@@ -35,7 +35,9 @@ class DeconvInfo(ctypes.Structure):
                 ('device_bytes', ctypes.c_size_t),
                 ('bytes_forward', ctypes.c_double),
                 ('bytes_normalization', ctypes.c_double),
-                ('bytes_iteration', ctypes.c_double)]
+                ('bytes_iteration', ctypes.c_double),
+                ('tiles_y', ctypes.c_int), ('tiles_x', ctypes.c_int),
+                ('tile_out_y', ctypes.c_int), ('tile_out_x', ctypes.c_int)]
 
 
 # name -> (argtypes); all return int status except the two noted below
@@ -44,6 +46,10 @@ _DECONV_SIGNATURES = {
                             c_double_p, ctypes.c_int, ctypes.c_int,
                             ctypes.c_int, ctypes.c_int, ctypes.c_int,
                             ctypes.c_int],
+    'lsted_deconv_create_tiled': [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                  c_double_p, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int],
     'lsted_deconv_destroy': [ctypes.c_void_p],
     'lsted_deconv_info': [ctypes.c_void_p, ctypes.POINTER(DeconvInfo)],
     'lsted_deconv_set_option': [ctypes.c_void_p, ctypes.c_char_p,
@@ -148,7 +154,8 @@ def bind_deconv_only(path):
 class DeconvHandle:
     """Thin RAII wrapper over lsted_deconv_* for one Deconvolver."""
 
-    def __init__(self, lib, psfs, image_shape, precision=32, device=0):
+    def __init__(self, lib, psfs, image_shape, precision=32, device=0,
+                 tile_fft_len=0):
         self.lib = lib
         psfs = np.ascontiguousarray(psfs, dtype=np.float64)
         assert psfs.ndim == 3
@@ -156,9 +163,9 @@ class DeconvHandle:
         self.Ny, self.Nx = int(image_shape[0]), int(image_shape[1])
         self.precision = precision
         self._h = ctypes.c_void_p()
-        lib.call('lsted_deconv_create', ctypes.byref(self._h), device,
+        lib.call('lsted_deconv_create_tiled', ctypes.byref(self._h), device,
                  psfs.ctypes.data_as(c_double_p), self.K, self.ny, self.nx,
-                 self.Ny, self.Nx, precision)
+                 self.Ny, self.Nx, precision, int(tile_fft_len))
 
     def close(self):
         if self._h:

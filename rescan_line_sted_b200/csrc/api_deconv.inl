@@ -7,8 +7,7 @@ struct lsted_deconv {
     int precision;
     int device;
     LSTED_BACKEND* bk;
-    lsted::DeconvEngine<float, LSTED_BACKEND>* e32;
-    lsted::DeconvEngine<double, LSTED_BACKEND>* e64;
+    lsted::EngineBase* e;
 };
 
 #define LSTED_TRY try {
@@ -17,30 +16,43 @@ struct lsted_deconv {
     catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }  \
     catch (const std::string& s) { return set_error(LSTED_ERR_ARG, s); }   \
     catch (const std::bad_alloc&) { return set_error(LSTED_ERR_ARG, "host allocation failed"); }
-#define LSTED_ENGINE(h, call)                  \
-    do {                                       \
-        (h)->bk->activate();                   \
-        if ((h)->precision == 32) (h)->e32->call; \
-        else (h)->e64->call;                   \
+#define LSTED_ENGINE(h, call)  \
+    do {                       \
+        (h)->bk->activate();   \
+        (h)->e->call;          \
     } while (0)
 
-extern "C" int lsted_deconv_create(lsted_deconv** out, int device, const double* psfs, int K, int ny,
-                                   int nx, int Ny, int Nx, int precision) {
+enum { kDefaultTileFftLen = 2160 };
+
+template <typename T>
+static lsted::EngineBase* make_engine(LSTED_BACKEND& bk, int K, int ny, int nx, int Ny, int Nx,
+                                      int tile_fft_len) {
+    if (tile_fft_len > 0)
+        return new lsted::TiledEngine<T, LSTED_BACKEND>(bk, K, ny, nx, Ny, Nx, tile_fft_len);
+    try {
+        return new lsted::DeconvEngine<T, LSTED_BACKEND>(bk, K, ny, nx, Ny, Nx);
+    } catch (const std::string& why) {
+        // too large for one shared-memory transform: overlap-save tiles
+        if (why.find("tile the object") == std::string::npos) throw;
+        return new lsted::TiledEngine<T, LSTED_BACKEND>(bk, K, ny, nx, Ny, Nx, kDefaultTileFftLen);
+    }
+}
+
+extern "C" int lsted_deconv_create_tiled(lsted_deconv** out, int device, const double* psfs, int K,
+                                         int ny, int nx, int Ny, int Nx, int precision,
+                                         int tile_fft_len) {
     if (!out || !psfs) return set_error(LSTED_ERR_ARG, "null pointer");
     if (precision != 32 && precision != 64) return set_error(LSTED_ERR_ARG, "precision must be 32 or 64");
     if (K < 1) return set_error(LSTED_ERR_ARG, "need at least one PSF");
+    if (tile_fft_len < 0) return set_error(LSTED_ERR_ARG, "negative tile FFT length");
     lsted_deconv* h = new lsted_deconv();
-    h->precision = precision; h->device = device; h->bk = 0; h->e32 = 0; h->e64 = 0;
+    h->precision = precision; h->device = device; h->bk = 0; h->e = 0;
     LSTED_TRY
     h->bk = new LSTED_BACKEND(device);
     h->bk->activate();
-    if (precision == 32) {
-        h->e32 = new lsted::DeconvEngine<float, LSTED_BACKEND>(*h->bk, K, ny, nx, Ny, Nx);
-        h->e32->set_psfs(psfs);
-    } else {
-        h->e64 = new lsted::DeconvEngine<double, LSTED_BACKEND>(*h->bk, K, ny, nx, Ny, Nx);
-        h->e64->set_psfs(psfs);
-    }
+    h->e = precision == 32 ? make_engine<float>(*h->bk, K, ny, nx, Ny, Nx, tile_fft_len)
+                           : make_engine<double>(*h->bk, K, ny, nx, Ny, Nx, tile_fft_len);
+    h->e->set_psfs(psfs);
     *out = h;
     return LSTED_OK;
     }
@@ -48,12 +60,16 @@ extern "C" int lsted_deconv_create(lsted_deconv** out, int device, const double*
     catch (const std::string& s) { lsted_deconv_destroy(h); return set_error(LSTED_ERR_ARG, s); }
 }
 
+extern "C" int lsted_deconv_create(lsted_deconv** out, int device, const double* psfs, int K, int ny,
+                                   int nx, int Ny, int Nx, int precision) {
+    return lsted_deconv_create_tiled(out, device, psfs, K, ny, nx, Ny, Nx, precision, 0);
+}
+
 extern "C" int lsted_deconv_destroy(lsted_deconv* h) {
     if (!h) return LSTED_OK;
     try {
         if (h->bk) h->bk->activate();
-        delete h->e32;
-        delete h->e64;
+        delete h->e;
         delete h->bk;
     } catch (...) {}
     delete h;
@@ -63,37 +79,35 @@ extern "C" int lsted_deconv_destroy(lsted_deconv* h) {
 extern "C" int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info) {
     if (!h || !info) return set_error(LSTED_ERR_ARG, "null pointer");
     memset(info, 0, sizeof(*info));
-    const lsted::ConvGeom& g = h->precision == 32 ? h->e32->g : h->e64->g;
-    const int K = h->precision == 32 ? h->e32->K : h->e64->K;
+    lsted::EngineInfo ei;
+    h->e->info(&ei);
     const int cb = h->precision == 32 ? 8 : 16;
-    info->K = K;
-    info->ny = h->precision == 32 ? h->e32->ny : h->e64->ny;
-    info->nx = h->precision == 32 ? h->e32->nx : h->e64->nx;
-    info->Ny = g.Ny; info->Nx = g.Nx; info->Ly = g.Ly; info->Lx = g.Lx;
-    info->cols_per_cta = g.C; info->row_pairs_per_cta = g.PR;
+    info->K = ei.K; info->ny = ei.ny; info->nx = ei.nx;
+    info->Ny = ei.Ny; info->Nx = ei.Nx; info->Ly = ei.Ly; info->Lx = ei.Lx;
+    info->cols_per_cta = ei.C; info->row_pairs_per_cta = ei.PR;
     info->precision = h->precision;
-    info->iterations_done = h->precision == 32 ? h->e32->iterations_done : h->e64->iterations_done;
+    info->iterations_done = ei.iterations_done;
     info->device = h->device;
-    info->row_smem_bytes = lsted::row_smem_bytes(g, cb);
-    info->col_smem_bytes = lsted::col_smem_bytes(g, cb);
+    info->row_smem_bytes = ei.row_smem;
+    info->col_smem_bytes = ei.col_smem;
     info->device_bytes = h->bk->bytes_allocated();
-    const double A = (double)(cb / 2) * g.Ny * g.Nx;
-    info->bytes_forward = (2.0 * K + 1.0) * A;
+    const double A = (double)(cb / 2) * ei.Ny * ei.Nx;
+    info->bytes_forward = (2.0 * ei.K + 1.0) * A;
     info->bytes_normalization = A;
-    info->bytes_iteration = (K + 4.0) * A;
+    info->bytes_iteration = (ei.K + 4.0) * A;
+    info->tiles_y = ei.tiles_y; info->tiles_x = ei.tiles_x;
+    info->tile_out_y = ei.tile_out_y; info->tile_out_x = ei.tile_out_x;
     return LSTED_OK;
 }
 
 extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double value) {
     if (!h || !name) return set_error(LSTED_ERR_ARG, "null pointer");
     if (!strcmp(name, "exact_clip")) {
-        if (h->precision == 32) h->e32->exact_clip = value != 0;
-        else h->e64->exact_clip = value != 0;
+        h->e->set_exact_clip(value != 0);
         return LSTED_OK;
     }
     if (!strcmp(name, "forget_normalization")) {
-        if (h->precision == 32) h->e32->forget_normalization();
-        else h->e64->forget_normalization();
+        h->e->forget_normalization();
         return LSTED_OK;
     }
     if (!strcmp(name, "prefetch")) { h->bk->set_prefetch(value != 0); return LSTED_OK; }
@@ -137,8 +151,7 @@ extern "C" int lsted_deconv_shard(lsted_deconv* h, int rank, int world, int k_of
     LSTED_TRY
     h->bk->activate();
     if (world > 1) h->bk->comm_init(unique_id, rank, world);
-    if (h->precision == 32) h->e32->set_sharding(rank, world, k_offset);
-    else h->e64->set_sharding(rank, world, k_offset);
+    h->e->set_sharding(rank, world, k_offset);
     return LSTED_OK;
     LSTED_CATCH
 }
@@ -152,7 +165,9 @@ extern "C" int lsted_deconv_iterate(lsted_deconv* h, int n) {
 }
 
 static int check_which(lsted_deconv* h, int which, int k) {
-    const int K = h->precision == 32 ? h->e32->K : h->e64->K;
+    lsted::EngineInfo ei;
+    h->e->info(&ei);
+    const int K = ei.K;
     if (which < 0 || which > 4) return 1;
     if ((which == LSTED_NOISELESS || which == LSTED_NOISY) ? (k < 0 || k >= K) : (k != 0)) return 1;
     return 0;

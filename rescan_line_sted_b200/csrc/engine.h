@@ -23,7 +23,32 @@ enum ArrayId {
     ARR_NORMALIZATION = 4
 };
 
-template <typename T, class BK> class DeconvEngine {
+// Precision-independent face of an engine: what the C ABI talks to.
+struct EngineInfo {
+    int K, ny, nx, Ny, Nx, Ly, Lx, C, PR, iterations_done;
+    size_t row_smem, col_smem;
+    int tiles_y, tiles_x, tile_out_y, tile_out_x;   // 1 x 1 unless the object is tiled
+};
+class EngineBase {
+  public:
+    virtual ~EngineBase() {}
+    virtual void set_psfs(const double* psfs_host) = 0;
+    virtual void upload_object(const double* obj_host) = 0;
+    virtual void simulate(double total_brightness, bool rescale, unsigned long long seed) = 0;
+    virtual void create_data(const double* obj_host, double total_brightness, bool rescale,
+                             unsigned long long seed) = 0;
+    virtual void iterate(int n) = 0;
+    virtual void get_array(int id, int k, double* host) = 0;
+    virtual void set_array(int id, int k, const double* host) = 0;
+    virtual void H_host(const double* x, double* out) = 0;
+    virtual void Ht_host(const double* y, double* out, bool normalize) = 0;
+    virtual void forget_normalization() = 0;
+    virtual void set_sharding(int rank, int world, int k_offset) = 0;
+    virtual void set_exact_clip(bool on) = 0;
+    virtual void info(EngineInfo* out) = 0;
+};
+
+template <typename T, class BK> class DeconvEngine : public EngineBase {
   public:
     ConvGeom g;
     int K, ny, nx;
@@ -31,10 +56,10 @@ template <typename T, class BK> class DeconvEngine {
     bool have_norm, have_estimate, exact_clip;
     int rank, world, k_offset;
 
-    DeconvEngine(BK& backend, int K_, int ny_, int nx_, int Ny, int Nx)
+    DeconvEngine(BK& backend, int K_, int ny_, int nx_, int Ny, int Nx, int force_L = 0)
         : K(K_), ny(ny_), nx(nx_), iterations_done(0), have_norm(false), have_estimate(false),
           exact_clip(false), rank(0), world(1), k_offset(0), bk(backend), tmpK(0) {
-        const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g, &BK::fast_cols);
+        const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g, &BK::fast_cols, force_L);
         if (why[0]) throw std::string(why);
         npix = (size_t)Ny * Nx;
         std::vector<cplx<T> > tw;
@@ -64,6 +89,15 @@ template <typename T, class BK> class DeconvEngine {
     }
 
     size_t pixels() const { return npix; }
+    void set_exact_clip(bool on) { exact_clip = on; }
+    void info(EngineInfo* o) {
+        memset(o, 0, sizeof(*o));
+        o->K = K; o->ny = ny; o->nx = nx; o->Ny = g.Ny; o->Nx = g.Nx; o->Ly = g.Ly; o->Lx = g.Lx;
+        o->C = g.C; o->PR = g.PR; o->iterations_done = iterations_done;
+        o->row_smem = row_smem_bytes(g, (int)sizeof(cplx<T>));
+        o->col_smem = col_smem_bytes(g, (int)sizeof(cplx<T>));
+        o->tiles_y = o->tiles_x = 1; o->tile_out_y = g.Ny; o->tile_out_x = g.Nx;
+    }
 
     // K7: PSFs (host, float64, [K][ny][nx]) -> OTFs, 1/(Lx*Ly) folded in.
     void set_psfs(const double* psfs_host) {

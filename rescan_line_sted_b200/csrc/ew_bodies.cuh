@@ -26,3 +26,56 @@ template <int OP, typename T> LSTED_HD void ew_apply(const EwArgs<T>& a, size_t 
 }
 
 }  // namespace lsted
+
+// ---------------------------------------------------------------------------
+// Window kernels of the tiled (overlap-save) engine: move data between the full
+// image arrays and one tile window of W x W pixels whose top-left corner sits at
+// (y0, x0) of the image (may be negative / past the edge: zero padding, like the
+// linear convolution of the reference).  Only the alias-free interior
+// [iy0, iy1) x [ix0, ix1) of a window is ever written back.
+// ---------------------------------------------------------------------------
+#include "poisson.cuh"
+namespace lsted {
+
+enum WinOp {
+    WIN_LOAD = 0,     // tile = window of big (zero outside the image)
+    WIN_ONES = 1,     // tile = 1 inside the image, 0 outside
+    WIN_STORE = 2,    // big[interior] = tile
+    WIN_SIMULATE = 3, // big[interior] = tile (noiseless); big2[interior] = Poisson(tile) + 1e-9
+    WIN_RATIO = 4,    // big[interior] = big2[interior] / tile      (ratio = measurement / expected)
+    WIN_UPDATE = 5    // big[interior] *= tile / big2[interior]     (estimate *= H_t(ratio) / norm)
+};
+
+template <typename T> struct WinArgs {
+    T* tile;          // [nimg][W][W]
+    T* big;           // [nimg][Ny][Nx]
+    T* big2;
+    int nimg, W, Ny, Nx;
+    int y0, x0;       // image coordinates of tile pixel (0, 0)
+    int iy0, iy1, ix0, ix1;  // interior of the window (tile coordinates)
+    unsigned long long seed;
+    unsigned int img0;
+};
+
+template <int OP, typename T> LSTED_HD void win_apply(const WinArgs<T>& a, size_t e) {
+    const size_t per = (size_t)a.W * a.W;
+    const int img = (int)(e / per);
+    const size_t r = e - (size_t)img * per;
+    const int wy = (int)(r / a.W), wx = (int)(r - (size_t)wy * a.W);
+    const int gy = a.y0 + wy, gx = a.x0 + wx;
+    const bool inside = gy >= 0 && gy < a.Ny && gx >= 0 && gx < a.Nx;
+    const size_t gi = (size_t)img * a.Ny * a.Nx + (size_t)(inside ? gy : 0) * a.Nx + (inside ? gx : 0);
+    if (OP == WIN_LOAD) { a.tile[e] = inside ? a.big[gi] : (T)0; return; }
+    if (OP == WIN_ONES) { a.tile[e] = inside ? (T)1 : (T)0; return; }
+    if (!inside || wy < a.iy0 || wy >= a.iy1 || wx < a.ix0 || wx >= a.ix1) return;
+    const T v = a.tile[e];
+    if (OP == WIN_STORE) a.big[gi] = v;
+    else if (OP == WIN_SIMULATE) {
+        a.big[gi] = v;
+        const unsigned long long pix = (unsigned long long)gy * a.Nx + gx;
+        a.big2[gi] = (T)(poisson_sample((double)v, a.seed, pix, a.img0 + img) + 1e-9);
+    } else if (OP == WIN_RATIO) a.big[gi] = a.big2[gi] / v;
+    else if (OP == WIN_UPDATE) a.big[gi] = a.big[gi] * (v / a.big2[gi]);
+}
+
+}  // namespace lsted

@@ -14,6 +14,7 @@
 
 #include "../../include/lsted.h"
 #include "engine.h"
+#include "tiled.h"
 #include "conv_fast.cuh"
 #include "ew_bodies.cuh"
 #include "psf_kernels.cuh"
@@ -104,6 +105,14 @@ __global__ void __launch_bounds__(kEwThreads) ew_kernel(const lsted::EwArgs<T> a
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
         lsted::ew_apply<OP, T>(a, i);
+}
+
+template <int OP, typename T>
+__global__ void __launch_bounds__(kEwThreads) win_kernel(const lsted::WinArgs<T> a) {
+    const size_t n = (size_t)a.nimg * a.W * a.W;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+        lsted::win_apply<OP, T>(a, e);
 }
 
 // Two-stage deterministic sum in double: per-block partials, then block 0.
@@ -397,6 +406,16 @@ class CudaBackend {
         if (blocks > cap) blocks = cap;
         before(KK_EW);
         ew_kernel<OP, T><<<(int)blocks, kEwThreads, 0, stream_>>>(a);
+        after();
+    }
+    template <int OP, typename T> void launch_win(const lsted::WinArgs<T>& a) {
+        const size_t n = (size_t)a.nimg * a.W * a.W;
+        if (n == 0) return;
+        size_t blocks = (n + kEwThreads - 1) / kEwThreads;
+        const size_t cap = (size_t)num_sms_ * 16;
+        if (blocks > cap) blocks = cap;
+        before(KK_EW);
+        win_kernel<OP, T><<<(int)blocks, kEwThreads, 0, stream_>>>(a);
         after();
     }
     template <typename T> void cast_in(T* dst, const double* src, size_t n, double s) {

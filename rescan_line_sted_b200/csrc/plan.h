@@ -68,8 +68,10 @@ inline int smem_pitch(int L, int elem_bytes, int C) {
 // `fast_C(L)` > 0 means the backend has a compile-time plan for column length L
 // that wants C columns per block (it then needs only the generic OTF kernel to
 // fit: two buffers instead of three).
+// `force_L` > 0 pins both transform lengths (overlap-save tiles: the window is as
+// long as the transform, only its interior is alias-free and only that is kept).
 inline const char* make_geom(int Ny, int Nx, int ny, int nx, int cplx_bytes, ConvGeom* g,
-                             int (*fast_C)(int L, int cplx_bytes) = 0) {
+                             int (*fast_C)(int L, int cplx_bytes) = 0, int force_L = 0) {
     memset(g, 0, sizeof(*g));
     if (Ny < 1 || Nx < 1 || ny < 1 || nx < 1) return "empty image or PSF";
     g->Ny = Ny; g->Nx = Nx;
@@ -80,6 +82,10 @@ inline const char* make_geom(int Ny, int Nx, int ny, int nx, int cplx_bytes, Con
     g->Lx = next_smooth_len(Nx + hx);
     if (g->Ly < ny) g->Ly = next_smooth_len(ny);  // the whole PSF must fit
     if (g->Lx < nx) g->Lx = next_smooth_len(nx);
+    if (force_L > 0) {
+        if (force_L < Ny || force_L < Nx || force_L < ny || force_L < nx) return "forced FFT length too short";
+        g->Ly = g->Lx = force_L;
+    }
     if (!make_fft_plan(g->Ly, &g->py) || !make_fft_plan(g->Lx, &g->px)) return "no FFT plan";
     g->Lxh = g->Lx / 2 + 1;
     g->C = cplx_bytes == 8 ? 4 : 2;

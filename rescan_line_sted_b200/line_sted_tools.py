@@ -14,6 +14,8 @@ Backend switches (environment, read at call time; signatures unchanged):
   LSTED_DEVICE      CUDA device ordinal (default 0)
   LSTED_EXACT_CLIP  1 -> clip every H_t term before summing (ref:587) instead
                     of summing in the Fourier domain and clipping once
+  LSTED_TILE_FFT    FFT length of overlap-save tiles (0/unset: tile only when the
+                    padded object does not fit one shared-memory transform)
 """
 import os
 import time
@@ -420,7 +422,8 @@ class Deconvolver:
                 self._handle.close()
             self._handle = _lib.DeconvHandle(
                 _lib.get(), _stack_psfs(self.psfs), shape[1:],
-                precision=_precision(), device=_device())
+                precision=_precision(), device=_device(),
+                tile_fft_len=int(os.environ.get('LSTED_TILE_FFT', '0') or 0))
             if os.environ.get('LSTED_EXACT_CLIP', '0') not in ('', '0'):
                 self._handle.set_option('exact_clip', 1)
             self._shape = shape

@@ -14,6 +14,7 @@
 #include <vector>
 #include "../../include/lsted.h"
 #include "../../rescan_line_sted_b200/csrc/engine.h"
+#include "../../rescan_line_sted_b200/csrc/tiled.h"
 #include "../../rescan_line_sted_b200/csrc/conv_fast.cuh"
 #include "../../rescan_line_sted_b200/csrc/ew_bodies.cuh"
 #include "../../rescan_line_sted_b200/csrc/psf_kernels.cuh"
@@ -132,6 +133,10 @@ class HostBackend {
     }
     template <int OP, typename T> void ew(const lsted::EwArgs<T>& a) {
         for (size_t i = 0; i < a.n; ++i) lsted::ew_apply<OP, T>(a, i);
+    }
+    template <int OP, typename T> void launch_win(const lsted::WinArgs<T>& a) {
+        const size_t n = (size_t)a.nimg * a.W * a.W;
+        for (size_t e = 0; e < n; ++e) lsted::win_apply<OP, T>(a, e);
     }
     template <typename T> void cast_in(T* dst, const double* src, size_t n, double s) {
         lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = dst; a.d1 = src; a.s = s; a.n = n;
