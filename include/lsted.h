@@ -79,6 +79,7 @@ typedef struct {
     double bytes_iteration;      /* (K+4) A                                          */
     int tiles_y, tiles_x;        /* overlap-save tiling of large objects (1 x 1: none) */
     int tile_out_y, tile_out_x;  /* pixels of the object each tile produces            */
+    int band_y0, band_y1;        /* image rows owned by this rank (tiled + sharded)    */
 } lsted_deconv_info_t;
 
 /* Deconvolver.__init__ (:479-494): psfs = [K][ny][nx].  precision 32 | 64.          */
@@ -113,7 +114,12 @@ int lsted_deconv_simulate(lsted_deconv* h, double total_brightness, int rescale,
  * are combined by ONE ncclAllReduce per RL iteration (of the Fourier-domain partial sum)
  * on the handle's stream.  `unique_id` = the 128 bytes lsted_nccl_unique_id() produced
  * on rank 0, distributed by the caller (e.g. torch.distributed broadcast).  NCCL is
- * dlopen()ed on first use; single-GPU users do not need it.                          */
+ * dlopen()ed on first use; single-GPU users do not need it.
+ * A TILED handle (lsted_deconv_create_tiled) shards differently: every rank gets ALL
+ * PSFs and owns a horizontal band of the object (k_offset is ignored); measurements and
+ * ratios live on the band plus the PSF halo (recomputed redundantly, identical noise
+ * because the Poisson stream is keyed by the global pixel index) and the only exchange
+ * is one ncclBroadcast of each band of the replicated estimate per RL iteration.      */
 enum { LSTED_NCCL_UNIQUE_ID_BYTES = 128 };
 int lsted_nccl_unique_id(char* out);
 int lsted_deconv_shard(lsted_deconv* h, int rank, int world, int k_offset, const char* unique_id);

@@ -37,7 +37,8 @@ class DeconvInfo(ctypes.Structure):
                 ('bytes_normalization', ctypes.c_double),
                 ('bytes_iteration', ctypes.c_double),
                 ('tiles_y', ctypes.c_int), ('tiles_x', ctypes.c_int),
-                ('tile_out_y', ctypes.c_int), ('tile_out_x', ctypes.c_int)]
+                ('tile_out_y', ctypes.c_int), ('tile_out_x', ctypes.c_int),
+                ('band_y0', ctypes.c_int), ('band_y1', ctypes.c_int)]
 
 
 # name -> (argtypes); all return int status except the two noted below

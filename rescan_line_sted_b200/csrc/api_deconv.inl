@@ -97,6 +97,7 @@ extern "C" int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info) {
     info->bytes_iteration = (ei.K + 4.0) * A;
     info->tiles_y = ei.tiles_y; info->tiles_x = ei.tiles_x;
     info->tile_out_y = ei.tile_out_y; info->tile_out_x = ei.tile_out_x;
+    info->band_y0 = ei.band_y0; info->band_y1 = ei.band_y1;
     return LSTED_OK;
 }
 

@@ -28,6 +28,7 @@ struct EngineInfo {
     int K, ny, nx, Ny, Nx, Ly, Lx, C, PR, iterations_done;
     size_t row_smem, col_smem;
     int tiles_y, tiles_x, tile_out_y, tile_out_x;   // 1 x 1 unless the object is tiled
+    int band_y0, band_y1;                           // image rows owned by this rank (tiled + sharded)
 };
 class EngineBase {
   public:
@@ -97,6 +98,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         o->row_smem = row_smem_bytes(g, (int)sizeof(cplx<T>));
         o->col_smem = col_smem_bytes(g, (int)sizeof(cplx<T>));
         o->tiles_y = o->tiles_x = 1; o->tile_out_y = g.Ny; o->tile_out_x = g.Nx;
+        o->band_y0 = 0; o->band_y1 = g.Ny;
     }
 
     // K7: PSFs (host, float64, [K][ny][nx]) -> OTFs, 1/(Lx*Ly) folded in.

@@ -53,6 +53,8 @@ template <typename T> struct WinArgs {
     int nimg, W, Ny, Nx;
     int y0, x0;       // image coordinates of tile pixel (0, 0)
     int iy0, iy1, ix0, ix1;  // interior of the window (tile coordinates)
+    int by0, brows;   // the big arrays hold image rows [by0, by0 + brows) (a band of a sharded object)
+    int sy0, sy1;     // only image rows [sy0, sy1) are written back
     unsigned long long seed;
     unsigned int img0;
 };
@@ -64,10 +66,12 @@ template <int OP, typename T> LSTED_HD void win_apply(const WinArgs<T>& a, size_
     const int wy = (int)(r / a.W), wx = (int)(r - (size_t)wy * a.W);
     const int gy = a.y0 + wy, gx = a.x0 + wx;
     const bool inside = gy >= 0 && gy < a.Ny && gx >= 0 && gx < a.Nx;
-    const size_t gi = (size_t)img * a.Ny * a.Nx + (size_t)(inside ? gy : 0) * a.Nx + (inside ? gx : 0);
-    if (OP == WIN_LOAD) { a.tile[e] = inside ? a.big[gi] : (T)0; return; }
+    const bool held = inside && gy >= a.by0 && gy < a.by0 + a.brows;   // row present in `big`
+    const size_t gi = (size_t)img * a.brows * a.Nx + (size_t)(held ? gy - a.by0 : 0) * a.Nx + (held ? gx : 0);
+    if (OP == WIN_LOAD) { a.tile[e] = held ? a.big[gi] : (T)0; return; }
     if (OP == WIN_ONES) { a.tile[e] = inside ? (T)1 : (T)0; return; }
-    if (!inside || wy < a.iy0 || wy >= a.iy1 || wx < a.ix0 || wx >= a.ix1) return;
+    if (!held || gy < a.sy0 || gy >= a.sy1 || wy < a.iy0 || wy >= a.iy1 || wx < a.ix0 || wx >= a.ix1)
+        return;
     const T v = a.tile[e];
     if (OP == WIN_STORE) a.big[gi] = v;
     else if (OP == WIN_SIMULATE) {

@@ -150,12 +150,13 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t);
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*CommDestroy)(ncclComm_t);
     const char* (*GetErrorString)(ncclResult_t);
     bool ok;
 };
 static NcclApi& nccl_api() {
-    static NcclApi api = {0, 0, 0, 0, 0, false};
+    static NcclApi api = {0, 0, 0, 0, 0, 0, false};
     if (api.ok) return api;
     void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -168,9 +169,11 @@ static NcclApi& nccl_api() {
     api.CommInitRank = (ncclResult_t(*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
     api.AllReduce = (ncclResult_t(*)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                                      cudaStream_t))dlsym(lib, "ncclAllReduce");
+    api.Broadcast = (ncclResult_t(*)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t,
+                                     cudaStream_t))dlsym(lib, "ncclBroadcast");
     api.CommDestroy = (ncclResult_t(*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
     api.GetErrorString = (const char* (*)(ncclResult_t))dlsym(lib, "ncclGetErrorString");
-    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString) {
+    if (!api.Broadcast || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString) {
         lsted::ApiError e; e.code = LSTED_ERR_NCCL; e.msg = "libnccl lacks a required symbol";
         throw e;
     }
@@ -242,6 +245,20 @@ class CudaBackend {
         before(KK_EW);
         NCCL_CHECK(nccl_api().AllReduce(p, p, n, ncclDouble, ncclSum, comm_, stream_));
         after();
+    }
+    void broadcast(float* p, size_t n, int root) {
+        before(KK_EW);
+        NCCL_CHECK(nccl_api().Broadcast(p, p, n, ncclFloat, root, comm_, stream_));
+        after();
+    }
+    void broadcast(double* p, size_t n, int root) {
+        before(KK_EW);
+        NCCL_CHECK(nccl_api().Broadcast(p, p, n, ncclDouble, root, comm_, stream_));
+        after();
+    }
+    void fill_double(double* p, size_t n, double v) {
+        if (v != 0.0) { lsted::ApiError e; e.code = LSTED_ERR_ARG; e.msg = "fill_double: zero only"; throw e; }
+        CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(double), stream_));
     }
     cudaStream_t stream() const { return stream_; }
 

@@ -95,3 +95,50 @@ class OrientationShardedDeconvolver:
 
     def close(self):
         self.handle.close()
+
+
+class TileShardedDeconvolver:
+    """A large object processed in overlap-save tiles with the image rows split
+    into one horizontal band per rank (BASELINE config 5).  Every rank passes
+    the same PSFs, object and seed; measurements and ratios exist only on the
+    rank's band (plus the PSF halo, recomputed redundantly), the estimate is a
+    replica refreshed by one NCCL broadcast per band per RL iteration."""
+
+    def __init__(self, psfs, image_shape, precision=64, device=0, group=None,
+                 lib=None, tile_fft_len=2160):
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        lib = lib or _lib.get()
+        self.handle = _lib.DeconvHandle(lib, psfs, image_shape, precision=precision,
+                                        device=device, tile_fft_len=tile_fft_len)
+        unique_id = [None]
+        if self.world > 1:
+            if self.rank == 0:
+                unique_id[0] = _lib.nccl_unique_id(lib)
+            dist.broadcast_object_list(unique_id, src=0, group=group)
+        self.handle.shard(self.rank, self.world, 0, unique_id[0])
+        info = self.handle.info()
+        self.rows = (info.band_y0, info.band_y1)
+
+    def create_data(self, obj, total_brightness, seed):
+        self.handle.create_data(obj, total_brightness, seed)
+
+    def set_noisy(self, k, image):
+        """Full-size image; the rank keeps the rows of its band."""
+        self.handle.set(_lib.NOISY, k, image)
+
+    def iterate(self, n=1):
+        self.handle.iterate(n)
+
+    @property
+    def estimate(self):
+        return self.handle.get(_lib.ESTIMATE)
+
+    def local_measurement(self, k, which=_lib.NOISY):
+        """Rows of the band (and its halo); zeros elsewhere."""
+        return self.handle.get(which, k)
+
+    def close(self):
+        self.handle.close()

@@ -32,6 +32,13 @@ def main():
 
     lib.cdll.emul_set_allreduce(allreduce)
 
+    @ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_double), ctypes.c_size_t, ctypes.c_int)
+    def broadcast(buf, n, root):
+        arr = np.ctypeslib.as_array(buf, shape=(n,))
+        dist.broadcast(torch.from_numpy(arr), src=root)
+
+    lib.cdll.emul_set_broadcast(broadcast)
+
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'fig2_2p0x_lr.npz'))
     out = {}
     for precision, tag in ((64, 'fp64'), (32, 'fp32')):
@@ -57,6 +64,23 @@ def main():
         out[tag] = {'noiseless': err_nl, 'est1': e1, 'norm': en, 'est8': e8,
                     'replica_diff': float((t - ref).abs().max())}
         d.close()
+    # tiled object sharded into row bands (config-5 style), against one unsharded handle
+    rng = np.random.default_rng(4)
+    psfs = rng.random((3, 9, 11))
+    obj = rng.random((1, 150, 170))
+    single = _lib.DeconvHandle(lib, psfs, (150, 170), precision=64)
+    single.create_data(obj, 1e7, 9)
+    single.iterate(4)
+    t = sharded.TileShardedDeconvolver(psfs, (150, 170), precision=64, lib=lib, tile_fft_len=64)
+    t.create_data(obj, 1e7, 9)
+    a, b = t.rows
+    noisy_same = all(np.array_equal(t.local_measurement(k)[0, a:b], single.get(_lib.NOISY, k)[0, a:b])
+                     for k in range(3))
+    t.iterate(4)
+    est = single.get(_lib.ESTIMATE)
+    out['tiles'] = {'rows': [int(a), int(b)], 'noisy_same': bool(noisy_same),
+                    'est': float(np.linalg.norm(t.estimate - est) / np.linalg.norm(est))}
+    t.close(), single.close()
     # sweep sharding: 6 operating points dealt round-robin, gathered in order
     exc = [0.1, 0.5, 1, 2, 4, 8]
     dep = [1, 3, 9, 27, 54, 81]

@@ -44,6 +44,24 @@ def main():
         out[tag]['noise_independent_of_world'] = bool(same)
         single.close()
         d.close()
+    # tiled object, row bands over the GPUs, 2160-point tiles (fast path), fp64
+    rng = np.random.default_rng(4)
+    psfs = rng.random((2, 9, 11))
+    obj = rng.random((1, 2300, 2200))
+    single = _lib.DeconvHandle(_lib.get(), psfs, (2300, 2200), precision=64, device=local,
+                               tile_fft_len=2160)
+    single.create_data(obj, 1e9, 9)
+    single.iterate(2)
+    t = sharded.TileShardedDeconvolver(psfs, (2300, 2200), precision=64, device=local)
+    t.create_data(obj, 1e9, 9)
+    a, b = t.rows
+    same = all(np.array_equal(t.local_measurement(k)[0, a:b], single.get(_lib.NOISY, k)[0, a:b])
+               for k in range(2))
+    t.iterate(2)
+    est = single.get(_lib.ESTIMATE)
+    out['tiles'] = {'noisy_same': bool(same),
+                    'est': float(np.linalg.norm(t.estimate - est) / np.linalg.norm(est))}
+    t.close(), single.close()
     if rank == 0:
         with open(sys.argv[1], 'w') as f:
             json.dump(out, f)

@@ -44,8 +44,11 @@ template <> struct PlanFor<float> { typedef Plan2160f type; };
 template <> struct PlanFor<double> { typedef Plan2160d type; };
 
 typedef void (*allreduce_cb)(double* buf, size_t n);
+typedef void (*broadcast_cb)(double* buf, size_t n, int root);
 static allreduce_cb g_allreduce = 0;
+static broadcast_cb g_broadcast = 0;
 extern "C" void emul_set_allreduce(allreduce_cb cb) { g_allreduce = cb; }
+extern "C" void emul_set_broadcast(broadcast_cb cb) { g_broadcast = cb; }
 
 class HostBackend {
   public:
@@ -75,6 +78,16 @@ class HostBackend {
         all_reduce_sum(tmp.data(), n);
         for (size_t i = 0; i < n; ++i) p[i] = (float)tmp[i];
     }
+    void broadcast(double* p, size_t n, int root) {
+        if (!g_broadcast) throw std::string("no broadcast callback installed");
+        g_broadcast(p, n, root);
+    }
+    void broadcast(float* p, size_t n, int root) {
+        std::vector<double> tmp(p, p + n);
+        broadcast(tmp.data(), n, root);
+        for (size_t i = 0; i < n; ++i) p[i] = (float)tmp[i];
+    }
+    void fill_double(double* p, size_t n, double v) { for (size_t i = 0; i < n; ++i) p[i] = v; }
     void set_profile(bool) {}
     void timer_start() {}
     float timer_stop() { return 0.f; }

@@ -48,6 +48,8 @@ def test_world_size_2_gloo(tmp_path):
     assert r['fp64']['est1'] < 1e-12 and r['fp64']['est8'] < 1e-11
     assert r['fp32']['noiseless'] < 1e-5 and r['fp32']['est1'] < 1e-5 and r['fp32']['est8'] < 1e-4
     assert r['fp64']['replica_diff'] == 0.0 and r['fp32']['replica_diff'] == 0.0
+    assert r['tiles']['rows'] == [0, 75] and r['tiles']['noisy_same']
+    assert r['tiles']['est'] < 1e-11
     exc = [0.1, 0.5, 1, 2, 4, 8]
     dep = [1, 3, 9, 27, 54, 81]
     want = [orc.psf_report('line', e, d, 8, 1, use_closed_form=True)['expected_emission']

@@ -34,6 +34,7 @@ def test_orientation_sharding_nccl(tmp_path):
         r = json.load(f)
     assert r['fp64']['est1'] < 1e-12 and r['fp64']['est8'] < 1e-11
     assert r['fp32']['est1'] < 1e-5 and r['fp32']['est8'] < 1e-4
+    assert r['tiles']['noisy_same'] and r['tiles']['est'] < 1e-11
     for tag in ('fp64', 'fp32'):
         assert r[tag]['replica_diff'] == 0.0
         assert r[tag]['noise_independent_of_world']
