@@ -10,6 +10,7 @@
 #include <string.h>
 #include <new>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/lsted.h"
@@ -266,9 +267,15 @@ class CudaBackend {
         void* p = 0;
         CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));
         bytes_ += bytes;
+        sizes_[p] = bytes;
         return p;
     }
-    void free(void* p) { if (p) cudaFree(p); }
+    void free(void* p) {
+        if (!p) return;
+        std::map<void*, size_t>::iterator it = sizes_.find(p);
+        if (it != sizes_.end()) { bytes_ -= it->second; sizes_.erase(it); }
+        cudaFree(p);
+    }
     size_t bytes_allocated() const { return bytes_; }
     void upload(void* d, const void* s, size_t n) {
         CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream_));
@@ -471,6 +478,7 @@ class CudaBackend {
     cudaStream_t stream_;
     size_t bytes_;
     bool profile_, use_fast_;
+    std::map<void*, size_t> sizes_;   // live allocations (for lsted_deconv_info)
     bool prefetch_ = true;
     ncclComm_t comm_ = 0;
     cudaEvent_t t0_, t1_;
