@@ -571,12 +571,6 @@ extern "C" int lsted_host_free(void* ptr) {
 // PSF synthesis (fp64)
 // ---------------------------------------------------------------------------
 namespace {
-struct DeviceBuf {
-    void* p;
-    explicit DeviceBuf(size_t bytes) : p(0) { CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); }
-    ~DeviceBuf() { if (p) cudaFree(p); }
-    template <typename U> U* as() { return (U*)p; }
-};
 void select_device(int device) {
     int count = 0;
     CUDA_CHECK(cudaGetDeviceCount(&count));
@@ -587,6 +581,37 @@ void select_device(int device) {
     }
     CUDA_CHECK(cudaSetDevice(device));
 }
+
+// psf_report is called hundreds of times in a row by tune_psf and the figure sweeps
+// with kilobytes of data: per-call cudaMalloc/cudaFree and one D2H copy per array
+// would dominate.  One workspace per device (device block + pinned host mirror,
+// grown on demand), one H2D and one D2H per call.
+struct PsfWorkspace {
+    int device;
+    void* dev; void* host; size_t cap;
+    cudaStream_t stream;
+    PsfWorkspace() : device(-1), dev(0), host(0), cap(0), stream(0) {}
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (dev) cudaFree(dev);
+        if (host) cudaFreeHost(host);
+        dev = host = 0; cap = 0;
+        const size_t want = bytes + bytes / 2 + 4096;
+        CUDA_CHECK(cudaMalloc(&dev, want));
+        CUDA_CHECK(cudaHostAlloc(&host, want, cudaHostAllocDefault));
+        cap = want;
+    }
+};
+PsfWorkspace& psf_workspace(int device) {
+    static thread_local std::map<int, PsfWorkspace> all;
+    PsfWorkspace& w = all[device];
+    if (w.device != device) {
+        w.device = device;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    }
+    return w;
+}
+inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 }  // namespace
 
 extern "C" int lsted_psf_illumination(int device, int psf_type, int batch, int n, const double* taps,
@@ -603,24 +628,33 @@ extern "C" int lsted_psf_illumination(int device, int psf_type, int batch, int n
         return set_error(LSTED_ERR_ARG, "PSF grid too large for the on-chip kernel");
     try {
         select_device(device);
+        PsfWorkspace& w = psf_workspace(device);
         const size_t img = (size_t)n * n, ntap = 2 * radius + 1;
-        DeviceBuf d_taps(sizeof(double) * ntap), d_eb(sizeof(double) * batch), d_db(sizeof(double) * batch);
-        DeviceBuf d_out(sizeof(double) * img * 5 * batch);
-        CUDA_CHECK(cudaMemcpy(d_taps.p, taps, sizeof(double) * ntap, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(d_eb.p, excitation_brightness, sizeof(double) * batch, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(d_db.p, depletion_brightness, sizeof(double) * batch, cudaMemcpyHostToDevice));
+        // input block: taps | exc | dep ; output block: [batch][5][n][n]
+        const size_t in_bytes = align256(sizeof(double) * (ntap + 2 * (size_t)batch));
+        const size_t out_bytes = sizeof(double) * img * 5 * batch;
+        w.reserve(in_bytes + out_bytes);
+        double* h_in = (double*)w.host;
+        memcpy(h_in, taps, sizeof(double) * ntap);
+        memcpy(h_in + ntap, excitation_brightness, sizeof(double) * batch);
+        memcpy(h_in + ntap + batch, depletion_brightness, sizeof(double) * batch);
+        double* d_in = (double*)w.dev;
+        double* d_out = (double*)((char*)w.dev + in_bytes);
+        double* h_out = (double*)((char*)w.host + in_bytes);
+        CUDA_CHECK(cudaMemcpyAsync(d_in, h_in, sizeof(double) * (ntap + 2 * (size_t)batch),
+                                   cudaMemcpyHostToDevice, w.stream));
         lsted::PsfIlluminationArgs a;
         a.psf_type = psf_type; a.n = n; a.radius = radius;
-        a.taps = d_taps.as<double>();
-        a.exc_brightness = d_eb.as<double>(); a.dep_brightness = d_db.as<double>();
-        a.out = d_out.as<double>();
-        lsted::psf_illumination_kernel<<<batch, lsted::kPsfThreads>>>(a);
+        a.taps = d_in; a.exc_brightness = d_in + ntap; a.dep_brightness = d_in + ntap + batch;
+        a.out = d_out;
+        lsted::psf_illumination_kernel<<<batch, lsted::kPsfThreads, 0, w.stream>>>(a);
         CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, w.stream));
+        CUDA_CHECK(cudaStreamSynchronize(w.stream));
         double* outs[5] = {excitation, depletion, excitation_fraction, depletion_fraction, sted};
         for (int b = 0; b < batch; ++b)
             for (int i = 0; i < 5; ++i)
-                CUDA_CHECK(cudaMemcpy(outs[i] + img * b, d_out.as<double>() + img * (5 * (size_t)b + i),
-                                      sizeof(double) * img, cudaMemcpyDeviceToHost));
+                memcpy(outs[i] + img * b, h_out + img * (5 * (size_t)b + i), sizeof(double) * img);
         return LSTED_OK;
     } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
 }
@@ -639,27 +673,36 @@ extern "C" int lsted_psf_rescan(int device, int batch, int n, const double* taps
             return set_error(LSTED_ERR_ARG, "rescan ratio out of range");
     try {
         select_device(device);
+        PsfWorkspace& w = psf_workspace(device);
         const size_t img = (size_t)n * n, ntap = 2 * radius + 1;
         const size_t W = wide ? (size_t)ratios[0] * n : 0;
-        DeviceBuf d_taps(sizeof(double) * ntap), d_rows(sizeof(double) * n * batch);
-        DeviceBuf d_ratios(sizeof(int) * batch), d_out(sizeof(double) * img * 3 * batch);
-        DeviceBuf d_wide(sizeof(double) * (size_t)n * W);
-        CUDA_CHECK(cudaMemcpy(d_taps.p, taps, sizeof(double) * ntap, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(d_rows.p, sted_rows, sizeof(double) * n * batch, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(d_ratios.p, ratios, sizeof(int) * batch, cudaMemcpyHostToDevice));
+        // input block: taps | rows[batch][n] | ratios[batch] ; output: [batch][3][n][n] | wide
+        const size_t in_doubles = ntap + (size_t)n * batch;
+        const size_t in_bytes = align256(sizeof(double) * in_doubles + sizeof(int) * batch);
+        const size_t out_bytes = sizeof(double) * (img * 3 * batch + (size_t)n * W);
+        w.reserve(in_bytes + out_bytes);
+        double* h_in = (double*)w.host;
+        memcpy(h_in, taps, sizeof(double) * ntap);
+        memcpy(h_in + ntap, sted_rows, sizeof(double) * n * batch);
+        memcpy(h_in + in_doubles, ratios, sizeof(int) * batch);
+        double* d_in = (double*)w.dev;
+        double* d_out = (double*)((char*)w.dev + in_bytes);
+        double* h_out = (double*)((char*)w.host + in_bytes);
+        CUDA_CHECK(cudaMemcpyAsync(d_in, h_in, sizeof(double) * in_doubles + sizeof(int) * batch,
+                                   cudaMemcpyHostToDevice, w.stream));
         lsted::PsfRescanArgs a;
-        a.n = n; a.radius = radius; a.taps = d_taps.as<double>();
-        a.sted_rows = d_rows.as<double>(); a.ratios = d_ratios.as<int>();
-        a.out = d_out.as<double>(); a.wide = wide ? d_wide.as<double>() : 0;
-        lsted::psf_rescan_kernel<<<batch, lsted::kPsfThreads>>>(a);
+        a.n = n; a.radius = radius; a.taps = d_in;
+        a.sted_rows = d_in + ntap; a.ratios = (const int*)(d_in + in_doubles);
+        a.out = d_out; a.wide = wide ? d_out + img * 3 * batch : 0;
+        lsted::psf_rescan_kernel<<<batch, lsted::kPsfThreads, 0, w.stream>>>(a);
         CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, w.stream));
+        CUDA_CHECK(cudaStreamSynchronize(w.stream));
         double* outs[3] = {emission, rescan, descan};
         for (int b = 0; b < batch; ++b)
             for (int i = 0; i < 3; ++i)
-                CUDA_CHECK(cudaMemcpy(outs[i] + img * b, d_out.as<double>() + img * (3 * (size_t)b + i),
-                                      sizeof(double) * img, cudaMemcpyDeviceToHost));
-        if (wide)
-            CUDA_CHECK(cudaMemcpy(wide, d_wide.p, sizeof(double) * (size_t)n * W, cudaMemcpyDeviceToHost));
+                memcpy(outs[i] + img * b, h_out + img * (3 * (size_t)b + i), sizeof(double) * img);
+        if (wide) memcpy(wide, h_out + img * 3 * batch, sizeof(double) * (size_t)n * W);
         return LSTED_OK;
     } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
 }
