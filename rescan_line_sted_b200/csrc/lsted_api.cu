@@ -57,10 +57,13 @@ struct DeviceCtx {
 #ifndef LSTED_ROW_RESIDENT_THREADS
 #define LSTED_ROW_RESIDENT_THREADS 480  // 3 row CTAs per SM: no register spills
 #endif
+#ifndef LSTED_FAST_C32
+#define LSTED_FAST_C32 4
+#endif
 #ifndef LSTED_FAST_PR
 #define LSTED_FAST_PR 1
 #endif
-typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, LSTED_FAST_PR> Plan2160f;
+typedef lsted::FastPlan<float, 16, 9, 15, 144, LSTED_FAST_C32, LSTED_FAST_PR> Plan2160f;
 typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 
 template <int MODE, class P>

@@ -341,17 +341,13 @@ def tune_psf(
             desired_resolution_improvement)
         if relative_resolution_error < relative_error:
             break
-    if verbose_results:
+    if verbose_results:  # same text as ref:463-474
         print("PSF tuning complete, after", num_iterations, "iterations.")
-        print(" Inputs:")
-        for k in sorted(args.keys()):
-            print('  ', k, ': ', args[k], sep='')
-        print(" Outputs:")
-        for k in sorted(results.keys()):
-            if k == 'psfs':
-                print('  ', k, ': ', sorted(results[k].keys()), sep='')
-            else:
-                print('  ', k, ': ', results[k], sep='')
+        for title, table in ((" Inputs:", args), (" Outputs:", results)):
+            print(title)
+            for k in sorted(table):
+                shown = sorted(table[k].keys()) if k == 'psfs' else table[k]
+                print('  ', k, ': ', shown, sep='')
         print()
     results.update(args)  # Combine the two dictionaries
     return results
@@ -541,21 +537,18 @@ class Deconvolver:
         return None
 
     def record_data(self):
-        """ref:550-565: dump psfs / object / measurements as TIFFs."""
-        if hasattr(self, 'psfs'):
-            psfs = np.squeeze(np.concatenate(self.psfs, axis=0))
-            np_tif.array_to_tif(psfs, self.output_prefix + 'psfs.tif')
-        if hasattr(self, 'true_object'):
-            np_tif.array_to_tif(
-                self.true_object, self.output_prefix + 'object.tif')
-        if hasattr(self, 'noiseless_measurement'):
-            nm = np.squeeze(np.concatenate(self.noiseless_measurement, axis=0))
-            np_tif.array_to_tif(
-                nm, self.output_prefix + 'noiseless_measurement.tif')
-        if hasattr(self, 'noisy_measurement'):
-            nm = np.squeeze(np.concatenate(self.noisy_measurement, axis=0))
-            np_tif.array_to_tif(
-                nm, self.output_prefix + 'noisy_measurement.tif')
+        """ref:550-565: dump psfs / object / measurements as TIFFs (whatever of
+        them exists so far)."""
+        def stack(arrays):
+            return np.squeeze(np.concatenate(arrays, axis=0))
+        outputs = (('psfs', 'psfs.tif', stack),
+                   ('true_object', 'object.tif', lambda a: a),
+                   ('noiseless_measurement', 'noiseless_measurement.tif', stack),
+                   ('noisy_measurement', 'noisy_measurement.tif', stack))
+        for attribute, filename, prepare in outputs:
+            if hasattr(self, attribute):
+                np_tif.array_to_tif(prepare(getattr(self, attribute)),
+                                    self.output_prefix + filename)
         return None
 
     def H(self, x):
