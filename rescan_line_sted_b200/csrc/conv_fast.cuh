@@ -35,6 +35,7 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
         LSM_COL = (SEQ + 15) / 16 * 16 + 16 / C_,
         COL_THREADS = NT_ * C_,
         COL_SMEM_ELEMS = 2 * C_ * LSM_COL,          // two ping-pong buffers
+        COL_OTF_ELEMS = C_ * RA * RB * RC,          // + one staged OTF slab [L][C] (bulk copy)
         // row CTA: PR groups of NTG threads (whole warps), one row pair each
         NTG = (NT_ + 31) / 32 * 32,
         LSM_ROW = (SEQ + 15) / 16 * 16 + 8,
@@ -62,8 +63,12 @@ template <class P> struct RowRegs {
     cplx<typename P::T> v[P::VREG];
 };
 
+#ifndef LSTED_COL_STAGE_OTF
+#define LSTED_COL_STAGE_OTF 1   // OTF slabs travel global -> shared by cp.async.bulk, one k ahead
+#endif
 template <class P> LSTED_HD size_t fast_col_smem_bytes() {
-    return sizeof(cplx<typename P::T>) * (size_t)P::COL_SMEM_ELEMS;
+    return sizeof(cplx<typename P::T>) * (size_t)(P::COL_SMEM_ELEMS + (LSTED_COL_STAGE_OTF ? P::COL_OTF_ELEMS : 0)) +
+           (LSTED_COL_STAGE_OTF ? 16 : 0);
 }
 template <class P> LSTED_HD size_t fast_row_smem_bytes() {
     return sizeof(cplx<typename P::T>) * (size_t)P::ROW_SMEM_ELEMS;
@@ -153,12 +158,26 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     cplx<T>* const s0 = buf0 + c * P::LSM_COL;                 \
     cplx<T>* const s1 = buf1 + c * P::LSM_COL;
 
+    // OTF slabs are staged in shared memory by the bulk-copy engine: the slab of
+    // orientation k+1 is requested as soon as every thread is done with slab k and
+    // lands while the transform of k runs (no registers, no per-thread copy work).
+    const bool stage = LSTED_COL_STAGE_OTF != 0;
+    cplx<T>* const otf_s = smem + (size_t)P::COL_SMEM_ELEMS;
+    mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
+    const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(cplx<T>));
+    const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
+    if (stage) {
+        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+            (void)r;
+            if (tid == 0) mbar_init(mbar);
+        });
+    }
     if (MODE == COL_H) {
         const cplx<T>* src = a.src + (size_t)xb * slab_ny;
-        const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
         cplx<T>* dst0 = a.dst + (size_t)xb * slab_ny;
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
             LSTED_COL_IDS
+            if (stage && tid == 0) bulk_load(otf_s, otf0, slab_bytes, mbar);
             col_load_fwd_a<P>(r.v, t, c, src, Ny);
             F::pass_a(r.v, t, s0);
         });
@@ -171,9 +190,10 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
         for (int k = 0; k <= K; ++k) {
             cx.phase(regs, [&](int tid, ColRegs<P>& r) {
                 LSTED_COL_IDS
-                if (k + 1 < K)   // the OTF slab of the next orientation streams in from HBM
-                    prefetch_l2_range(otf0 + (size_t)(k + 1) * img_ly, slab_ly * sizeof(cplx<T>), tid,
-                                      P::COL_THREADS);
+                // HBM -> L2 ahead of the bulk copy (staged) or of the loads (direct)
+                const int ahead = stage ? 2 : 1;
+                if (k + ahead < K)
+                    prefetch_l2_range(otf0 + (size_t)(k + ahead) * img_ly, slab_bytes, tid, P::COL_THREADS);
                 if (k == 0) {
                     F::pass_c(r.v, t, s1, tw);
                     LSTED_UNROLL
@@ -183,13 +203,20 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                     col_store_inv_c<P>(r.v, t, c, dst0 + (size_t)(k - 1) * img_ny, g.sy, Ny);
                 }
                 if (k < K) {
-                    col_otf_product<P, false>(r, t, c, otf0 + (size_t)k * img_ly, false);
+                    if (stage) {
+                        mbar_wait(mbar, (unsigned)(k & 1));
+                        col_otf_product<P, false>(r, t, c, otf_s, false);
+                    } else {
+                        col_otf_product<P, false>(r, t, c, otf0 + (size_t)k * img_ly, false);
+                    }
                     I::pass_a(r.v, t, s0);
                 }
             });
             if (k == K) break;
             cx.phase(regs, [&](int tid, ColRegs<P>& r) {
                 LSTED_COL_IDS
+                if (stage && tid == 0 && k + 1 < K)
+                    bulk_load(otf_s, otf0 + (size_t)(k + 1) * img_ly, slab_bytes, mbar);
                 I::load_b(r.v, t, s0, tw);
                 I::pass_b(r.v, t, s1);
             });
@@ -198,19 +225,27 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     }
     // COL_HT: per k [accumulate product k-1 | load k, forward pass A] then pass B
     const cplx<T>* src0 = a.src + (size_t)xb * slab_ny;
-    const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
     for (int k = 0; k <= K; ++k) {
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
             LSTED_COL_IDS
             if (k + 1 < K && !a.src_same)
                 prefetch_l2_range(src0 + (size_t)(k + 1) * img_ny, slab_ny * sizeof(cplx<T>), tid,
                                   P::COL_THREADS);
-            if (k < K)   // product k happens at the start of the next phase
-                prefetch_l2_range(otf0 + (size_t)k * img_ly, slab_ly * sizeof(cplx<T>), tid,
-                                  P::COL_THREADS);
+            if (stage) {
+                // slab m is consumed in iteration m+1; slab k is requested once slab k-1 is done with
+                if (k + 1 < K) prefetch_l2_range(otf0 + (size_t)(k + 1) * img_ly, slab_bytes, tid, P::COL_THREADS);
+                if (tid == 0 && k == 0) bulk_load(otf_s, otf0, slab_bytes, mbar);
+            } else if (k < K) {   // product k happens at the start of the next phase
+                prefetch_l2_range(otf0 + (size_t)k * img_ly, slab_bytes, tid, P::COL_THREADS);
+            }
             if (k > 0) {
                 F::pass_c(r.v, t, s1, tw);
-                col_otf_product<P, true>(r, t, c, otf0 + (size_t)(k - 1) * img_ly, k == 1);
+                if (stage) {
+                    mbar_wait(mbar, (unsigned)((k - 1) & 1));
+                    col_otf_product<P, true>(r, t, c, otf_s, k == 1);
+                } else {
+                    col_otf_product<P, true>(r, t, c, otf0 + (size_t)(k - 1) * img_ly, k == 1);
+                }
             }
             if (k < K) {
                 col_load_fwd_a<P>(r.v, t, c, src0 + (a.src_same ? 0 : (size_t)k * img_ny), Ny);
@@ -224,6 +259,8 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
         if (k == K) break;
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
             LSTED_COL_IDS
+            if (stage && tid == 0 && k > 0 && k < K)
+                bulk_load(otf_s, otf0 + (size_t)k * img_ly, slab_bytes, mbar);
             F::load_b(r.v, t, s0, tw);
             F::pass_b(r.v, t, s1);
         });

@@ -41,14 +41,23 @@ template <typename T> LSTED_HD cplx<T> fma_real(cplx<T> a, T s, cplx<T> b) {
 #define LSTED_PACKED_F32X2 1
 #endif
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && defined(LSTED_PACKED_F32X2)
-// Blackwell packed fp32 pairs (FADD2 / FMUL2 / FFMA2): a complex add, subtract or
-// real scaling is one instruction on a 64-bit register pair.
+// Blackwell packed fp32 pairs (FADD2 / FMUL2 / FFMA2) on the 64-bit register pair that
+// holds one complex number.  The operands of these instructions take a lane swap
+// (.LO_HI), a per-lane sign (.NP / .PN) and a scalar broadcast (R.F32) for free, so
+//   complex add / subtract / real scaling       = 1 instruction,
+//   complex x complex, complex x (cos, sin)     = 2 instructions (FMUL2 + FFMA2),
+//   multiplication by +-i                       = 0 (folded into the consumer).
 LSTED_HD cplx<float> operator+(cplx<float> a, cplx<float> b) {
     const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
     return mk<float>(r.x, r.y);
 }
 LSTED_HD cplx<float> operator-(cplx<float> a, cplx<float> b) {
-    const float2 r = __ffma2_rn(make_float2(b.x, b.y), make_float2(-1.f, -1.f), make_float2(a.x, a.y));
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
+    return mk<float>(r.x, r.y);
+}
+LSTED_HD cplx<float> operator*(cplx<float> a, cplx<float> b) {
+    const float2 t = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.x));
+    const float2 r = __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), t);
     return mk<float>(r.x, r.y);
 }
 LSTED_HD cplx<float> scale(cplx<float> a, float s) {
@@ -109,6 +118,50 @@ LSTED_HD void async_copy_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
 }
+// Bulk asynchronous copy global -> shared (TMA engine, `cp.async.bulk`): ONE thread
+// issues one instruction for a whole contiguous slab, completion is tracked by an
+// mbarrier (transaction bytes); no registers and no per-thread copy instructions.
+// Host build (CPU replay): a plain memcpy at issue time.
+typedef unsigned long long mbar_t;
+LSTED_HD void mbar_init(mbar_t* bar) {
+#ifdef __CUDA_ARCH__
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+    *bar = 0;
+#endif
+}
+// bytes: multiple of 16; dst / src 16-byte aligned
+LSTED_HD void bulk_load(void* dst_smem, const void* src, unsigned bytes, mbar_t* bar) {
+#ifdef __CUDA_ARCH__
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+#else
+    (void)bar;
+    const char* s = (const char*)src;
+    char* d = (char*)dst_smem;
+    for (unsigned i = 0; i < bytes; ++i) d[i] = s[i];
+#endif
+}
+LSTED_HD void mbar_wait(mbar_t* bar, unsigned parity) {
+#ifdef __CUDA_ARCH__
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    } while (!done);
+#else
+    (void)bar; (void)parity;
+#endif
+}
 // `nthreads` threads sweep [p, p + bytes) in 128-byte lines
 LSTED_HD void prefetch_l2_range(const void* p, size_t bytes, int tid, int nthreads) {
     const char* c = (const char*)p;
@@ -120,8 +173,7 @@ template <int DIR, typename T> LSTED_HD cplx<T> mul_dir_i(cplx<T> a) {
 }
 // a * (c + DIR*i*s) where (c, s) = (cos t, sin t), t >= 0: forward uses exp(-it)
 template <int DIR, typename T> LSTED_HD cplx<T> mul_cs(cplx<T> a, T c, T s) {
-    return DIR < 0 ? mk<T>(a.x * c + a.y * s, a.y * c - a.x * s)
-                   : mk<T>(a.x * c - a.y * s, a.y * c + a.x * s);
+    return a * mk<T>(c, DIR < 0 ? -s : s);
 }
 // twiddle from a forward table entry w = exp(-i t)
 template <int DIR, typename T> LSTED_HD cplx<T> mul_tw(cplx<T> a, cplx<T> w) {
@@ -129,34 +181,62 @@ template <int DIR, typename T> LSTED_HD cplx<T> mul_tw(cplx<T> a, cplx<T> w) {
 }
 
 // ---------------------------------------------------------------------------
-// In-register DFTs, natural order in, natural order out.
+// Two complex sequences side by side ("dual" element, fp32 fast path v2): one
+// thread carries the same butterfly of two independent transforms, so twiddles,
+// addresses, predicates and shared-memory instructions (one 128-bit access per
+// element) are shared; each half is an ordinary packed complex number.
 // ---------------------------------------------------------------------------
-template <int R, int DIR, typename T> struct Dft;
+struct alignas(16) c2 { cplx<float> a, b; };
+LSTED_HD c2 mk2(cplx<float> a, cplx<float> b) { c2 r; r.a = a; r.b = b; return r; }
+LSTED_HD c2 operator+(c2 u, c2 v) { return mk2(u.a + v.a, u.b + v.b); }
+LSTED_HD c2 operator-(c2 u, c2 v) { return mk2(u.a - v.a, u.b - v.b); }
+LSTED_HD c2 scale(c2 u, float s) { return mk2(scale(u.a, s), scale(u.b, s)); }
+LSTED_HD c2 fma_real(c2 u, float s, c2 v) { return mk2(fma_real(u.a, s, v.a), fma_real(u.b, s, v.b)); }
+template <int DIR> LSTED_HD c2 mul_dir_i(c2 u) { return mk2(mul_dir_i<DIR>(u.a), mul_dir_i<DIR>(u.b)); }
+template <int DIR> LSTED_HD c2 mul_cs(c2 u, float c, float s) {
+    return mk2(mul_cs<DIR>(u.a, c, s), mul_cs<DIR>(u.b, c, s));
+}
+template <int DIR> LSTED_HD c2 mul_tw(c2 u, cplx<float> w) {
+    return mk2(mul_tw<DIR>(u.a, w), mul_tw<DIR>(u.b, w));
+}
+LSTED_HD c2 operator*(c2 u, c2 v) { return mk2(u.a * v.a, u.b * v.b); }
 
-template <int DIR, typename T> struct Dft<2, DIR, T> {
-    static LSTED_HD void run(cplx<T>* v) {
-        cplx<T> a = v[0];
+// scalar type behind an element type
+template <class V> struct ScalarOf;
+template <typename T> struct ScalarOf<cplx<T> > { typedef T type; };
+template <> struct ScalarOf<c2> { typedef float type; };
+
+// ---------------------------------------------------------------------------
+// In-register DFTs, natural order in, natural order out, on any element type V
+// (cplx<float>, cplx<double>, c2).
+// ---------------------------------------------------------------------------
+template <int R, int DIR, class V> struct DftE;
+
+template <int DIR, class V> struct DftE<2, DIR, V> {
+    static LSTED_HD void run(V* v) {
+        V a = v[0];
         v[0] = a + v[1];
         v[1] = a - v[1];
     }
 };
 
-template <int DIR, typename T> struct Dft<3, DIR, T> {
-    static LSTED_HD void run(cplx<T>* v) {
+template <int DIR, class V> struct DftE<3, DIR, V> {
+    typedef typename ScalarOf<V>::type T;
+    static LSTED_HD void run(V* v) {
         const T s3 = (T)0.86602540378443864676;
-        cplx<T> t = v[1] + v[2];
-        cplx<T> d = mul_dir_i<DIR>(scale(v[1] - v[2], s3));
-        cplx<T> m = fma_real(t, (T)-0.5, v[0]);
+        V t = v[1] + v[2];
+        V d = mul_dir_i<DIR>(scale(v[1] - v[2], s3));
+        V m = fma_real(t, (T)-0.5, v[0]);
         v[0] = v[0] + t;
         v[1] = m + d;
         v[2] = m - d;
     }
 };
 
-template <int DIR, typename T> struct Dft<4, DIR, T> {
-    static LSTED_HD void run(cplx<T>* v) {
-        cplx<T> a = v[0] + v[2], b = v[0] - v[2];
-        cplx<T> c = v[1] + v[3], d = mul_dir_i<DIR>(v[1] - v[3]);
+template <int DIR, class V> struct DftE<4, DIR, V> {
+    static LSTED_HD void run(V* v) {
+        V a = v[0] + v[2], b = v[0] - v[2];
+        V c = v[1] + v[3], d = mul_dir_i<DIR>(v[1] - v[3]);
         v[0] = a + c;
         v[1] = b + d;
         v[2] = a - c;
@@ -164,16 +244,17 @@ template <int DIR, typename T> struct Dft<4, DIR, T> {
     }
 };
 
-template <int DIR, typename T> struct Dft<5, DIR, T> {
-    static LSTED_HD void run(cplx<T>* v) {
-        const T c1 = (T)0.30901699437494742410, c2 = (T)-0.80901699437494742410;
+template <int DIR, class V> struct DftE<5, DIR, V> {
+    typedef typename ScalarOf<V>::type T;
+    static LSTED_HD void run(V* v) {
+        const T c1 = (T)0.30901699437494742410, c2_ = (T)-0.80901699437494742410;
         const T s1 = (T)0.95105651629515357212, s2 = (T)0.58778525229247312917;
-        cplx<T> t1 = v[1] + v[4], t2 = v[2] + v[3];
-        cplx<T> t3 = v[1] - v[4], t4 = v[2] - v[3];
-        cplx<T> a1 = fma_real(t2, c2, fma_real(t1, c1, v[0]));
-        cplx<T> a2 = fma_real(t2, c1, fma_real(t1, c2, v[0]));
-        cplx<T> b1 = mul_dir_i<DIR>(fma_real(t4, s2, scale(t3, s1)));
-        cplx<T> b2 = mul_dir_i<DIR>(fma_real(t4, -s1, scale(t3, s2)));
+        V t1 = v[1] + v[4], t2 = v[2] + v[3];
+        V t3 = v[1] - v[4], t4 = v[2] - v[3];
+        V a1 = fma_real(t2, c2_, fma_real(t1, c1, v[0]));
+        V a2 = fma_real(t2, c1, fma_real(t1, c2_, v[0]));
+        V b1 = mul_dir_i<DIR>(fma_real(t4, s2, scale(t3, s1)));
+        V b2 = mul_dir_i<DIR>(fma_real(t4, -s1, scale(t3, s2)));
         v[0] = v[0] + t1 + t2;
         v[1] = a1 + b1;
         v[4] = a1 - b1;
@@ -209,14 +290,15 @@ template <int R, typename T> LSTED_HD void unit_root(int m, T& c, T& s) {
 }
 
 // R = R1*R2 by one in-register Cooley-Tukey step.
-template <int R, int R1, int R2, int DIR, typename T> struct DftComposite {
-    static LSTED_HD void run(cplx<T>* v) {
-        cplx<T> y[R2][R1];
+template <int R, int R1, int R2, int DIR, class V> struct DftComposite {
+    typedef typename ScalarOf<V>::type T;
+    static LSTED_HD void run(V* v) {
+        V y[R2][R1];
         LSTED_UNROLL
         for (int n2 = 0; n2 < R2; ++n2) {
             LSTED_UNROLL
             for (int n1 = 0; n1 < R1; ++n1) y[n2][n1] = v[n2 + R2 * n1];
-            Dft<R1, DIR, T>::run(y[n2]);
+            DftE<R1, DIR, V>::run(y[n2]);
             LSTED_UNROLL
             for (int k1 = 1; k1 < R1; ++k1) {
                 if (n2 * k1 != 0) {
@@ -228,18 +310,44 @@ template <int R, int R1, int R2, int DIR, typename T> struct DftComposite {
         }
         LSTED_UNROLL
         for (int k1 = 0; k1 < R1; ++k1) {
-            cplx<T> z[R2];
+            V z[R2];
             LSTED_UNROLL
             for (int n2 = 0; n2 < R2; ++n2) z[n2] = y[n2][k1];
-            Dft<R2, DIR, T>::run(z);
+            DftE<R2, DIR, V>::run(z);
             LSTED_UNROLL
             for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = z[k2];
         }
     }
 };
-template <int DIR, typename T> struct Dft<8, DIR, T> : DftComposite<8, 4, 2, DIR, T> {};
-template <int DIR, typename T> struct Dft<9, DIR, T> : DftComposite<9, 3, 3, DIR, T> {};
-template <int DIR, typename T> struct Dft<16, DIR, T> : DftComposite<16, 4, 4, DIR, T> {};
+template <int DIR, class V> struct DftE<8, DIR, V> : DftComposite<8, 4, 2, DIR, V> {};
+template <int DIR, class V> struct DftE<9, DIR, V> : DftComposite<9, 3, 3, DIR, V> {};
+template <int DIR, class V> struct DftE<16, DIR, V> : DftComposite<16, 4, 4, DIR, V> {};
+
+// Good-Thomas 15-point DFT (3 x 5, no twiddles): n = 5*n1 + 3*n2,
+// k = 10*k1 + 6*k2 (mod 15).
+template <int DIR, class V> struct DftE<15, DIR, V> {
+    static LSTED_HD void run(V* v) {
+        V y[5][3];
+        LSTED_UNROLL
+        for (int n2 = 0; n2 < 5; ++n2) {
+            LSTED_UNROLL
+            for (int n1 = 0; n1 < 3; ++n1) y[n2][n1] = v[(5 * n1 + 3 * n2) % 15];
+            DftE<3, DIR, V>::run(y[n2]);
+        }
+        LSTED_UNROLL
+        for (int k1 = 0; k1 < 3; ++k1) {
+            V z[5];
+            LSTED_UNROLL
+            for (int n2 = 0; n2 < 5; ++n2) z[n2] = y[n2][k1];
+            DftE<5, DIR, V>::run(z);
+            LSTED_UNROLL
+            for (int k2 = 0; k2 < 5; ++k2) v[(10 * k1 + 6 * k2) % 15] = z[k2];
+        }
+    }
+};
+
+// historical spelling: DFT on cplx<T>
+template <int R, int DIR, typename T> struct Dft : DftE<R, DIR, cplx<T> > {};
 
 // ---------------------------------------------------------------------------
 // Plans

@@ -23,29 +23,6 @@
 
 namespace lsted {
 
-// Good-Thomas 15-point DFT (3 x 5, no twiddles): n = 5*n1 + 3*n2,
-// k = 10*k1 + 6*k2 (mod 15).
-template <int DIR, typename T> struct Dft<15, DIR, T> {
-    static LSTED_HD void run(cplx<T>* v) {
-        cplx<T> y[5][3];
-        LSTED_UNROLL
-        for (int n2 = 0; n2 < 5; ++n2) {
-            LSTED_UNROLL
-            for (int n1 = 0; n1 < 3; ++n1) y[n2][n1] = v[(5 * n1 + 3 * n2) % 15];
-            Dft<3, DIR, T>::run(y[n2]);
-        }
-        LSTED_UNROLL
-        for (int k1 = 0; k1 < 3; ++k1) {
-            cplx<T> z[5];
-            LSTED_UNROLL
-            for (int n2 = 0; n2 < 5; ++n2) z[n2] = y[n2][k1];
-            Dft<5, DIR, T>::run(z);
-            LSTED_UNROLL
-            for (int k2 = 0; k2 < 5; ++k2) v[(10 * k1 + 6 * k2) % 15] = z[k2];
-        }
-    }
-};
-
 constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 constexpr int imax(int a, int b) { return a > b ? a : b; }
 // smallest p >= n with p % 16 == r % 16
@@ -55,7 +32,9 @@ constexpr int pitch_congruent(int n, int r) {
     return p;
 }
 
-template <typename T, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3 {
+template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
+    typedef typename ScalarOf<V>::type T;
+    typedef cplx<T> W;   // twiddles are always single complex numbers
     enum {
         RA = RA_, RB = RB_, RC = RC_, NT = NT_,
         L = RA * RB * RC,
@@ -68,12 +47,12 @@ template <typename T, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3 {
     };
 
     // Pass A on registers v[m*RA + q] = x[j + q*NA], j = t + m*NT.
-    static LSTED_HD void pass_a(cplx<T>* v, int t, cplx<T>* sm) {
+    static LSTED_HD void pass_a(V* v, int t, V* sm) {
         LSTED_UNROLL
         for (int m = 0; m < MA; ++m) {
             const int j = t + m * NT;
             if (j < NA) {
-                Dft<RA, DIR, T>::run(v + m * RA);
+                DftE<RA, DIR, V>::run(v + m * RA);
                 LSTED_UNROLL
                 for (int q = 0; q < RA; ++q) sm[q * PA + j] = v[m * RA + q];
             }
@@ -82,14 +61,14 @@ template <typename T, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3 {
     // w[q] = w1^q for q = 1..N by binary splitting (product depth <= log2 N, so the
     // rounding error stays at a few ulp); replaces N-1 scattered table look-ups,
     // which cost up to 32 L1 wavefronts each, by one coalesced load + N-1 products.
-    template <int N> static LSTED_HD void twiddle_powers(cplx<T> w1, cplx<T>* w) {
+    template <int N> static LSTED_HD void twiddle_powers(W w1, W* w) {
         w[1] = w1;
         LSTED_UNROLL
         for (int q = 2; q <= N; ++q) w[q] = w[q / 2] * w[q - q / 2];
     }
-    static LSTED_HD void load_b(cplx<T>* v, int t, const cplx<T>* sm, const cplx<T>* tw) {
+    static LSTED_HD void load_b(V* v, int t, const V* sm, const W* tw) {
         // every butterfly of this thread has the same k = j % RA when NT % RA == 0
-        cplx<T> w[RB];
+        W w[RB];
         if (NT % RA == 0) twiddle_powers<RB - 1>(tw[RC * (t % RA)], w);
         LSTED_UNROLL
         for (int m = 0; m < MB; ++m) {
@@ -100,19 +79,19 @@ template <typename T, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3 {
                 if (NT % RA != 0) twiddle_powers<RB - 1>(tw[RC * k], w);
                 LSTED_UNROLL
                 for (int q = 0; q < RB; ++q) {
-                    cplx<T> x = sm[pos + q * RC];
+                    V x = sm[pos + q * RC];
                     if (q > 0) x = mul_tw<DIR>(x, w[q]);
                     v[m * RB + q] = x;
                 }
             }
         }
     }
-    static LSTED_HD void pass_b(cplx<T>* v, int t, cplx<T>* sm) {
+    static LSTED_HD void pass_b(V* v, int t, V* sm) {
         LSTED_UNROLL
         for (int m = 0; m < MB; ++m) {
             const int j = t + m * NT;
             if (j < NB) {
-                Dft<RB, DIR, T>::run(v + m * RB);
+                DftE<RB, DIR, V>::run(v + m * RB);
                 LSTED_UNROLL
                 for (int q = 0; q < RB; ++q) sm[q * PB + j] = v[m * RB + q];
             }
@@ -120,24 +99,25 @@ template <typename T, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3 {
     }
     // Loads pass-C operands, applies twiddles and the butterflies; on return
     // v[m*RC + q] = X[j + q*NC].
-    static LSTED_HD void pass_c(cplx<T>* v, int t, const cplx<T>* sm, const cplx<T>* tw) {
+    static LSTED_HD void pass_c(V* v, int t, const V* sm, const W* tw) {
         LSTED_UNROLL
         for (int m = 0; m < MC; ++m) {
             const int j = t + m * NT;
             if (j < NC) {
                 const int pos = (j / RA) * PB + (j % RA);
-                cplx<T> w[RC];
+                W w[RC];
                 twiddle_powers<RC - 1>(tw[j], w);
                 LSTED_UNROLL
                 for (int q = 0; q < RC; ++q) {
-                    cplx<T> x = sm[pos + q * RA];
+                    V x = sm[pos + q * RA];
                     if (q > 0) x = mul_tw<DIR>(x, w[q]);
                     v[m * RC + q] = x;
                 }
-                Dft<RC, DIR, T>::run(v + m * RC);
+                DftE<RC, DIR, V>::run(v + m * RC);
             }
         }
     }
 };
+template <typename T, int DIR, int RA, int RB, int RC, int NT> struct Fft3 : Fft3E<cplx<T>, DIR, RA, RB, RC, NT> {};
 
 }  // namespace lsted

@@ -125,7 +125,7 @@ class HostBackend {
         if (use_fast_ && MODE != lsted::COL_OTF && a.g.Ly == P::L && a.g.C == P::C) {
 #pragma omp parallel
             {
-                std::vector<lsted::cplx<T> > smem((size_t)P::COL_SMEM_ELEMS);
+                std::vector<lsted::cplx<T> > smem(lsted::fast_col_smem_bytes<P>() / sizeof(lsted::cplx<T>) + 1);
                 std::vector<lsted::ColRegs<P> > regs(P::COL_THREADS);
                 HostCtx cx;
                 cx.nthreads = P::COL_THREADS;
