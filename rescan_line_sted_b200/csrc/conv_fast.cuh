@@ -40,8 +40,10 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
         NTG = (NT_ + 31) / 32 * 32,
         LSM_ROW = (SEQ + 15) / 16 * 16 + 8,
         ROW_THREADS = NTG * PR_,
-        // two ping-pong buffers + one staging buffer (2 measurement rows of <= L pixels) per pair
-        ROW_SMEM_ELEMS = 3 * PR_ * LSM_ROW,
+        // two ping-pong buffers + staging per pair: 2 measurement rows of <= L pixels (ROW_MID),
+        // 2 normalisation rows + 2 estimate rows (ROW_FINAL)
+        ROW_BUFS = 3, ROW_FINAL_BUFS = sizeof(T_) == 4 ? 4 : 3,
+        ROW_SMEM_ELEMS = ROW_BUFS * PR_ * LSM_ROW,
         VREG = imax(Fwd::VREG, Inv::VREG),
         NKEEP = Fwd::MC * Fwd::RC,
         // Hermitian split: thread t owns bins t + q*NC; its mirror bins live in thread NC - t
@@ -61,6 +63,9 @@ template <class P> struct ColRegs {
 };
 template <class P> struct RowRegs {
     cplx<typename P::T> v[P::VREG];
+    typename P::Fwd::Tw twf;
+    typename P::Inv::Tw twi;
+    cplx<typename P::T> ramp0;           // crop-offset phase ramp at this thread's first bin
 };
 
 #ifndef LSTED_COL_STAGE_OTF
@@ -70,8 +75,9 @@ template <class P> LSTED_HD size_t fast_col_smem_bytes() {
     return sizeof(cplx<typename P::T>) * (size_t)(P::COL_SMEM_ELEMS + (LSTED_COL_STAGE_OTF ? P::COL_OTF_ELEMS : 0)) +
            (LSTED_COL_STAGE_OTF ? 16 : 0);
 }
-template <class P> LSTED_HD size_t fast_row_smem_bytes() {
-    return sizeof(cplx<typename P::T>) * (size_t)P::ROW_SMEM_ELEMS;
+template <class P> LSTED_HD size_t fast_row_smem_bytes(int mode) {
+    const int bufs = mode == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
+    return sizeof(cplx<typename P::T>) * (size_t)bufs * P::PR * P::LSM_ROW;
 }
 
 // ---------------------------------------------------------------------------
@@ -166,12 +172,10 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
     const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(cplx<T>));
     const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
-    if (stage) {
-        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-            (void)r;
-            if (tid == 0) mbar_init(mbar);
-        });
-    }
+    cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+        (void)r;   // (hoisting base twiddles here costs spills at 96 registers / 576 threads)
+        if (stage && tid == 0) mbar_init(mbar);
+    });
     if (MODE == COL_H) {
         const cplx<T>* src = a.src + (size_t)xb * slab_ny;
         cplx<T>* dst0 = a.dst + (size_t)xb * slab_ny;
@@ -301,6 +305,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     // the data of a pair sit at logical positions shift + pixel during the transforms
     const int shift = (MODE == ROW_FWD) ? 0 : g.sx;
     const size_t xb_stride = (size_t)Ny * C;  // elements between consecutive column blocks
+    const int NBUF = MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
+    const bool stage_est = MODE == ROW_FINAL && P::ROW_FINAL_BUFS == 4;
 
 #define LSTED_ROW_IDS                                      \
     const int f = tid / P::NTG, t = tid - f * P::NTG;      \
@@ -308,10 +314,11 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     const bool live = pair < Py && t < P::NT;              \
     const int y = 2 * pair;                                \
     const bool two = y + 1 < Ny;                           \
-    cplx<T>* const s0 = smem + (size_t)(3 * f) * P::LSM_ROW;      \
-    cplx<T>* const s1 = smem + (size_t)(3 * f + 1) * P::LSM_ROW;  \
-    T* const stage = (T*)(smem + (size_t)(3 * f + 2) * P::LSM_ROW); \
-    (void)s0; (void)s1; (void)stage; (void)y; (void)live; (void)two;
+    cplx<T>* const s0 = smem + (size_t)(NBUF * f) * P::LSM_ROW;      \
+    cplx<T>* const s1 = smem + (size_t)(NBUF * f + 1) * P::LSM_ROW;  \
+    T* const stage = (T*)(smem + (size_t)(NBUF * f + 2) * P::LSM_ROW); \
+    T* const stage2 = (T*)(smem + (size_t)(NBUF * f + 3) * P::LSM_ROW); /* only if NBUF == 4 */ \
+    (void)s0; (void)s1; (void)stage; (void)stage2; (void)y; (void)live; (void)two;
 
     // Software prefetch across CTAs: the operands of the row pairs that will be
     // scheduled roughly one wave later are pulled into L2 now (spectra: one
@@ -340,6 +347,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             if (!live) return;
+            F::load_tw(r.twf, t, tw);
             LSTED_UNROLL
             for (int m = 0; m < F::MA; ++m) {
                 const int j = t + m * P::NT;
@@ -365,14 +373,24 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         const cplx<T>* src = a.spec_in + spec_off;
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
-            if (MODE == ROW_MID && pair < Py) {
-                // measurement rows y, y+1 -> shared memory, asynchronously (used after
-                // the inverse transform, two barriers from here)
-                const T* m0 = a.aux + real_off + (size_t)y * Nx;
+            if ((MODE == ROW_MID || MODE == ROW_FINAL) && pair < Py) {
+                // measurement (MID) or normalisation + estimate (FINAL) rows y, y+1 -> shared
+                // memory, asynchronously (used after the inverse transform, two barriers from here)
+                const T* m0 = (MODE == ROW_MID ? a.aux + real_off : a.aux) + (size_t)y * Nx;
                 async_copy_row(stage, m0, Nx, t, P::NTG);
                 if (two) async_copy_row(stage + P::L, m0 + Nx, Nx, t, P::NTG);
+                if (stage_est) {
+                    const T* e0 = a.real_out + (size_t)y * Nx;
+                    async_copy_row(stage2, e0, Nx, t, P::NTG);
+                    if (two) async_copy_row(stage2 + P::L, e0 + Nx, Nx, t, P::NTG);
+                }
             }
             if (!live) return;
+            I::load_tw(r.twi, t, tw);
+            if (MODE == ROW_MID || MODE == ROW_FINAL) {
+                F::load_tw(r.twf, t, tw);
+                r.ramp0 = tw[(t * shift) % Lx];
+            }
             const cplx<T>* lo = src + ((size_t)(t / C) * Ny + y) * C + (t % C);
             const int tm = Lx - t;  // mirror of bin t; (tm - q*NC) is the mirror of bin t + q*NC
             LSTED_UNROLL
@@ -399,10 +417,10 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             if (live) {
-                I::load_b(r.v, t, s0, tw);
+                I::load_b(r.v, t, s0, r.twi);
                 I::pass_b(r.v, t, s1);
             }
-            if (MODE == ROW_MID) async_copy_wait_all();   // visible to the group after the barrier
+            if (MODE == ROW_MID || MODE == ROW_FINAL) async_copy_wait_all();   // visible after the barrier
         });
         // inverse pass C, the pointwise step on registers (logical position
         // idx = j + q*NC holds pixel idx - sx of rows y (re) and y+1 (im)) and the
@@ -413,33 +431,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             if (!live) return;
-            // Issue every global load of the pointwise step up front (they overlap
-            // pass C); the arithmetic comes afterwards.
-            cplx<T> pa[MODE == ROW_FINAL ? I::MC * I::RC : 1];
-            cplx<T> pe[MODE == ROW_FINAL ? I::MC * I::RC : 1];
-            if (MODE == ROW_FINAL) {
-                LSTED_UNROLL
-                for (int m = 0; m < I::MC; ++m) {
-                    const int j = t + m * P::NT;
-                    LSTED_UNROLL
-                    for (int q = 0; q < I::RC; ++q) {
-                        const int i = j + q * I::NC - shift;
-                        cplx<T> av = mk<T>(1, 1), ev = mk<T>(0, 0);
-                        if (j < I::NC && i >= 0 && i < Nx) {
-                            const size_t o = (size_t)y * Nx + i;
-                            av.x = aux[o];
-                            if (two) av.y = aux[o + Nx];
-                            if (MODE == ROW_FINAL) {
-                                ev.x = out[o];
-                                if (two) ev.y = out[o + Nx];
-                            }
-                        }
-                        pa[m * I::RC + q] = av;
-                        if (MODE == ROW_FINAL) pe[m * I::RC + q] = ev;
-                    }
-                }
-            }
-            I::pass_c(r.v, t, s1, tw);
+            I::pass_c(r.v, t, s1, r.twi);
             LSTED_UNROLL
             for (int m = 0; m < I::MC; ++m) {
                 const int j = t + m * P::NT;
@@ -462,11 +454,11 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                                 w.x = fast_div(stage[i], clip0(z.x));
                                 if (two) w.y = fast_div(stage[P::L + i], clip0(z.y));
                             } else {  // ROW_FINAL
-                                const cplx<T> nv = pa[m * I::RC + q], ev = pe[m * I::RC + q];
-                                w.x = ev.x * fast_div(clip0(z.x), nv.x);
+                                w.x = (stage_est ? stage2[i] : out[o]) * fast_div(clip0(z.x), stage[i]);
                                 out[o] = w.x;
                                 if (two) {
-                                    w.y = ev.y * fast_div(clip0(z.y), nv.y);
+                                    w.y = (stage_est ? stage2[P::L + i] : out[o + Nx]) *
+                                          fast_div(clip0(z.y), stage[P::L + i]);
                                     out[o + Nx] = w.y;
                                 }
                             }
@@ -503,14 +495,14 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     cx.phase(regs, [&](int tid, RowRegs<P>& r) {
         LSTED_ROW_IDS
         if (!live) return;
-        F::load_b(r.v, t, s0, tw);
+        F::load_b(r.v, t, s0, r.twf);
         F::pass_b(r.v, t, s1);
     });
     // Forward pass C; the upper half of the spectrum goes to the mirror thread.
     cx.phase(regs, [&](int tid, RowRegs<P>& r) {
         LSTED_ROW_IDS
         if (!live) return;
-        F::pass_c(r.v, t, s1, tw);
+        F::pass_c(r.v, t, s1, r.twf);
         LSTED_UNROLL
         for (int q = P::QH; q < P::RCF; ++q) s0[(q - P::QH) * P::PX + t] = r.v[q];
     });
@@ -523,8 +515,10 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         const int tp = t == 0 ? 0 : P::NC - t;         // mirror thread
         const int qoff = t == 0 ? 1 : 0;               // thread 0 mirrors onto itself, one q up
         cplx<T>* pk = dst + ((size_t)(t / C) * Ny + y) * C + (t % C);
-        const int step = (t * shift) % Lx;             // twiddle index of the phase ramp at q = 0
-        const int qstep = (P::NC * shift) % Lx;
+        // phase ramp exp(+2 pi i k shift / L) at bins k = t + q*NC: ramp0 * d^q with the
+        // thread-independent step d (powers by binary splitting, no table gathers)
+        cplx<T> dq[P::QH + 2];
+        if (shift) F::template twiddle_powers<P::QH>(tw[(P::NC * shift) % Lx], dq);
         LSTED_UNROLL
         for (int q = 0; q <= P::QH; ++q) {
             const int k = t + q * P::NC;
@@ -545,7 +539,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             cplx<T> oa = mk<T>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y - z2.y));  // (z1 + conj z2)/2
             cplx<T> ob = mk<T>((T)0.5 * (z1.y + z2.y), (T)0.5 * (z2.x - z1.x));  // (z1 - conj z2)/(2i)
             if (shift) {
-                const cplx<T> ph = conj(tw[(step + q * qstep) % Lx]);
+                const cplx<T> ph = conj(q == 0 ? r.ramp0 : r.ramp0 * dq[q]);
                 oa = oa * ph;
                 ob = ob * ph;
             }

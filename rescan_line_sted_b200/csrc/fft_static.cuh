@@ -40,8 +40,13 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
         L = RA * RB * RC,
         NA = RB * RC, NB = RA * RC, NC = RA * RB,   // butterflies per pass
         MA = ceil_div(NA, NT), MB = ceil_div(NB, NT), MC = ceil_div(NC, NT),
-        PA = (NA % 2) ? NA : NA + 1,
-        PB = (RA % 16 == 0) ? pitch_congruent(NB, 0) : ((NB % 2) ? NB : NB + 1),
+        // exchange pitches (brute-forced over the access patterns of load_b / pass_c,
+        // scripts/smem_bank_conflicts.py): RA = 16 is conflict-free with PA odd, PB = 0 (mod 16);
+        // RA = 15 wants PB = 15 (mod 16) (and PA = 3 (mod 16) for 8-byte elements: also conflict-free
+        // for the 4 interleaved sequences of a column CTA)
+        PA = (RA % 16 == 15 && NA % 16 == 0 && sizeof(V) == 8) ? NA + 3 : ((NA % 2) ? NA : NA + 1),
+        PB = (RA % 16 == 0) ? pitch_congruent(NB, 0)
+           : (RA % 16 == 15) ? pitch_congruent(NB, 15) : ((NB % 2) ? NB : NB + 1),
         SEQ = imax(imax(RA * PA, RB * PB), L),      // shared elements per sequence
         VREG = imax(imax(MA * RA, MB * RB), MC * RC)
     };
@@ -66,17 +71,32 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
         LSTED_UNROLL
         for (int q = 2; q <= N; ++q) w[q] = w[q / 2] * w[q - q / 2];
     }
-    static LSTED_HD void load_b(V* v, int t, const V* sm, const W* tw) {
+    // Base twiddles of one thread (they depend on t only): loaded once per kernel, not
+    // once per transform -- no global load sits at the head of a pass any more.
+    struct Tw { W b[(NT_ % RA_ == 0) ? 1 : MB]; W c[MC]; };
+    static LSTED_HD void load_tw(Tw& w, int t, const W* tw) {
+        LSTED_UNROLL
+        for (int m = 0; m < ((NT % RA == 0) ? 1 : (int)MB); ++m) {
+            const int j = t + m * NT;
+            w.b[m] = tw[(j < NB) ? RC * (j % RA) : 0];
+        }
+        LSTED_UNROLL
+        for (int m = 0; m < MC; ++m) {
+            const int j = t + m * NT;
+            w.c[m] = tw[(j < NC) ? j : 0];
+        }
+    }
+    static LSTED_HD void load_b(V* v, int t, const V* sm, const Tw& bw) {
         // every butterfly of this thread has the same k = j % RA when NT % RA == 0
         W w[RB];
-        if (NT % RA == 0) twiddle_powers<RB - 1>(tw[RC * (t % RA)], w);
+        if (NT % RA == 0) twiddle_powers<RB - 1>(bw.b[0], w);
         LSTED_UNROLL
         for (int m = 0; m < MB; ++m) {
             const int j = t + m * NT;
             if (j < NB) {
                 const int k = j % RA;
                 const int pos = k * PA + j / RA;
-                if (NT % RA != 0) twiddle_powers<RB - 1>(tw[RC * k], w);
+                if (NT % RA != 0) twiddle_powers<RB - 1>(bw.b[(NT % RA != 0) ? m : 0], w);
                 LSTED_UNROLL
                 for (int q = 0; q < RB; ++q) {
                     V x = sm[pos + q * RC];
@@ -85,6 +105,11 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
                 }
             }
         }
+    }
+    static LSTED_HD void load_b(V* v, int t, const V* sm, const W* tw) {
+        Tw bw;
+        load_tw(bw, t, tw);
+        load_b(v, t, sm, bw);
     }
     static LSTED_HD void pass_b(V* v, int t, V* sm) {
         LSTED_UNROLL
@@ -99,14 +124,14 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
     }
     // Loads pass-C operands, applies twiddles and the butterflies; on return
     // v[m*RC + q] = X[j + q*NC].
-    static LSTED_HD void pass_c(V* v, int t, const V* sm, const W* tw) {
+    static LSTED_HD void pass_c(V* v, int t, const V* sm, const Tw& bw) {
         LSTED_UNROLL
         for (int m = 0; m < MC; ++m) {
             const int j = t + m * NT;
             if (j < NC) {
                 const int pos = (j / RA) * PB + (j % RA);
                 W w[RC];
-                twiddle_powers<RC - 1>(tw[j], w);
+                twiddle_powers<RC - 1>(bw.c[m], w);
                 LSTED_UNROLL
                 for (int q = 0; q < RC; ++q) {
                     V x = sm[pos + q * RA];
@@ -116,6 +141,11 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
                 DftE<RC, DIR, V>::run(v + m * RC);
             }
         }
+    }
+    static LSTED_HD void pass_c(V* v, int t, const V* sm, const W* tw) {
+        Tw bw;
+        load_tw(bw, t, tw);
+        pass_c(v, t, sm, bw);
     }
 };
 template <typename T, int DIR, int RA, int RB, int RC, int NT> struct Fft3 : Fft3E<cplx<T>, DIR, RA, RB, RC, NT> {};

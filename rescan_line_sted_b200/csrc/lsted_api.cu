@@ -329,7 +329,7 @@ class CudaBackend {
     }
     template <int MODE, class P> void launch_row_fast(int grid, const lsted::RowArgs<typename P::T>& a,
                                                       int kind) {
-        const size_t smem = lsted::fast_row_smem_bytes<P>();
+        const size_t smem = lsted::fast_row_smem_bytes<P>(MODE);
         static bool configured = false;
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P>,

@@ -102,7 +102,7 @@ class HostBackend {
             grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
 #pragma omp parallel
             {
-                std::vector<lsted::cplx<T> > smem((size_t)P::ROW_SMEM_ELEMS);
+                std::vector<lsted::cplx<T> > smem(lsted::fast_row_smem_bytes<P>(MODE) / sizeof(lsted::cplx<T>));
                 std::vector<lsted::RowRegs<P> > regs(P::ROW_THREADS);
                 HostCtx cx;
                 cx.nthreads = P::ROW_THREADS;
