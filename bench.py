@@ -269,9 +269,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
-    # PSFs through the product's own PSF path (GPU), rotated by the caller.
+    # PSFs through the product's own PSF path (GPU): psf_report + on-device orientation step.
+    from rescan_line_sted_b200 import orientations
     base = st.psf_report('line', verbose=False, **FIG2_2P0X_LR)['psfs']['rescan_sted']
-    psfs = orientation_psfs(base, K)
+    psfs = orientations.line_orientation_psfs(base, K, EMISSION_2P0X_LR)
     obj_host = synthetic_object(N)
     brightness = total_brightness(N)
 

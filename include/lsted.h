@@ -61,6 +61,14 @@ int lsted_psf_rescan(int device, int batch, int n, const double* taps, int radiu
                      const double* sted_rows, const int* ratios, double* emission,
                      double* rescan, double* descan, double* wide);
 
+/* Orientation step of Deconvolver's caller (line_sted_figure_2.py:264-272, used at
+ * :244-247): rotate one plane [n0][n1] to `batch` orientations like
+ * scipy.ndimage.rotate(order=3, mode='constant', cval=0, reshape=False) and clip to
+ * [0, clip_hi].  xform = [batch][6] = the 2x2 matrix [[c, s], [-s, c]] (row-major) and
+ * the offset centre - matrix*centre of each angle (host: cosdg/sindg).  out [batch][n0][n1]. */
+int lsted_psf_rotate(int device, int batch, int n0, int n1, const double* plane,
+                     const double* xform, double clip_hi, double* out);
+
 /* ---------------- Deconvolver, line_sted_tools.py:478-594 -------------------------------- */
 typedef struct lsted_deconv lsted_deconv;
 

@@ -90,6 +90,8 @@ _CORE_SIGNATURES = {
     'lsted_psf_rescan': [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
                          ctypes.c_int, c_double_p, c_int_p, c_double_p,
                          c_double_p, c_double_p, c_double_p],
+    'lsted_psf_rotate': [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                         c_double_p, c_double_p, ctypes.c_double, c_double_p],
 }
 
 # every symbol include/lsted.h declares (checked by tests/test_cabi_symbols.py)

@@ -662,6 +662,39 @@ extern "C" int lsted_psf_illumination(int device, int psf_type, int batch, int n
     } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
 }
 
+extern "C" int lsted_psf_rotate(int device, int batch, int n0, int n1, const double* plane,
+                               const double* xform, double clip_hi, double* out) {
+    if (!plane || !xform || !out) return set_error(LSTED_ERR_ARG, "null pointer");
+    if (batch < 1 || n0 < 1 || n1 < 1 || (long long)n0 * n1 > (1 << 24))
+        return set_error(LSTED_ERR_ARG, "bad rotate arguments");
+    try {
+        select_device(device);
+        PsfWorkspace& w = psf_workspace(device);
+        const size_t img = (size_t)n0 * n1;
+        // input block: plane | xform[batch][6]; scratch + output: 2 x [batch][n0][n1]
+        const size_t in_doubles = img + 6 * (size_t)batch;
+        const size_t in_bytes = align256(sizeof(double) * in_doubles);
+        const size_t out_bytes = sizeof(double) * img * batch;
+        w.reserve(in_bytes + 2 * out_bytes);
+        double* h_in = (double*)w.host;
+        memcpy(h_in, plane, sizeof(double) * img);
+        memcpy(h_in + img, xform, sizeof(double) * 6 * batch);
+        double* d_in = (double*)w.dev;
+        double* d_out = (double*)((char*)w.dev + in_bytes);
+        double* h_out = (double*)((char*)w.host + in_bytes);
+        CUDA_CHECK(cudaMemcpyAsync(d_in, h_in, sizeof(double) * in_doubles, cudaMemcpyHostToDevice, w.stream));
+        lsted::PsfRotateArgs a;
+        a.n0 = n0; a.n1 = n1; a.plane = d_in; a.xform = d_in + img; a.clip_hi = clip_hi;
+        a.out = d_out; a.coef = d_out + img * batch;
+        lsted::psf_rotate_kernel<<<batch, lsted::kPsfThreads, 0, w.stream>>>(a);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, w.stream));
+        CUDA_CHECK(cudaStreamSynchronize(w.stream));
+        memcpy(out, h_out, out_bytes);
+        return LSTED_OK;
+    } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
+}
+
 extern "C" int lsted_psf_rescan(int device, int batch, int n, const double* taps, int radius,
                                 const double* sted_rows, const int* ratios, double* emission,
                                 double* rescan, double* descan, double* wide) {

@@ -199,6 +199,98 @@ LSTED_HD void psf_rescan_body(Ctx& cx, int b, const PsfRescanArgs& a, PsfSmem* s
     }
 }
 
+// ---------------------------------------------------------------------------
+// Orientation step: the caller of Deconvolver rotates one
+// system PSF to K line orientations with scipy.ndimage.rotate(order=3,
+// mode='constant', reshape=False) and clips to [0, 1.1*max]
+// (line_sted_figure_2.py:264-272, used at :244-247).  One CTA per orientation:
+//   1. cubic B-spline prefilter of the plane, axis 0 then axis 1 (gain 6, pole
+//      sqrt(3)-2, mirror boundary with the exact whole-line causal start),
+//   2. four-tap interpolation at matrix*(i,j)+offset, 0 outside [0, n-1],
+//      coefficient indices mirrored at the edges, 3. clip.
+// ---------------------------------------------------------------------------
+struct PsfRotateArgs {
+    int n0, n1;            // plane shape
+    const double* plane;   // [n0][n1], shared by all orientations
+    const double* xform;   // [batch][6]: m00 m01 m10 m11 offset0 offset1
+    double clip_hi;
+    double* coef;          // [batch][n0][n1] scratch (spline coefficients)
+    double* out;           // [batch][n0][n1]
+};
+
+// in-place prefilter of one line c[0], c[stride], ... (n elements)
+LSTED_HD void spline_prefilter_line(double* c, int n, size_t stride) {
+    if (n < 2) return;
+    const double z = sqrt(3.0) - 2.0;
+    const double gain = (1.0 - z) * (1.0 - 1.0 / z);
+    for (int i = 0; i < n; ++i) c[i * stride] *= gain;
+    double z_n_1 = 1.0;
+    for (int i = 0; i < n - 1; ++i) z_n_1 *= z;
+    double s = c[0] + z_n_1 * c[(n - 1) * stride];
+    double z_i = z;
+    for (int i = 1; i < n - 1; ++i) {
+        s += z_i * (c[i * stride] + z_n_1 * c[(n - 1 - i) * stride]);
+        z_i *= z;
+    }
+    c[0] = s / (1.0 - z_n_1 * z_n_1);
+    for (int i = 1; i < n; ++i) c[i * stride] += z * c[(i - 1) * stride];
+    c[(n - 1) * stride] = (z * c[(n - 2) * stride] + c[(n - 1) * stride]) * z / (z * z - 1.0);
+    for (int i = n - 2; i >= 0; --i) c[i * stride] = z * (c[(i + 1) * stride] - c[i * stride]);
+}
+LSTED_HD int spline_mirror(int idx, int n) {
+    if (n <= 1) return 0;
+    const int s2 = 2 * n - 2;
+    if (idx < 0) {
+        idx = s2 * (-idx / s2) + idx;
+        idx = idx <= 1 - n ? idx + s2 : -idx;
+    } else if (idx >= n) {
+        idx -= s2 * (idx / s2);
+        if (idx >= n) idx = s2 - idx;
+    }
+    return idx;
+}
+LSTED_HD void cubic_weights(double x, double* w) {
+    const double y = x - floor(x), z = 1.0 - y;
+    w[1] = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
+    w[2] = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
+    w[0] = z * z * z / 6.0;
+    w[3] = 1.0 - w[0] - w[1] - w[2];
+}
+
+template <class Ctx> LSTED_HD void psf_rotate_body(Ctx& cx, int b, const PsfRotateArgs& a) {
+    const int n0 = a.n0, n1 = a.n1;
+    const size_t img = (size_t)n0 * n1;
+    double* co = a.coef + img * b;
+    double* out = a.out + img * b;
+    const double* m = a.xform + 6 * (size_t)b;
+    cx.parallel_for(n1, [&](int j) {          // axis 0: one column per thread
+        for (int i = 0; i < n0; ++i) co[(size_t)i * n1 + j] = a.plane[(size_t)i * n1 + j];
+        spline_prefilter_line(co + j, n0, (size_t)n1);
+    });
+    cx.parallel_for(n0, [&](int i) {          // axis 1: one row per thread
+        spline_prefilter_line(co + (size_t)i * n1, n1, 1);
+    });
+    cx.parallel_for((int)img, [&](int e) {
+        const int i = e / n1, j = e - i * n1;
+        const double y = m[0] * i + m[1] * j + m[4];
+        const double x = m[2] * i + m[3] * j + m[5];
+        double v = 0.0;
+        if (!(y < 0.0 || y > (double)(n0 - 1) || x < 0.0 || x > (double)(n1 - 1))) {
+            double wy[4], wx[4];
+            cubic_weights(y, wy);
+            cubic_weights(x, wx);
+            const int sy = (int)floor(y) - 1, sx = (int)floor(x) - 1;
+            int xx[4];
+            for (int q = 0; q < 4; ++q) xx[q] = spline_mirror(sx + q, n1);
+            for (int p = 0; p < 4; ++p) {
+                const double* row = co + (size_t)spline_mirror(sy + p, n0) * n1;
+                for (int q = 0; q < 4; ++q) v += wy[p] * wx[q] * row[xx[q]];
+            }
+        }
+        out[e] = v < 0.0 ? 0.0 : (v > a.clip_hi ? a.clip_hi : v);
+    });
+}
+
 #ifdef __CUDACC__
 struct PsfDeviceCtx {
     template <class F> __device__ __forceinline__ void parallel_for(int n, F f) {
@@ -215,6 +307,10 @@ __global__ void __launch_bounds__(kPsfThreads) psf_rescan_kernel(PsfRescanArgs a
     __shared__ PsfSmem sm;
     PsfDeviceCtx cx;
     psf_rescan_body(cx, blockIdx.x, a, &sm);
+}
+__global__ void __launch_bounds__(kPsfThreads) psf_rotate_kernel(PsfRotateArgs a) {
+    PsfDeviceCtx cx;
+    psf_rotate_body(cx, blockIdx.x, a);
 }
 #endif
 

@@ -25,6 +25,6 @@ def build_emulator():
 
 def emulator_library():
     sigs = dict(_lib._DECONV_SIGNATURES)
-    for name in ('lsted_psf_illumination', 'lsted_psf_rescan'):
+    for name in ('lsted_psf_illumination', 'lsted_psf_rescan', 'lsted_psf_rotate'):
         sigs[name] = _lib._CORE_SIGNATURES[name]
     return _lib.Library(build_emulator(), sigs)

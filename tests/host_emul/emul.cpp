@@ -274,3 +274,15 @@ extern "C" int lsted_psf_rescan(int, int batch, int n, const double* taps, int r
             memcpy(outs[i] + img * b, out.data() + img * (3 * (size_t)b + i), sizeof(double) * img);
     return 0;
 }
+
+extern "C" int lsted_psf_rotate(int, int batch, int n0, int n1, const double* plane,
+                               const double* xform, double clip_hi, double* out) {
+    const size_t img = (size_t)n0 * n1;
+    std::vector<double> coef(img * batch);
+    lsted::PsfRotateArgs a;
+    a.n0 = n0; a.n1 = n1; a.plane = plane; a.xform = xform; a.clip_hi = clip_hi;
+    a.coef = coef.data(); a.out = out;
+    HostCtx cx;
+    for (int b = 0; b < batch; ++b) lsted::psf_rotate_body(cx, b, a);
+    return 0;
+}
