@@ -275,7 +275,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
         I::load_b(r.v, t, s0, tw);
         I::pass_b(r.v, t, s1);
     });
-    cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+    cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
         LSTED_COL_IDS
         I::pass_c(r.v, t, s1, tw);
         col_store_inv_c<P>(r.v, t, c, dst, g.sy, Ny);
@@ -332,7 +332,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             const int rows2 = (Ny - y2) < 2 * P::PR ? (Ny - y2) : 2 * P::PR;
             const cplx<T>* sp = a.spec_in + (size_t)img2 * g.nxb * C * Ny + (size_t)y2 * C;
             const T* ax = (MODE == ROW_MID ? a.aux + (size_t)img2 * Ny * Nx : a.aux) + (size_t)y2 * Nx;
-            cx.phase(regs, [&](int tid, RowRegs<P>& r) {
+            cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {   // prefetches only: no barrier
                 (void)r;
                 for (int xb = tid; xb < g.nxb; xb += P::ROW_THREADS) prefetch_l2(sp + (size_t)xb * xb_stride);
                 prefetch_l2_range(ax, (size_t)rows2 * Nx * sizeof(T), tid, P::ROW_THREADS);
@@ -509,7 +509,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     // Hermitian split of the lower half, crop-offset phase ramp, XB store:
     // bins k = t + q*NC with mirror L - k = (NC - t) + (RC - 1 - q)*NC.
     cplx<T>* dst = a.spec_out + spec_off;
-    cx.phase(regs, [&](int tid, RowRegs<P>& r) {
+    cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {   // last phase: nothing to wait for
         LSTED_ROW_IDS
         if (!live) return;
         const int tp = t == 0 ? 0 : P::NC - t;         // mirror thread

@@ -51,6 +51,10 @@ struct DeviceCtx {
         f((int)threadIdx.x, *regs);
         __syncthreads();
     }
+    // a phase nothing later depends on through shared memory (prefetches, final stores)
+    template <class R, class F> __device__ __forceinline__ void phase_nosync(R* regs, F f) {
+        f((int)threadIdx.x, *regs);
+    }
 };
 
 // Compile-time plans of the fast path (conv_fast.cuh): 2160 = 16 * 9 * 15.

@@ -35,6 +35,7 @@ struct HostCtx {
     template <class R, class F> void phase(R* regs, F f) {
         for (int t = 0; t < nthreads; ++t) f(t, regs[t]);
     }
+    template <class R, class F> void phase_nosync(R* regs, F f) { phase(regs, f); }
 };
 
 typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 1> Plan2160f;
