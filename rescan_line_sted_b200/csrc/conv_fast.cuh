@@ -430,6 +430,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         const T* aux = (MODE == ROW_MID) ? a.aux + real_off : a.aux;
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
+            if (MODE == ROW_INV_SIM && t == 0) *(int*)stage = 0;   // noise queue (below)
             if (!live) return;
             I::pass_c(r.v, t, s1, r.twi);
             LSTED_UNROLL
@@ -470,12 +471,15 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             if (MODE == ROW_MID || MODE == ROW_FINAL) F::pass_a(r.v, t, s0);
         });
         if (MODE == ROW_INV_SIM) {
-            // Shot noise.  A rolled loop over the pixels this thread just wrote (one
-            // copy of the sampler in the instruction stream, values re-read from L1/L2).
+            // Shot noise in two dense steps.  (1) every pixel this thread just wrote gets the
+            // first PTRS attempt (or the whole small-lambda sampler); the ~10 % the squeeze does
+            // not accept go to a queue in shared memory; (2) the queue is drained by all threads
+            // with the full sampler, so its logarithms never run behind a half-empty warp.
             cx.phase(regs, [&](int tid, RowRegs<P>& r) {
                 LSTED_ROW_IDS
                 (void)r;
                 if (!live) return;
+                int* const queue = (int*)stage;       // [0] = count, [1..] = pixel offsets
                 const int nr = two ? 2 : 1;
                 LSTED_NOUNROLL
                 for (int e = 0; e < I::MC * I::RC * 2; ++e) {
@@ -485,8 +489,28 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                     const int i = j + q * I::NC - shift;
                     if (j < I::NC && rr < nr && i >= 0 && i < Nx) {
                         const size_t o = (size_t)(y + rr) * Nx + i;
-                        out2[o] = (T)(poisson_sample((double)out[o], a.seed, o, a.img0 + img) + 1e-9);
+                        const double lam = (double)out[o];
+                        double k;
+                        if (!(lam >= 10.0)) {
+                            out2[o] = (T)(poisson_sample(lam, a.seed, o, a.img0 + img) + 1e-9);
+                        } else if (poisson_fast_ptrs(lam, a.seed, o, a.img0 + img, k)) {
+                            out2[o] = (T)(k + 1e-9);
+                        } else {
+                            queue[1 + smem_counter_next(queue)] = rr * Nx + i;
+                        }
                     }
+                }
+            });
+            cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {
+                LSTED_ROW_IDS
+                (void)r;
+                if (pair >= Py) return;
+                const int* const queue = (const int*)stage;
+                const int n = queue[0];
+                LSTED_NOUNROLL
+                for (int e = t; e < n; e += P::NTG) {
+                    const size_t o = (size_t)y * Nx + queue[1 + e];
+                    out2[o] = (T)(poisson_sample((double)out[o], a.seed, o, a.img0 + img) + 1e-9);
                 }
             });
         }

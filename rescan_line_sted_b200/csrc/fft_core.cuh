@@ -118,6 +118,14 @@ LSTED_HD void async_copy_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
 }
+// CTA-wide counter in shared memory (host replay: threads run one after another)
+LSTED_HD int smem_counter_next(int* counter) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(counter, 1);
+#else
+    return (*counter)++;
+#endif
+}
 // Bulk asynchronous copy global -> shared (TMA engine, `cp.async.bulk`): ONE thread
 // issues one instruction for a whole contiguous slab, completion is tracked by an
 // mbarrier (transaction bytes); no registers and no per-thread copy instructions.

@@ -150,3 +150,39 @@ def test_poisson_large_lambda_moments(lib, lam):
     assert poisson(lib, 0.0, 10).max() == 0
     a, b = poisson(lib, lam, 100, seed=3), poisson(lib, lam, 100, seed=4)
     assert np.array_equal(a, x[:100]) and not np.array_equal(a, b)
+
+
+def test_fast_path_noise_field_is_the_sampler_field(lib):
+    """ROW_INV_SIM of the 2160 fast path draws the noise in two steps (first PTRS attempt,
+    then a shared-memory queue of the pixels the squeeze rejected); the field has to be
+    exactly poisson_sample(noiseless[pixel], seed, pixel, image) -- also for lambda < 10
+    and lambda == 0 -- and identical to the generic kernels' field."""
+    rng = np.random.default_rng(5)
+    ny, nx, seed = 4, 2048, 11
+    psfs = rng.random((2, 3, 9))
+    obj = rng.random((1, ny, nx)) * 40.0
+    obj[0, 1, :700] *= 1e4              # large lambda (PTRS) ...
+    obj[0, :, 100:400] = 0.0            # ... dark stretches (lambda ~ 0) ...
+    obj[0, :, 1200:1500] *= 0.01        # ... and lambda < 10 (multiplication method)
+    fields = []
+    for fast in (1, 0):
+        h = _lib.DeconvHandle(lib, psfs, (ny, nx), precision=64)
+        h.set_option('fast_path', fast)
+        h.create_data(obj, None, seed)
+        assert (h.info().Lx == 2160) and (h.info().row_pairs_per_cta >= 1)
+        noiseless = np.stack([h.get(_lib.NOISELESS, k) for k in range(2)])
+        noisy = np.stack([h.get(_lib.NOISY, k) for k in range(2)])
+        fields.append(noisy)
+        h.close()
+    assert np.array_equal(fields[0], fields[1])
+    lib.cdll.emul_poisson.argtypes = [ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64,
+                                      ctypes.c_int, dp]
+    one = np.empty(1)
+    flat = noiseless.reshape(2, -1)
+    for k in range(2):
+        for pix in list(range(0, ny * nx, 97)) + [ny * nx - 1]:
+            # emul_poisson samples image 0; image k is covered by the fast/generic equality
+            if k == 0:
+                lib.cdll.emul_poisson(float(flat[k, pix]), seed, pix, 1, one.ctypes.data_as(dp))
+                assert fields[0].reshape(2, -1)[k, pix] == one[0] + 1e-9
+    assert (noiseless < 10).any() and (noiseless > 1e4).any()
