@@ -16,12 +16,11 @@
 // length Lx), columns complex-to-complex (length Ly) on the Lx/2+1
 // non-redundant columns.
 //
-// Spectrum layout in HBM ("XB"): columns are grouped in blocks of C; block
-// xb holds rows x C complex values contiguously:
-//     index(y, x) = ((x / C) * rows + y) * C + (x % C)
-// so a column CTA streams one fully contiguous slab, and a row CTA that
-// owns 2*PR adjacent rows writes 2*PR*C*sizeof(complex) contiguous bytes
-// per block (128 B for fp32 with C = 4, PR = 2).
+// Spectrum layout in HBM: columns are grouped in blocks of C; block xb holds
+// rows x C complex values contiguously, OTFs as [y][c] ("XB"), row spectra as
+// [y/2][c][y%2] ("XB2", see xb2_index), so a column CTA streams one fully
+// contiguous slab, and a row CTA that owns 2*PR adjacent rows moves
+// 2*PR*C*sizeof(complex) contiguous bytes per block.
 #pragma once
 #include "fft_core.cuh"
 #include "poisson.cuh"
@@ -40,8 +39,18 @@ struct ConvGeom {
     FftPlan px, py;
 };
 
-LSTED_HD size_t xb_index(int y, int x, int rows, int C) {
+LSTED_HD size_t xb_index(int y, int x, int rows, int C) {   // OTF arrays: [xb][y][c]
     return ((size_t)(x / C) * rows + y) * C + (x % C);
+}
+// Row-spectrum arrays ("XB2"): inside a column block the two rows of a row pair sit
+// side by side per column, [xb][y/2][c][y%2], so a row thread moves (A[k], B[k]) of its
+// pair with ONE 16-byte access (half the L1 wavefronts of two 8-byte ones 32 bytes
+// apart) while a column CTA still streams a fully contiguous slab.  Images with an odd
+// number of rows are stored as if they had one more (never read).
+LSTED_HD int even_rows(int rows) { return (rows + 1) & ~1; }
+LSTED_HD size_t slab2_index(int y, int c, int C) { return (size_t)(y & ~1) * C + 2 * c + (y & 1); }
+LSTED_HD size_t xb2_index(int xb, int y, int c, int rows, int C) {
+    return (size_t)xb * even_rows(rows) * C + slab2_index(y, c, C);
 }
 
 enum RowMode {
@@ -86,7 +95,7 @@ LSTED_HD void row_body(Ctx& cx, int block, const RowArgs<T>& a, cplx<T>* smem) {
     cplx<T>* b0 = smem;
     cplx<T>* b1 = smem + (size_t)g.PR * Lp;
     const size_t real_off = (size_t)img * Ny * Nx;
-    const size_t spec_off = (size_t)img * g.nxb * C * Ny;
+    const size_t spec_off = (size_t)img * g.nxb * C * even_rows(Ny);
     cplx<T>* fwd_in;    // packed rows (a + i b) ready for the forward transform
     cplx<T>* fwd_free;  // scratch for it
 
@@ -114,9 +123,9 @@ LSTED_HD void row_body(Ctx& cx, int block, const RowArgs<T>& a, cplx<T>* smem) {
             const int k = xb * C + c;
             if (k >= Lxh) return;
             const int y = row0 + 2 * f;
-            const size_t ia = ((size_t)xb * Ny + y) * C + c;
+            const size_t ia = xb2_index(xb, y, c, Ny, C);
             cplx<T> A = src[ia];
-            cplx<T> B = (y + 1 < Ny) ? src[ia + C] : mk<T>(0, 0);
+            cplx<T> B = (y + 1 < Ny) ? src[ia + 1] : mk<T>(0, 0);
             const bool self = (k == 0) || (2 * k == Lx);
             if (self) { A.y = 0; B.y = 0; }
             b0[f * Lp + pad<T>(k)] = mk<T>(A.x - B.y, A.y + B.x);
@@ -188,7 +197,7 @@ LSTED_HD void row_body(Ctx& cx, int block, const RowArgs<T>& a, cplx<T>* smem) {
             if (rr & 1) o = mk<T>((T)0.5 * (z1.y + z2.y), (T)0.5 * (z2.x - z1.x));  // (z1 - conj z2)/(2i)
             else        o = mk<T>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y - z2.y));  // (z1 + conj z2)/2
         }
-        dst[((size_t)xb * Ny + row0 + rr) * C + c] = o;
+        dst[xb2_index(xb, row0 + rr, c, Ny, C)] = o;
     });
 }
 
@@ -223,15 +232,15 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
     cplx<T>* b2 = smem + (size_t)2 * C * Lp;
     const size_t slab_ly = (size_t)C * Ly;          // one OTF slab
     const size_t img_ly = (size_t)g.nxb * slab_ly;  // one OTF image
-    const size_t slab_ny = (size_t)C * Ny;
+    const size_t slab_ny = (size_t)C * even_rows(Ny);   // row spectra: XB2 layout
     const size_t img_ny = (size_t)g.nxb * slab_ny;
 
     if (MODE == COL_OTF) {
         const int rows = a.rows_in;
-        const cplx<T>* src = a.src + ((size_t)kk * g.nxb + xb) * C * rows;
+        const cplx<T>* src = a.src + ((size_t)kk * g.nxb + xb) * C * even_rows(rows);
         cx.parallel_for(C * Ly, [&](int w) {
             const int y = w / C, c = w - y * C;
-            b0[c * Lp + pad<T>(y)] = (y < rows) ? src[w] : mk<T>(0, 0);
+            b0[c * Lp + pad<T>(y)] = (y < rows) ? src[slab2_index(y, c, C)] : mk<T>(0, 0);
         });
         SmemSrc<T> s0 = {b0, Lp};
         const cplx<T>* z = fft_batch<-1, T>(cx, g.py, a.tw, s0, b1, b0, C, Lp);
@@ -246,7 +255,7 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
         const cplx<T>* src = a.src + (size_t)xb * slab_ny;
         cx.parallel_for(C * Ly, [&](int w) {
             const int y = w / C, c = w - y * C;
-            b0[c * Lp + pad<T>(y)] = (y < Ny) ? src[w] : mk<T>(0, 0);
+            b0[c * Lp + pad<T>(y)] = (y < Ny) ? src[slab2_index(y, c, C)] : mk<T>(0, 0);
         });
         SmemSrc<T> s0 = {b0, Lp};
         cplx<T>* A = fft_batch<-1, T>(cx, g.py, a.tw, s0, b1, b0, C, Lp);
@@ -263,7 +272,7 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
             cplx<T>* dst = a.dst + (size_t)k * img_ny + (size_t)xb * slab_ny;
             cx.parallel_for(C * Ny, [&](int w) {
                 const int y = w / C, c = w - y * C;
-                dst[w] = z[c * Lp + pad<T>(g.sy + y)];
+                dst[slab2_index(y, c, C)] = z[c * Lp + pad<T>(g.sy + y)];
             });
         }
         return;
@@ -273,7 +282,7 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
         const cplx<T>* src = a.src + (a.src_same ? 0 : (size_t)k * img_ny) + (size_t)xb * slab_ny;
         cx.parallel_for(C * Ly, [&](int w) {
             const int y = w / C, c = w - y * C;
-            b0[c * Lp + pad<T>(y)] = (y < Ny) ? src[w] : mk<T>(0, 0);
+            b0[c * Lp + pad<T>(y)] = (y < Ny) ? src[slab2_index(y, c, C)] : mk<T>(0, 0);
         });
         SmemSrc<T> s0 = {b0, Lp};
         const cplx<T>* z = fft_batch<-1, T>(cx, g.py, a.tw, s0, b1, b0, C, Lp);
@@ -290,7 +299,7 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
     cplx<T>* dst = a.dst + (size_t)xb * slab_ny;
     cx.parallel_for(C * Ny, [&](int w) {
         const int y = w / C, c = w - y * C;
-        dst[w] = z[c * Lp + pad<T>(g.sy + y)];
+        dst[slab2_index(y, c, C)] = z[c * Lp + pad<T>(g.sy + y)];
     });
 }
 

@@ -83,7 +83,22 @@ template <class P> LSTED_HD size_t fast_row_smem_bytes(int mode) {
 // ---------------------------------------------------------------------------
 // Column kernels
 // ---------------------------------------------------------------------------
-// Forward pass-A operands of column c from an XB slab with `rows` valid rows.
+// XB2 slab addressing for the rows y = y0 + q*STEP a column thread touches (q is a
+// compile-time index): slab2_index(y, c) = y*C + 2c - (y & 1)*(C - 1), and the parity of y
+// is the parity of y0, flipped for odd q when STEP is odd -- two base offsets per thread
+// and immediate offsets per q instead of integer work per access.
+template <class P, int STEP> struct SlabRows {
+    long long base[2];   // element offset at q even / q odd, without the q*STEP*C term
+    LSTED_HD SlabRows(int y0, int c) {
+        const int par = y0 & 1;
+        const long long lin = (long long)y0 * P::C + 2 * c;
+        base[0] = lin - par * (P::C - 1);
+        base[1] = lin - ((STEP % 2) ? 1 - par : par) * (P::C - 1);
+    }
+    LSTED_HD long long at(int q) const { return base[q & 1] + (long long)q * STEP * P::C; }
+};
+
+// Forward pass-A operands of column c from an XB2 slab with `rows` valid rows.
 template <class P>
 LSTED_HD void col_load_fwd_a(cplx<typename P::T>* v, int t, int c, const cplx<typename P::T>* slab,
                              int rows) {
@@ -93,10 +108,11 @@ LSTED_HD void col_load_fwd_a(cplx<typename P::T>* v, int t, int c, const cplx<ty
     for (int m = 0; m < F::MA; ++m) {
         const int j = t + m * P::NT;
         if (j < F::NA) {
+            const SlabRows<P, F::NA> sr(j, c);
             LSTED_UNROLL
             for (int q = 0; q < F::RA; ++q) {
                 const int y = j + q * F::NA;
-                v[m * F::RA + q] = (y < rows) ? slab[(size_t)y * P::C + c] : mk<T>(0, 0);
+                v[m * F::RA + q] = (y < rows) ? slab[sr.at(q)] : mk<T>(0, 0);
             }
         }
     }
@@ -111,10 +127,11 @@ LSTED_HD void col_store_inv_c(const cplx<typename P::T>* v, int t, int c, cplx<t
     for (int m = 0; m < I::MC; ++m) {
         const int j = t + m * P::NT;
         if (j < I::NC) {
+            const SlabRows<P, I::NC> sr(j - sy, c);
             LSTED_UNROLL
             for (int q = 0; q < I::RC; ++q) {
                 const int y = j + q * I::NC - sy;
-                if (y >= 0 && y < Ny) slab[(size_t)y * P::C + c] = v[m * I::RC + q];
+                if (y >= 0 && y < Ny) slab[sr.at(q)] = v[m * I::RC + q];
             }
         }
     }
@@ -153,7 +170,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     const int Ny = g.Ny, Ly = P::L;  // == g.Ly (checked at launch)
     const int xb = block;
     const size_t slab_ly = (size_t)P::C * Ly, img_ly = (size_t)g.nxb * slab_ly;
-    const size_t slab_ny = (size_t)P::C * Ny, img_ny = (size_t)g.nxb * slab_ny;
+    const size_t slab_ny = (size_t)P::C * even_rows(Ny), img_ny = (size_t)g.nxb * slab_ny;   // XB2
     const cplx<T>* tw = a.tw;
     cplx<T>* const buf0 = smem;
     cplx<T>* const buf1 = smem + (size_t)P::C * P::LSM_COL;
@@ -300,11 +317,13 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     const int img = block / bpi;
     const int pair0 = (block - img * bpi) * P::PR;
     const size_t real_off = (size_t)img * Ny * Nx;
-    const size_t spec_off = (size_t)img * g.nxb * C * Ny;
+    const int Nye = even_rows(Ny);
+    const size_t spec_off = (size_t)img * g.nxb * C * Nye;
     const cplx<T>* tw = a.tw;
     // the data of a pair sit at logical positions shift + pixel during the transforms
     const int shift = (MODE == ROW_FWD) ? 0 : g.sx;
-    const size_t xb_stride = (size_t)Ny * C;  // elements between consecutive column blocks
+    const size_t xb_stride = (size_t)Nye * C;  // elements between consecutive column blocks
+    // XB2: the pair (row y, row y+1) of column c sits at ((xb*Nye + y)*C + 2c) + {0, 1}
     const int NBUF = MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
     const bool stage_est = MODE == ROW_FINAL && P::ROW_FINAL_BUFS == 4;
 
@@ -330,7 +349,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         if (a.prefetch_ahead > 0 && img2 < a.nimg && pair2 < Py) {
             const int y2 = 2 * pair2;
             const int rows2 = (Ny - y2) < 2 * P::PR ? (Ny - y2) : 2 * P::PR;
-            const cplx<T>* sp = a.spec_in + (size_t)img2 * g.nxb * C * Ny + (size_t)y2 * C;
+            const cplx<T>* sp = a.spec_in + (size_t)img2 * g.nxb * C * Nye + (size_t)y2 * C;
             const T* ax = (MODE == ROW_MID ? a.aux + (size_t)img2 * Ny * Nx : a.aux) + (size_t)y2 * Nx;
             cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {   // prefetches only: no barrier
                 (void)r;
@@ -391,24 +410,23 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 F::load_tw(r.twf, t, tw);
                 r.ramp0 = tw[(t * shift) % Lx];
             }
-            const cplx<T>* lo = src + ((size_t)(t / C) * Ny + y) * C + (t % C);
+            const cplx<T>* lo = src + ((size_t)(t / C) * Nye + y) * C + 2 * (t % C);
             const int tm = Lx - t;  // mirror of bin t; (tm - q*NC) is the mirror of bin t + q*NC
             LSTED_UNROLL
             for (int q = 0; q < I::RA; ++q) {
                 const int i = t + q * P::NC;
                 bool upper = q > P::QH;
                 if (q == P::QH) upper = 2 * i > Lx;
-                cplx<T> A, B;
+                const cplx<T>* p;
                 if (q < P::QH || (q == P::QH && !upper)) {
-                    const cplx<T>* p = lo + (size_t)(q * (P::NC / C)) * xb_stride;
-                    A = p[0];
-                    B = two ? p[C] : mk<T>(0, 0);
+                    p = lo + (size_t)(q * (P::NC / C)) * xb_stride;
                 } else {
                     const int k = tm - q * P::NC;
-                    const cplx<T>* p = src + ((size_t)(k / C) * Ny + y) * C + (k % C);
-                    A = p[0];
-                    B = two ? p[C] : mk<T>(0, 0);
+                    p = src + ((size_t)(k / C) * Nye + y) * C + 2 * (k % C);
                 }
+                cplx<T> A, B;
+                load_pair(p, A, B);   // one 16-byte (fp32) access; the slot of a missing last row is never used
+                if (!two) B = mk<T>(0, 0);
                 if ((q == 0 && t == 0) || 2 * i == Lx) { A.y = 0; B.y = 0; }
                 r.v[q] = upper ? mk<T>(A.x + B.y, B.x - A.y) : mk<T>(A.x - B.y, A.y + B.x);
             }
@@ -538,7 +556,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         if (!live) return;
         const int tp = t == 0 ? 0 : P::NC - t;         // mirror thread
         const int qoff = t == 0 ? 1 : 0;               // thread 0 mirrors onto itself, one q up
-        cplx<T>* pk = dst + ((size_t)(t / C) * Ny + y) * C + (t % C);
+        cplx<T>* pk = dst + ((size_t)(t / C) * Nye + y) * C + 2 * (t % C);
         // phase ramp exp(+2 pi i k shift / L) at bins k = t + q*NC: ramp0 * d^q with the
         // thread-independent step d (powers by binary splitting, no table gathers)
         cplx<T> dq[P::QH + 2];
@@ -548,11 +566,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             const int k = t + q * P::NC;
             if (q == P::QH && 2 * k > Lx) {
                 // past the Nyquist bin: only the zero padding of the last column block
-                if (k < g.nxb * C) {
-                    cplx<T>* p = pk + (size_t)(q * (P::NC / C)) * xb_stride;
-                    p[0] = mk<T>(0, 0);
-                    if (two) p[C] = mk<T>(0, 0);
-                }
+                if (k < g.nxb * C)
+                    store_pair(pk + (size_t)(q * (P::NC / C)) * xb_stride, mk<T>(0, 0), mk<T>(0, 0));
                 continue;
             }
             const cplx<T> z1 = r.v[q];
@@ -567,12 +582,204 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 oa = oa * ph;
                 ob = ob * ph;
             }
-            cplx<T>* p = pk + (size_t)(q * (P::NC / C)) * xb_stride;
-            p[0] = oa;
-            if (two) p[C] = ob;
+            // (a missing last row has its own never-read slot: the pair is always stored whole)
+            store_pair(pk + (size_t)(q * (P::NC / C)) * xb_stride, oa, two ? ob : mk<T>(0, 0));
         }
     });
 #undef LSTED_ROW_IDS
+}
+
+
+// ---------------------------------------------------------------------------
+// ROW_MID, two row pairs per thread group ("dual", fp32).  Same operator, same HBM
+// layout and same arithmetic as row_fast_body<ROW_MID>; the elements are c2 (two
+// independent packed-complex sequences side by side), so every twiddle, address,
+// predicate and barrier is shared by four image rows, every shared-memory access
+// is 128 bits wide, and each thread carries two independent dependency chains.
+// Needs Ny % 4 == 0 (the caller falls back to the single-pair kernel otherwise).
+// ---------------------------------------------------------------------------
+template <class P> struct RowDual {
+    typedef typename P::T T;
+    typedef Fft3E<c2, -1, P::Fwd::RA, P::Fwd::RB, P::Fwd::RC, P::NT> F;
+    typedef Fft3E<c2, +1, P::Inv::RA, P::Inv::RB, P::Inv::RC, P::NT> I;
+    enum {
+        SEQ = imax(F::SEQ, I::SEQ),
+        LSM = (SEQ + 7) / 8 * 8 + 4,            // c2 elements per exchange buffer
+        THREADS = P::NTG,
+        STAGE_FLOATS = 4 * P::L,                // four measurement rows
+        VREG = imax(F::VREG, I::VREG)
+    };
+    struct Regs {
+        c2 v[VREG];
+        typename F::Tw twf;
+        typename I::Tw twi;
+        cplx<T> ramp0;
+    };
+    static LSTED_HD size_t smem_bytes() { return sizeof(c2) * 2 * (size_t)LSM + sizeof(T) * (size_t)STAGE_FLOATS; }
+    static_assert(sizeof(typename P::T) == 4, "dual row kernel is fp32 only");
+    static_assert((P::RCF - P::QH) * P::PX <= LSM, "mirror exchange must fit one buffer");
+};
+
+template <class P, class Ctx>
+LSTED_HD void row_mid_dual_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
+                                unsigned char* smem_raw, typename RowDual<P>::Regs* regs) {
+    typedef typename P::T T;
+    typedef RowDual<P> D;
+    typedef typename D::F F;
+    typedef typename D::I I;
+    typedef typename D::Regs R;
+    const ConvGeom& g = a.g;
+    const int Ny = g.Ny, Nx = g.Nx;
+    const int Lx = P::L, C = P::C;
+    const int qpi = Ny / 4;                        // quads per image
+    const int img = block / qpi;
+    const int y = 4 * (block - img * qpi);         // first of the four rows
+    const size_t real_off = (size_t)img * Ny * Nx;
+    const size_t spec_off = (size_t)img * g.nxb * C * Ny;   // Ny % 4 == 0: already even
+    const cplx<T>* tw = a.tw;
+    const int shift = g.sx;
+    const size_t xb_stride = (size_t)Ny * C;
+    c2* const s0 = (c2*)smem_raw;
+    c2* const s1 = s0 + D::LSM;
+    T* const stage = (T*)(s1 + D::LSM);
+    const cplx<T>* src = a.spec_in + spec_off;
+    const T* meas = a.aux + real_off + (size_t)y * Nx;
+
+    // L2 prefetch for the CTA one wave ahead (as in row_fast_body)
+    {
+        const int ahead = block + a.prefetch_ahead;
+        const int img2 = ahead / qpi;
+        if (a.prefetch_ahead > 0 && img2 < a.nimg) {
+            const int y2 = 4 * (ahead - img2 * qpi);
+            const cplx<T>* sp = a.spec_in + (size_t)img2 * g.nxb * C * Ny + (size_t)y2 * C;
+            const T* ax = a.aux + (size_t)img2 * Ny * Nx + (size_t)y2 * Nx;
+            cx.phase_nosync(regs, [&](int tid, R& r) {
+                (void)r;
+                for (int xb = tid; xb < g.nxb; xb += D::THREADS) prefetch_l2(sp + (size_t)xb * xb_stride);
+                prefetch_l2_range(ax, (size_t)4 * Nx * sizeof(T), tid, D::THREADS);
+            });
+        }
+    }
+    // Hermitian unpack of the four half spectra straight into inverse pass-A registers
+    cx.phase(regs, [&](int tid, R& r) {
+        const int t = tid;
+        LSTED_UNROLL
+        for (int rr = 0; rr < 4; ++rr) async_copy_row(stage + rr * P::L, meas + (size_t)rr * Nx, Nx, t, D::THREADS);
+        if (t >= P::NT) return;
+        I::load_tw(r.twi, t, tw);
+        F::load_tw(r.twf, t, tw);
+        r.ramp0 = tw[(t * shift) % Lx];
+        const cplx<T>* lo = src + ((size_t)(t / C) * Ny + y) * C + 2 * (t % C);
+        const int u = Lx - t;   // mirror of bin t; (u - q*NC) is the mirror of bin t + q*NC
+        LSTED_UNROLL
+        for (int q = 0; q < I::RA; ++q) {
+            const int i = t + q * P::NC;
+            bool upper = q > P::QH;
+            if (q == P::QH) upper = 2 * i > Lx;
+            const cplx<T>* p;
+            if (!upper) {
+                p = lo + (size_t)(q * (P::NC / C)) * xb_stride;
+            } else {
+                const int k = u - q * P::NC;
+                p = src + ((size_t)(k / C) * Ny + y) * C + 2 * (k % C);
+            }
+            cplx<T> A0, B0, A1, B1;   // rows y, y+1 and (one row pair = 2C elements further) y+2, y+3
+            load_pair(p, A0, B0);
+            load_pair(p + 2 * C, A1, B1);
+            if ((q == 0 && t == 0) || 2 * i == Lx) { A0.y = 0; B0.y = 0; A1.y = 0; B1.y = 0; }
+            // Z = A + iB below the Nyquist bin, conj(A) + i conj(B) of the mirror bin above it
+            r.v[q] = upper ? mk2(mk<T>(A0.x + B0.y, B0.x - A0.y), mk<T>(A1.x + B1.y, B1.x - A1.y))
+                           : mk2(mk<T>(A0.x - B0.y, A0.y + B0.x), mk<T>(A1.x - B1.y, A1.y + B1.x));
+        }
+        I::pass_a(r.v, t, s0);
+    });
+    cx.phase(regs, [&](int tid, R& r) {
+        const int t = tid;
+        if (t < P::NT) {
+            I::load_b(r.v, t, s0, r.twi);
+            I::pass_b(r.v, t, s1);
+        }
+        async_copy_wait_all();
+    });
+    // inverse pass C, ratio = measurement / clip(expected) on registers, forward pass A
+    cx.phase(regs, [&](int tid, R& r) {
+        const int t = tid;
+        if (t >= P::NT) return;
+        I::pass_c(r.v, t, s1, r.twi);
+        LSTED_UNROLL
+        for (int m = 0; m < I::MC; ++m) {
+            const int j = t + m * P::NT;
+            if (j < I::NC) {
+                LSTED_UNROLL
+                for (int q = 0; q < I::RC; ++q) {
+                    const int i = j + q * I::NC - shift;
+                    const c2 z = r.v[m * I::RC + q];
+                    c2 w = mk2(mk<T>(0, 0), mk<T>(0, 0));
+                    if (i >= 0 && i < Nx) {
+                        w.a.x = fast_div(stage[i], clip0(z.a.x));
+                        w.a.y = fast_div(stage[P::L + i], clip0(z.a.y));
+                        w.b.x = fast_div(stage[2 * P::L + i], clip0(z.b.x));
+                        w.b.y = fast_div(stage[3 * P::L + i], clip0(z.b.y));
+                    }
+                    r.v[m * I::RC + q] = w;
+                }
+            }
+        }
+        F::pass_a(r.v, t, s0);
+    });
+    cx.phase(regs, [&](int tid, R& r) {
+        const int t = tid;
+        if (t >= P::NT) return;
+        F::load_b(r.v, t, s0, r.twf);
+        F::pass_b(r.v, t, s1);
+    });
+    cx.phase(regs, [&](int tid, R& r) {
+        const int t = tid;
+        if (t >= P::NT) return;
+        F::pass_c(r.v, t, s1, r.twf);
+        LSTED_UNROLL
+        for (int q = P::QH; q < P::RCF; ++q) s0[(q - P::QH) * P::PX + t] = r.v[q];
+    });
+    cplx<T>* dst = a.spec_out + spec_off;
+    cx.phase_nosync(regs, [&](int tid, R& r) {
+        const int t = tid;
+        if (t >= P::NT) return;
+        const int tp = t == 0 ? 0 : P::NC - t;         // mirror thread
+        const int qoff = t == 0 ? 1 : 0;               // thread 0 mirrors onto itself, one q up
+        cplx<T>* pk = dst + ((size_t)(t / C) * Ny + y) * C + 2 * (t % C);
+        cplx<T> dq[P::QH + 2];
+        if (shift) Fft3E<cplx<T>, -1, P::Fwd::RA, P::Fwd::RB, P::Fwd::RC, P::NT>::template twiddle_powers<P::QH>(
+            tw[(P::NC * shift) % Lx], dq);
+        LSTED_UNROLL
+        for (int q = 0; q <= P::QH; ++q) {
+            const int k = t + q * P::NC;
+            cplx<T>* p = pk + (size_t)(q * (P::NC / C)) * xb_stride;
+            if (q == P::QH && 2 * k > Lx) {
+                // past the Nyquist bin: only the zero padding of the last column block
+                if (k < g.nxb * C) {
+                    store_pair(p, mk<T>(0, 0), mk<T>(0, 0));
+                    store_pair(p + 2 * C, mk<T>(0, 0), mk<T>(0, 0));
+                }
+                continue;
+            }
+            const c2 z1 = r.v[q];
+            c2 z2;
+            const int qm = P::RCF - 1 - q + qoff;      // q of the mirror bin in thread tp
+            if (t == 0 && q == 0) z2 = z1;
+            else z2 = s0[(qm - P::QH) * P::PX + tp];
+            // (z1 + conj z2)/2 and (z1 - conj z2)/(2i) of both sequences
+            cplx<T> oa0 = mk<T>((T)0.5 * (z1.a.x + z2.a.x), (T)0.5 * (z1.a.y - z2.a.y));
+            cplx<T> ob0 = mk<T>((T)0.5 * (z1.a.y + z2.a.y), (T)0.5 * (z2.a.x - z1.a.x));
+            cplx<T> oa1 = mk<T>((T)0.5 * (z1.b.x + z2.b.x), (T)0.5 * (z1.b.y - z2.b.y));
+            cplx<T> ob1 = mk<T>((T)0.5 * (z1.b.y + z2.b.y), (T)0.5 * (z2.b.x - z1.b.x));
+            if (shift) {
+                const cplx<T> ph = conj(q == 0 ? r.ramp0 : r.ramp0 * dq[q]);
+                oa0 = oa0 * ph; ob0 = ob0 * ph; oa1 = oa1 * ph; ob1 = ob1 * ph;
+            }
+            store_pair(p, oa0, ob0);
+            store_pair(p + 2 * C, oa1, ob1);
+        }
+    });
 }
 
 }  // namespace lsted

@@ -70,7 +70,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         tw.resize(g.Ly); fill_twiddles<T>(g.Ly, tw.data());
         tw_y = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * g.Ly);
         bk.upload(tw_y, tw.data(), sizeof(cplx<T>) * g.Ly);
-        otf = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * spec_elems(g, g.Ly) * K);
+        otf = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * otf_elems(g) * K);
         spec1 = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * spec_elems(g, g.Ny));
         specK = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * spec_elems(g, g.Ny) * K);
         true_object = (T*)bk.alloc(sizeof(T) * npix);
@@ -318,7 +318,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
             for (int k = 0; k < K; ++k) {
                 ColArgs<T> ct = col_args(g);
                 ct.src = specK + (same_input ? 0 : spec_elems(g, g.Ny) * k);
-                ct.otf = otf + spec_elems(g, g.Ly) * k;
+                ct.otf = otf + otf_elems(g) * k;
                 ct.dst = spec1; ct.K = 1;
                 bk.template launch_col<COL_HT, T>(g.nxb, ct);
                 RowArgs<T> rb = row_args(g);

@@ -118,6 +118,19 @@ LSTED_HD void async_copy_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
 }
+// Two adjacent complex numbers (the two rows of a row pair in the XB2 spectrum layout)
+// in one access: 16 bytes for fp32 (LDG.128 / STG.128), two 16-byte ones for fp64.
+template <typename T> LSTED_HD void load_pair(const cplx<T>* p, cplx<T>& a, cplx<T>& b) { a = p[0]; b = p[1]; }
+template <typename T> LSTED_HD void store_pair(cplx<T>* p, cplx<T> a, cplx<T> b) { p[0] = a; p[1] = b; }
+#ifdef __CUDA_ARCH__
+LSTED_HD void load_pair(const cplx<float>* p, cplx<float>& a, cplx<float>& b) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    a = mk<float>(v.x, v.y); b = mk<float>(v.z, v.w);
+}
+LSTED_HD void store_pair(cplx<float>* p, cplx<float> a, cplx<float> b) {
+    *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
+}
+#endif
 // CTA-wide counter in shared memory (host replay: threads run one after another)
 LSTED_HD int smem_counter_next(int* counter) {
 #ifdef __CUDA_ARCH__

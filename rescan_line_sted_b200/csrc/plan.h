@@ -110,7 +110,9 @@ inline const char* make_geom(int Ny, int Nx, int ny, int nx, int cplx_bytes, Con
     return "";
 }
 
-inline size_t spec_elems(const ConvGeom& g, int rows) { return (size_t)g.nxb * g.C * rows; }
+// elements of one spectrum array with `rows` rows: row spectra (XB2) round the rows up to even
+inline size_t spec_elems(const ConvGeom& g, int rows) { return (size_t)g.nxb * g.C * even_rows(rows); }
+inline size_t otf_elems(const ConvGeom& g) { return (size_t)g.nxb * g.C * g.Ly; }   // XB, all Ly rows
 inline int row_blocks(const ConvGeom& g) { return (((g.Ny + 1) / 2) + g.PR - 1) / g.PR; }
 inline size_t row_smem_bytes(const ConvGeom& g, int cplx_bytes) {
     return (size_t)2 * g.PR * g.Lpx * cplx_bytes;

@@ -51,10 +51,14 @@ static broadcast_cb g_broadcast = 0;
 extern "C" void emul_set_allreduce(allreduce_cb cb) { g_allreduce = cb; }
 extern "C" void emul_set_broadcast(broadcast_cb cb) { g_broadcast = cb; }
 
+static int g_dual_launches = 0;
+extern "C" int emul_dual_launches(void) { return g_dual_launches; }
+
 class HostBackend {
   public:
     explicit HostBackend(int) : bytes_(0), use_fast_(true) {}
     void set_fast_path(bool on) { use_fast_ = on; }
+    void set_row_dual(bool on) { row_dual_ = on; }
     int row_prefetch_distance() const { return 3; }
     void set_prefetch(bool) {}
     static int fast_cols(int L, int cplx_bytes) {
@@ -99,6 +103,9 @@ class HostBackend {
 
     template <int MODE, typename T> void launch_row(int grid, const lsted::RowArgs<T>& a) {
         typedef typename PlanFor<T>::type P;
+        if (use_fast_ && row_dual_ && MODE == lsted::ROW_MID && a.g.Lx == P::L && a.g.C == P::C &&
+            a.g.Ny % 4 == 0 && launch_row_mid_dual(a))
+            return;
         if (use_fast_ && a.g.Lx == P::L && a.g.C == P::C) {
             grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
 #pragma omp parallel
@@ -120,6 +127,23 @@ class HostBackend {
 #pragma omp for schedule(dynamic)
             for (int b = 0; b < grid; ++b) lsted::row_body<MODE, T>(cx, b, a, smem.data());
         }
+    }
+    bool launch_row_mid_dual(const lsted::RowArgs<double>&) { return false; }
+    bool launch_row_mid_dual(const lsted::RowArgs<float>& a) {
+        typedef lsted::RowDual<Plan2160f> D;
+        ++g_dual_launches;
+        const int grid = a.nimg * (a.g.Ny / 4);
+#pragma omp parallel
+        {
+            std::vector<lsted::c2> smem(D::smem_bytes() / sizeof(lsted::c2) + 1);
+            std::vector<D::Regs> regs(D::THREADS);
+            HostCtx cx;
+            cx.nthreads = D::THREADS;
+#pragma omp for schedule(dynamic)
+            for (int b = 0; b < grid; ++b)
+                lsted::row_mid_dual_body<Plan2160f>(cx, b, a, (unsigned char*)smem.data(), regs.data());
+        }
+        return true;
     }
     template <int MODE, typename T> void launch_col(int grid, const lsted::ColArgs<T>& a) {
         typedef typename PlanFor<T>::type P;
@@ -181,6 +205,7 @@ class HostBackend {
   private:
     size_t bytes_;
     bool use_fast_;
+    bool row_dual_ = false;
 };
 
 #define LSTED_BACKEND HostBackend

@@ -186,3 +186,60 @@ def test_fast_path_noise_field_is_the_sampler_field(lib):
                 lib.cdll.emul_poisson(float(flat[k, pix]), seed, pix, 1, one.ctypes.data_as(dp))
                 assert fields[0].reshape(2, -1)[k, pix] == one[0] + 1e-9
     assert (noiseless < 10).any() and (noiseless > 1e4).any()
+
+
+def test_dual_row_mid_matches_single_pair_kernel_and_oracle(lib):
+    """row_mid_dual_body (two row pairs per thread group, c2 elements) against the
+    single-pair fast kernel and the oracle on a 2160-wide geometry, fp32."""
+    rng = np.random.default_rng(8)
+    ny, nx = 8, 2048
+    psfs = rng.random((3, 5, 107)) + 0.1
+    psfs /= psfs.sum(axis=(1, 2), keepdims=True)
+    obj = rng.random((1, ny, nx)) + 0.05
+    meas = [rng.poisson(50.0, (1, ny, nx)).astype(np.float64) + 1e-9 for _ in range(3)]
+    est = {}
+    launches = {}
+    for dual in (1, 0):
+        before = lib.cdll.emul_dual_launches()
+        h = _lib.DeconvHandle(lib, psfs, (ny, nx), precision=32)
+        h.set_option('row_dual', dual)
+        h.create_data(obj, 1e7, 1)
+        assert h.info().Lx == 2160
+        for k in range(3):
+            h.set(_lib.NOISY, k, meas[k])
+        h.iterate(2)
+        est[dual] = h.get(_lib.ESTIMATE)
+        launches[dual] = lib.cdll.emul_dual_launches() - before
+        h.close()
+    assert launches == {1: 2, 0: 0}
+    o = orc.Deconvolver([p[None] for p in psfs])
+    o.create_data_from_object(obj, total_brightness=1e7, random_seed=1)
+    o.noisy_measurement = meas
+    o.iterate(); o.iterate()
+    assert rel_l2(est[1], est[0]) < 1e-6
+    assert rel_l2(est[1], o.estimate) < 1e-5
+    assert rel_l2(est[0], o.estimate) < 1e-5
+
+
+@pytest.mark.parametrize('shape', [(7, 2100), (6, 2048), (2, 2101)])
+def test_fast_rows_odd_and_ragged_shapes(lib, shape):
+    """2160-wide fast row kernels on images with an odd / non-multiple-of-4 number of
+    rows (XB2 spectrum layout: the missing last row has a never-read slot)."""
+    rng = np.random.default_rng(12)
+    psfs = rng.random((2, 3, 21))
+    x = rng.random((1,) + shape)
+    y = rng.random((2,) + shape)
+    for precision, tol in ((64, 1e-12), (32, 1e-5)):
+        o = orc.Deconvolver([p[None] for p in psfs])
+        h = _lib.DeconvHandle(lib, psfs, shape, precision=precision)
+        assert h.info().Lx == 2160
+        assert rel_l2(h.H(x), np.concatenate(o.H(x))) < tol
+        assert rel_l2(h.Ht(y, True), o.H_t([v[None] for v in y])) < tol
+        h.create_data(x, 1e8, 3)
+        o.create_data_from_object(x, 1e8, 3)
+        noisy = [h.get(_lib.NOISY, k) for k in range(2)]
+        o.noisy_measurement = noisy
+        h.iterate(2)
+        o.iterate(); o.iterate()
+        assert rel_l2(h.get(_lib.ESTIMATE), o.estimate) < 10 * tol
+        h.close()
