@@ -1,3 +1,8 @@
+#!/usr/bin/env python3
+"""Brute-force count of shared-memory wavefronts of the Fft3E exchange patterns
+(fft_static.cuh: pass A/B stores, load_b, pass C loads) for candidate pitches PA / PB,
+for a row CTA (one sequence) and a column CTA (C interleaved sequences), 8- and 16-byte
+elements.  This is where the RA = 15 pitches (PA = 147, PB = 255) come from."""
 # shared-memory wavefront count for the 8-byte-element exchange patterns of Fft3E
 import itertools
 def wavefronts(addrs, elem_bytes=8):
