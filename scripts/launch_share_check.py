@@ -10,10 +10,10 @@ import json
 import re
 import sys
 
-NAMES = [('row_fast_kernel<(int)0', 'row_fwd'), ('row_fast_kernel<(int)1', 'row_inv_store'),
-         ('row_fast_kernel<(int)2', 'row_inv_sim'), ('row_fast_kernel<(int)3', 'row_mid'),
-         ('row_mid_dual_kernel', 'row_mid'), ('row_fast_kernel<(int)4', 'row_final'),
-         ('col_fast_kernel<(int)1', 'col_h'), ('col_fast_kernel<(int)2', 'col_ht')]
+NAMES = [('row_fast_kernel<0', 'row_fwd'), ('row_fast_kernel<1', 'row_inv_store'),
+         ('row_fast_kernel<2', 'row_inv_sim'), ('row_fast_kernel<3', 'row_mid'),
+         ('row_mid_dual_kernel', 'row_mid'), ('row_fast_kernel<4', 'row_final'),
+         ('col_fast_kernel<1', 'col_h'), ('col_fast_kernel<2', 'col_ht')]
 
 
 def main(csv_path, json_path):
@@ -28,7 +28,7 @@ def main(csv_path, json_path):
         us = float(r[val_i].replace(',', '')) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(r[unit_i], 1.0)
         key = 'other'
         for pat, short in NAMES:
-            if pat in r[name_i]:
+            if pat in r[name_i].replace('(int)', ''):
                 key = short
         tot[key] += us
         cnt[key] += 1
