@@ -353,7 +353,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             const T* ax = (MODE == ROW_MID ? a.aux + (size_t)img2 * Ny * Nx : a.aux) + (size_t)y2 * Nx;
             cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {   // prefetches only: no barrier
                 (void)r;
-                for (int xb = tid; xb < g.nxb; xb += P::ROW_THREADS) prefetch_l2(sp + (size_t)xb * xb_stride);
+                for (int xb = tid; xb < g.nxb; xb += P::ROW_THREADS)
+                    prefetch_chunk(sp + (size_t)xb * xb_stride, (unsigned)(2 * P::PR * C * sizeof(cplx<T>)));
                 prefetch_l2_range(ax, (size_t)rows2 * Nx * sizeof(T), tid, P::ROW_THREADS);
                 if (MODE == ROW_FINAL)
                     prefetch_l2_range(a.real_out + (size_t)y2 * Nx, (size_t)rows2 * Nx * sizeof(T), tid,
@@ -655,7 +656,8 @@ LSTED_HD void row_mid_dual_body(Ctx& cx, int block, const RowArgs<typename P::T>
             const T* ax = a.aux + (size_t)img2 * Ny * Nx + (size_t)y2 * Nx;
             cx.phase_nosync(regs, [&](int tid, R& r) {
                 (void)r;
-                for (int xb = tid; xb < g.nxb; xb += D::THREADS) prefetch_l2(sp + (size_t)xb * xb_stride);
+                for (int xb = tid; xb < g.nxb; xb += D::THREADS)
+                    prefetch_chunk(sp + (size_t)xb * xb_stride, (unsigned)(4 * C * sizeof(cplx<T>)));
                 prefetch_l2_range(ax, (size_t)4 * Nx * sizeof(T), tid, D::THREADS);
             });
         }

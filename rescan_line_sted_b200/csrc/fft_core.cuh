@@ -37,6 +37,9 @@ template <typename T> LSTED_HD cplx<T> scale(cplx<T> a, T s) { return mk<T>(a.x 
 template <typename T> LSTED_HD cplx<T> fma_real(cplx<T> a, T s, cplx<T> b) {
     return mk<T>(a.x * s + b.x, a.y * s + b.y);
 }
+#ifndef LSTED_NO_BULK_PREFETCH
+#define LSTED_BULK_PREFETCH 1
+#endif
 #ifndef LSTED_NO_PACKED_F32X2
 #define LSTED_PACKED_F32X2 1
 #endif
@@ -183,9 +186,34 @@ LSTED_HD void mbar_wait(mbar_t* bar, unsigned parity) {
     (void)bar; (void)parity;
 #endif
 }
-// `nthreads` threads sweep [p, p + bytes) in 128-byte lines
-LSTED_HD void prefetch_l2_range(const void* p, size_t bytes, int tid, int nthreads) {
+// Bulk L2 prefetch (`cp.async.bulk.prefetch.L2`, one instruction for a whole contiguous
+// range, handled by the bulk-copy engine instead of one LSU request per 128-byte line).
+// p 16-byte aligned, bytes a multiple of 16.
+LSTED_HD void prefetch_l2_bulk(const void* p, unsigned bytes) {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+    (void)p; (void)bytes;
+#endif
+}
+// one small chunk with a per-thread address: the plain line prefetch (a bulk prefetch is a
+// warp-uniform instruction; with 32 different addresses the compiler serialises the lanes,
+// ~6 issue slots per chunk, which costs more than the LSU request it saves)
+LSTED_HD void prefetch_chunk(const void* p, unsigned bytes) {
+    (void)bytes;
+    prefetch_l2(p);
+}
+// [p, p + bytes) towards L2: split into `pieces` bulk prefetches issued by threads
+// 0..pieces-1 when alignment allows, else `nthreads` threads sweep it in 128-byte lines
+LSTED_HD void prefetch_l2_range(const void* p, size_t bytes, int tid, int nthreads, int pieces = 4) {
     const char* c = (const char*)p;
+#ifdef LSTED_BULK_PREFETCH
+    if ((((size_t)p) & 15) == 0 && bytes % ((size_t)16 * pieces) == 0 && bytes / pieces < (1u << 30)) {
+        const size_t piece = bytes / pieces;
+        if (tid < pieces) prefetch_l2_bulk(c + (size_t)tid * piece, (unsigned)piece);
+        return;
+    }
+#endif
     for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)nthreads * 128) prefetch_l2(c + off);
 }
 // multiply by -i (DIR = -1, forward) or +i (DIR = +1, inverse)
