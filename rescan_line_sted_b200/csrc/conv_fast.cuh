@@ -303,14 +303,20 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
 // ---------------------------------------------------------------------------
 // Row kernels
 // ---------------------------------------------------------------------------
-template <int MODE, class P, class Ctx>
+// Compile-time image geometry of the row kernels: with Nx and the crop offset known, the
+// per-pixel bounds tests `0 <= i < Nx` fold away for all but the first and last butterfly leg
+// (and the row strides become constants).  RowGeomRuntime keeps everything in registers.
+struct RowGeomRuntime { enum { NX = 0, SX = 0 }; };
+template <int NX_, int SX_> struct RowGeomFixed { enum { NX = NX_, SX = SX_ }; };
+
+template <int MODE, class P, class Ctx, class G = RowGeomRuntime>
 LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
-                            cplx<typename P::T>* smem, RowRegs<P>* regs) {
+                            cplx<typename P::T>* smem, RowRegs<P>* regs, G = G()) {
     typedef typename P::T T;
     typedef typename P::Fwd F;
     typedef typename P::Inv I;
     const ConvGeom& g = a.g;
-    const int Ny = g.Ny, Nx = g.Nx;
+    const int Ny = g.Ny, Nx = G::NX ? (int)G::NX : g.Nx;   // (checked at launch)
     const int Lx = P::L, C = P::C;  // == g.Lx, g.C (checked at launch)
     const int Py = (Ny + 1) / 2;
     const int bpi = (Py + P::PR - 1) / P::PR;
@@ -321,7 +327,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     const size_t spec_off = (size_t)img * g.nxb * C * Nye;
     const cplx<T>* tw = a.tw;
     // the data of a pair sit at logical positions shift + pixel during the transforms
-    const int shift = (MODE == ROW_FWD) ? 0 : g.sx;
+    const int shift = (MODE == ROW_FWD) ? 0 : (G::NX ? (int)G::SX : g.sx);
     const size_t xb_stride = (size_t)Nye * C;  // elements between consecutive column blocks
     // XB2: the pair (row y, row y+1) of column c sits at ((xb*Nye + y)*C + 2c) + {0, 1}
     const int NBUF = MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;

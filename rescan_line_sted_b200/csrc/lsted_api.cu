@@ -71,13 +71,15 @@ struct DeviceCtx {
 typedef lsted::FastPlan<float, 16, 9, 15, 144, LSTED_FAST_C32, LSTED_FAST_PR> Plan2160f;
 typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 
-template <int MODE, class P>
+// G: image geometry known at compile time (the 2048-wide / 107-wide-PSF headline case) or not
+typedef lsted::RowGeomFixed<2048, 53> RowGeom2048;
+template <int MODE, class P, class G = lsted::RowGeomRuntime>
 __global__ void __launch_bounds__(P::ROW_THREADS, sizeof(typename P::T) == 4 ? (LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
 row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceCtx cx;
     lsted::RowRegs<P> r;
-    lsted::row_fast_body<MODE, P>(cx, blockIdx.x, a,
+    lsted::row_fast_body<MODE, P, DeviceCtx, G>(cx, blockIdx.x, a,
                                   reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
 }
 
@@ -348,17 +350,24 @@ class CudaBackend {
     template <int MODE, class P> void launch_row_fast(int grid, const lsted::RowArgs<typename P::T>& a,
                                                       int kind) {
         const size_t smem = lsted::fast_row_smem_bytes<P>(MODE);
+        // fp32 kernels that index pixels have an instance with the headline geometry folded in
+        const bool fixed = sizeof(typename P::T) == 4 && MODE != lsted::ROW_FWD &&
+                           a.g.Nx == (int)RowGeom2048::NX && a.g.sx == (int)RowGeom2048::SX;
         static bool configured = false;
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (sizeof(typename P::T) == 4)
+                CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
         }
         before(kind);
         // the plan's own pairs-per-CTA decides the grid (the generic geometry may differ)
         const int fast_grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
         (void)grid;
-        row_fast_kernel<MODE, P><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
+        if (fixed) row_fast_kernel<MODE, P, RowGeom2048><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
+        else row_fast_kernel<MODE, P><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
         after();
     }
     template <int MODE, class P> void launch_col_fast(int grid, const lsted::ColArgs<typename P::T>& a,

@@ -114,9 +114,16 @@ class HostBackend {
                 std::vector<lsted::RowRegs<P> > regs(P::ROW_THREADS);
                 HostCtx cx;
                 cx.nthreads = P::ROW_THREADS;
+                // same dispatch as the CUDA backend: compile-time geometry for 2048-wide rows
+                const bool fixed = sizeof(T) == 4 && MODE != lsted::ROW_FWD && a.g.Nx == 2048 && a.g.sx == 53;
 #pragma omp for schedule(dynamic)
-                for (int b = 0; b < grid; ++b)
-                    lsted::row_fast_body<MODE, P>(cx, b, a, smem.data(), regs.data());
+                for (int b = 0; b < grid; ++b) {
+                    if (fixed)
+                        lsted::row_fast_body<MODE, P, HostCtx, lsted::RowGeomFixed<2048, 53> >(
+                            cx, b, a, smem.data(), regs.data());
+                    else
+                        lsted::row_fast_body<MODE, P>(cx, b, a, smem.data(), regs.data());
+                }
             }
             return;
         }
