@@ -36,6 +36,7 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
         COL_THREADS = NT_ * C_,
         COL_SMEM_ELEMS = 2 * C_ * LSM_COL,          // two ping-pong buffers
         COL_OTF_ELEMS = C_ * RA * RB * RC,          // + one staged OTF slab [L][C] (bulk copy)
+        COL_TW = 256,                               // + base twiddles
         // row CTA: PR groups of NTG threads (whole warps), one row pair each
         NTG = (NT_ + 31) / 32 * 32,
         LSM_ROW = (SEQ + 15) / 16 * 16 + 8,
@@ -54,6 +55,8 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
     static_assert(Fwd::MC == 1 && Fwd::NC == NT_, "row split assumes one pass-C butterfly per thread");
     static_assert(Inv::MA == 1 && Inv::NA == NT_, "row unpack assumes one pass-A butterfly per thread");
     static_assert(RC % 2 == 1, "row split assumes an odd last radix");
+    static_assert(RA * RC < 256 && RC * RA < 256 && NT_ <= 256 && NT_ * C_ >= 256 && RA * RB * RC >= 256,
+                  "base twiddles of both transforms must sit in the first COL_TW table entries");
     static_assert((RC - QH) * PX <= LSM_ROW, "mirror exchange must fit one row buffer");
 };
 
@@ -71,8 +74,13 @@ template <class P> struct RowRegs {
 #ifndef LSTED_COL_STAGE_OTF
 #define LSTED_COL_STAGE_OTF 1   // OTF slabs travel global -> shared by cp.async.bulk, one k ahead
 #endif
+// + the first COL_TW twiddles in shared memory: every base twiddle of the plan
+// (tw[RC*(j%RA)], tw[j], j < NT) has an index below that, and with >200 KB of shared memory
+// per CTA the L1 is too small to keep the global table resident (the LDGs at the head of
+// each pass went to L2)
 template <class P> LSTED_HD size_t fast_col_smem_bytes() {
-    return sizeof(cplx<typename P::T>) * (size_t)(P::COL_SMEM_ELEMS + (LSTED_COL_STAGE_OTF ? P::COL_OTF_ELEMS : 0)) +
+    return sizeof(cplx<typename P::T>) * (size_t)(P::COL_SMEM_ELEMS + P::COL_TW +
+                                                  (LSTED_COL_STAGE_OTF ? P::COL_OTF_ELEMS : 0)) +
            (LSTED_COL_STAGE_OTF ? 16 : 0);
 }
 template <class P> LSTED_HD size_t fast_row_smem_bytes(int mode) {
@@ -149,9 +157,9 @@ LSTED_HD void col_otf_product(ColRegs<P>& r, int t, int c, const cplx<typename P
             LSTED_UNROLL
             for (int q = 0; q < F::RC; ++q) {
                 const cplx<T> o = otf[(size_t)(j + q * F::NC) * P::C + c];
-                if (ACCUMULATE) {
-                    const cplx<T> p = r.v[m * F::RC + q] * o;
-                    r.keep[m * F::RC + q] = first ? p : r.keep[m * F::RC + q] + p;
+                if (ACCUMULATE) {   // keep starts at zero: one complex multiply-accumulate
+                    (void)first;
+                    r.keep[m * F::RC + q] = cmac(r.v[m * F::RC + q], o, r.keep[m * F::RC + q]);
                 } else {
                     r.v[m * F::RC + q] = r.keep[m * F::RC + q] * o;
                 }
@@ -171,7 +179,8 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     const int xb = block;
     const size_t slab_ly = (size_t)P::C * Ly, img_ly = (size_t)g.nxb * slab_ly;
     const size_t slab_ny = (size_t)P::C * even_rows(Ny), img_ny = (size_t)g.nxb * slab_ny;   // XB2
-    const cplx<T>* tw = a.tw;
+    cplx<T>* const tw_s = smem + (size_t)P::COL_SMEM_ELEMS;   // base twiddles (filled below)
+    const cplx<T>* tw = tw_s;
     cplx<T>* const buf0 = smem;
     cplx<T>* const buf1 = smem + (size_t)P::C * P::LSM_COL;
     const int K = a.K;
@@ -185,12 +194,17 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     // orientation k+1 is requested as soon as every thread is done with slab k and
     // lands while the transform of k runs (no registers, no per-thread copy work).
     const bool stage = LSTED_COL_STAGE_OTF != 0;
-    cplx<T>* const otf_s = smem + (size_t)P::COL_SMEM_ELEMS;
+    cplx<T>* const otf_s = tw_s + P::COL_TW;
     mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
     const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(cplx<T>));
     const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
     cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-        (void)r;   // (hoisting base twiddles here costs spills at 96 registers / 576 threads)
+        // (hoisting base twiddles into registers costs spills at 96 registers / 576 threads)
+        if (tid < P::COL_TW) tw_s[tid] = a.tw[tid];
+        if (MODE == COL_HT) {
+            LSTED_UNROLL
+            for (int i = 0; i < P::NKEEP; ++i) r.keep[i] = mk<T>(0, 0);
+        }
         if (stage && tid == 0) mbar_init(mbar);
     });
     if (MODE == COL_H) {

@@ -73,6 +73,17 @@ LSTED_HD cplx<float> fma_real(cplx<float> a, float s, cplx<float> b) {
 }
 #endif
 template <typename T> LSTED_HD cplx<T> conj(cplx<T> a) { return mk<T>(a.x, -a.y); }
+// a * b + c
+template <typename T> LSTED_HD cplx<T> cmac(cplx<T> a, cplx<T> b, cplx<T> c) {
+    return mk<T>(a.x * b.x - a.y * b.y + c.x, a.x * b.y + a.y * b.x + c.y);
+}
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && defined(LSTED_PACKED_F32X2)
+LSTED_HD cplx<float> cmac(cplx<float> a, cplx<float> b, cplx<float> c) {   // 2 x FFMA2
+    const float2 t = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.x), make_float2(c.x, c.y));
+    const float2 r = __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), t);
+    return mk<float>(r.x, r.y);
+}
+#endif
 // Branch-free fp32 division (MUFU.RCP based, <= 2 ulp) so the compiler can keep
 // many independent loads/divisions in flight; fp64 divides exactly.
 LSTED_HD float fast_div(float a, float b) {
