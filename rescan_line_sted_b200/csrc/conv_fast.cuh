@@ -168,14 +168,20 @@ LSTED_HD void col_otf_product(ColRegs<P>& r, int t, int c, const cplx<typename P
     }
 }
 
-template <int MODE, class P, class Ctx>
+// Compile-time image geometry of the column kernels (rows and crop offset): as for the row
+// kernels, the `0 <= y < Ny` tests then survive only on the first and last butterfly leg.
+struct ColGeomRuntime { enum { NY = 0, SY = 0 }; };
+template <int NY_, int SY_> struct ColGeomFixed { enum { NY = NY_, SY = SY_ }; };
+
+template <int MODE, class P, class Ctx, class G = ColGeomRuntime>
 LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
-                            cplx<typename P::T>* smem, ColRegs<P>* regs) {
+                            cplx<typename P::T>* smem, ColRegs<P>* regs, G = G()) {
     typedef typename P::T T;
     typedef typename P::Fwd F;
     typedef typename P::Inv I;
     const ConvGeom& g = a.g;
-    const int Ny = g.Ny, Ly = P::L;  // == g.Ly (checked at launch)
+    const int Ny = G::NY ? (int)G::NY : g.Ny, Ly = P::L;  // == g.Ly (checked at launch)
+    const int sy = G::NY ? (int)G::SY : g.sy;
     const int xb = block;
     const size_t slab_ly = (size_t)P::C * Ly, img_ly = (size_t)g.nxb * slab_ly;
     const size_t slab_ny = (size_t)P::C * even_rows(Ny), img_ny = (size_t)g.nxb * slab_ny;   // XB2
@@ -235,7 +241,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                     for (int i = 0; i < P::NKEEP; ++i) r.keep[i] = r.v[i];
                 } else {
                     I::pass_c(r.v, t, s1, tw);
-                    col_store_inv_c<P>(r.v, t, c, dst0 + (size_t)(k - 1) * img_ny, g.sy, Ny);
+                    col_store_inv_c<P>(r.v, t, c, dst0 + (size_t)(k - 1) * img_ny, sy, Ny);
                 }
                 if (k < K) {
                     if (stage) {
@@ -309,7 +315,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
         LSTED_COL_IDS
         I::pass_c(r.v, t, s1, tw);
-        col_store_inv_c<P>(r.v, t, c, dst, g.sy, Ny);
+        col_store_inv_c<P>(r.v, t, c, dst, sy, Ny);
     });
 #undef LSTED_COL_IDS
 }

@@ -93,13 +93,14 @@ row_mid_dual_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
     lsted::row_mid_dual_body<P>(cx, blockIdx.x, a, smem_raw, &r);
 }
 
-template <int MODE, class P>
+typedef lsted::ColGeomFixed<2048, 53> ColGeom2048;
+template <int MODE, class P, class G = lsted::ColGeomRuntime>
 __global__ void __launch_bounds__(P::COL_THREADS, 1)
 col_fast_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceCtx cx;
     lsted::ColRegs<P> r;
-    lsted::col_fast_body<MODE, P>(cx, blockIdx.x, a,
+    lsted::col_fast_body<MODE, P, DeviceCtx, G>(cx, blockIdx.x, a,
                                   reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
 }
 
@@ -373,14 +374,20 @@ class CudaBackend {
     template <int MODE, class P> void launch_col_fast(int grid, const lsted::ColArgs<typename P::T>& a,
                                                       int kind) {
         const size_t smem = lsted::fast_col_smem_bytes<P>();
+        const bool fixed = sizeof(typename P::T) == 4 && a.g.Ny == (int)ColGeom2048::NY &&
+                           a.g.sy == (int)ColGeom2048::SY && a.rows_in == a.g.Ny;
         static bool configured = false;
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (sizeof(typename P::T) == 4)
+                CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P, ColGeom2048>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
         }
         before(kind);
-        col_fast_kernel<MODE, P><<<grid, P::COL_THREADS, smem, stream_>>>(a);
+        if (fixed) col_fast_kernel<MODE, P, ColGeom2048><<<grid, P::COL_THREADS, smem, stream_>>>(a);
+        else col_fast_kernel<MODE, P><<<grid, P::COL_THREADS, smem, stream_>>>(a);
         after();
     }
     template <int MODE> bool try_fast_row(int grid, const lsted::RowArgs<float>& a, int kind) {

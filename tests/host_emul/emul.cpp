@@ -161,10 +161,16 @@ class HostBackend {
                 std::vector<lsted::ColRegs<P> > regs(P::COL_THREADS);
                 HostCtx cx;
                 cx.nthreads = P::COL_THREADS;
+                const bool fixed = sizeof(T) == 4 && a.g.Ny == 2048 && a.g.sy == 53;
 #pragma omp for schedule(dynamic)
-                for (int b = 0; b < grid; ++b)
-                    lsted::col_fast_body<(MODE == lsted::COL_OTF ? lsted::COL_H : MODE), P>(
-                        cx, b, a, smem.data(), regs.data());
+                for (int b = 0; b < grid; ++b) {
+                    if (fixed)
+                        lsted::col_fast_body<(MODE == lsted::COL_OTF ? lsted::COL_H : MODE), P, HostCtx,
+                                             lsted::ColGeomFixed<2048, 53> >(cx, b, a, smem.data(), regs.data());
+                    else
+                        lsted::col_fast_body<(MODE == lsted::COL_OTF ? lsted::COL_H : MODE), P>(
+                            cx, b, a, smem.data(), regs.data());
+                }
             }
             return;
         }
