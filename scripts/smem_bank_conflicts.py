@@ -141,3 +141,20 @@ for PA,PB in ((145,241),(146,255),(145,255),(147,255),(149,255),(159,255)):
 print('fwd', colplan(16,9,15,144,135,240))
 print('fp64 rows inv (147,255)', plan16(15,9,16,144,147,255), '(145,255)', plan16(15,9,16,144,145,255))
 print('fp32 rows inv (147,255)', plan(15,9,16,144,147,255))
+print('--- row plan 12 x 12 x 15, 180 threads')
+for PA in (180, 181, 183, 185, 187, 189, 191):
+    for PB in (180, 181, 183, 185, 187, 189, 191):
+        a, i, seq = plan(12, 12, 15, 180, PA, PB)
+        if a <= i * 1.02: print('fwd', PA, PB, a, i, seq)
+best = []
+for PA in range(144, 160):
+    for PB in range(180, 200):
+        a, i, seq = plan(15, 12, 12, 180, PA, PB)
+        best.append((a, seq, PA, PB, i))
+best.sort(); print('inv', best[:6])
+bestf = []
+for PA in range(180, 200):
+    for PB in range(180, 200):
+        a, i, seq = plan(12, 12, 15, 180, PA, PB)
+        bestf.append((a, seq, PA, PB, i))
+bestf.sort(); print('fwd', bestf[:6])
