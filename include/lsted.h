@@ -131,6 +131,14 @@ int lsted_deconv_simulate(lsted_deconv* h, double total_brightness, int rescale,
 enum { LSTED_NCCL_UNIQUE_ID_BYTES = 128 };
 int lsted_nccl_unique_id(char* out);
 int lsted_deconv_shard(lsted_deconv* h, int rank, int world, int k_offset, const char* unique_id);
+/* Orientation sharding, fast path: sum the partial H_t spectra of the ranks INSIDE the column
+ * kernel over NVLink peer memory (no all-reduce after it).  One process per GPU: every rank
+ * exports LSTED_P2P_HANDLE_BYTES of CUDA-IPC handles (after lsted_deconv_shard), the caller
+ * all-gathers them (torch.distributed) and hands every rank the [world][...] table.  Without
+ * these two calls the reduction is the NCCL all-reduce of lsted_deconv_shard.              */
+#define LSTED_P2P_HANDLE_BYTES 192
+int lsted_deconv_p2p_export(lsted_deconv* h, char* handles_out, int capacity);
+int lsted_deconv_p2p_attach(lsted_deconv* h, const char* all_handles, int world);
 /* iterate() n times (:520-531); no host transfers.                                 */
 int lsted_deconv_iterate(lsted_deconv* h, int n);
 /* attribute access; k is the PSF index for the per-PSF lists, else 0.

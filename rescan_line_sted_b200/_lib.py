@@ -62,6 +62,8 @@ _DECONV_SIGNATURES = {
                               ctypes.c_uint64],
     'lsted_deconv_shard': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                            ctypes.c_int, ctypes.c_char_p],
+    'lsted_deconv_p2p_export': [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int],
+    'lsted_deconv_p2p_attach': [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int],
     'lsted_deconv_iterate': [ctypes.c_void_p, ctypes.c_int],
     'lsted_deconv_get': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                          c_double_p],
@@ -215,6 +217,19 @@ class DeconvHandle:
         """Orientation sharding: this handle holds PSFs k_offset..k_offset+K-1."""
         self.lib.call('lsted_deconv_shard', self._h, int(rank), int(world),
                       int(k_offset), unique_id)
+
+    P2P_HANDLE_BYTES = 192
+
+    def p2p_export(self):
+        """CUDA-IPC handles of this rank's peer-memory reduction buffers (bytes)."""
+        buf = ctypes.create_string_buffer(self.P2P_HANDLE_BYTES)
+        self.lib.call('lsted_deconv_p2p_export', self._h, buf, self.P2P_HANDLE_BYTES)
+        return buf.raw
+
+    def p2p_attach(self, all_handles, world):
+        """all_handles: the exports of ranks 0..world-1, concatenated."""
+        assert len(all_handles) == world * self.P2P_HANDLE_BYTES
+        self.lib.call('lsted_deconv_p2p_attach', self._h, all_handles, int(world))
 
     def iterate(self, n=1):
         self.lib.call('lsted_deconv_iterate', self._h, int(n))

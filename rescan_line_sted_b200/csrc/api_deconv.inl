@@ -158,6 +158,25 @@ extern "C" int lsted_deconv_shard(lsted_deconv* h, int rank, int world, int k_of
     LSTED_CATCH
 }
 
+extern "C" int lsted_deconv_p2p_export(lsted_deconv* h, char* handles_out, int capacity) {
+    if (!h || !handles_out) return set_error(LSTED_ERR_ARG, "null pointer");
+    if (capacity < LSTED_P2P_HANDLE_BYTES) return set_error(LSTED_ERR_ARG, "handle buffer too small");
+    LSTED_TRY
+    h->bk->activate();
+    h->e->p2p_export(handles_out);
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
+extern "C" int lsted_deconv_p2p_attach(lsted_deconv* h, const char* all_handles, int world) {
+    if (!h || !all_handles || world < 2) return set_error(LSTED_ERR_ARG, "bad arguments");
+    LSTED_TRY
+    h->bk->activate();
+    h->e->p2p_attach(all_handles);
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
 extern "C" int lsted_deconv_iterate(lsted_deconv* h, int n) {
     if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
     LSTED_TRY

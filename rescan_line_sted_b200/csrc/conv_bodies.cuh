@@ -204,6 +204,7 @@ LSTED_HD void row_body(Ctx& cx, int block, const RowArgs<T>& a, cplx<T>* smem) {
     });
 }
 
+enum { kMaxPeers = 8 };
 enum ColMode {
     COL_OTF = 0,  // zero-padded forward transform, scaled, all Ly rows stored
     COL_H = 1,    // one input spectrum -> K products -> K inverse transforms
@@ -220,6 +221,14 @@ template <typename T> struct ColArgs {
     int rows_in;            // valid input rows (zero padded up to Ly)
     int src_same;           // HT: every k reads the same input spectrum (H_t of all-ones images)
     T scale;                // OTF: 1/(Lx*Ly)
+    // HT of the fast path with orientations sharded over GPUs: the cross-GPU sum is done inside
+    // the kernel over NVLink peer memory (see col_fast_body).  world <= 1: off.
+    int p2p_world, p2p_rank;
+    unsigned p2p_epoch;               // number of this fused reduction (1, 2, ...)
+    cplx<T>* p2p_recv[kMaxPeers];     // per rank: [world][nxb][Ly*C] partial Fourier-domain sums
+    unsigned* p2p_flags[kMaxPeers];   // per rank: [world][nxb] "partial of (src, block) landed" epochs
+    cplx<T>* p2p_spec[kMaxPeers];     // per rank: the output spectrum (XB2, Ny rows)
+    unsigned* p2p_done[kMaxPeers];    // per rank: count of finished blocks
 };
 
 // Column-block kernel body.  smem: 3 * C * Lpy complex.

@@ -200,6 +200,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     // orientation k+1 is requested as soon as every thread is done with slab k and
     // lands while the transform of k runs (no registers, no per-thread copy work).
     const bool stage = LSTED_COL_STAGE_OTF != 0;
+    const bool p2p = MODE == COL_HT && a.p2p_world > 1;   // fused cross-GPU reduction (below)
     cplx<T>* const otf_s = tw_s + P::COL_TW;
     mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
     const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(cplx<T>));
@@ -291,7 +292,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
             if (k < K) {
                 col_load_fwd_a<P>(r.v, t, c, src0 + (a.src_same ? 0 : (size_t)k * img_ny), Ny);
                 F::pass_a(r.v, t, s0);
-            } else {
+            } else if (!p2p) {
                 LSTED_UNROLL
                 for (int i = 0; i < P::NKEEP; ++i) r.v[i] = r.keep[i];
                 I::pass_a(r.v, t, s0);
@@ -306,16 +307,73 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
             F::pass_b(r.v, t, s1);
         });
     }
+    if (p2p) {
+        // Orientations sharded over GPUs: `keep` is this rank's partial Fourier-domain sum.
+        // The cross-GPU sum runs inside this kernel over NVLink peer memory, block by
+        // block, overlapped with the transforms of the other blocks (no all-reduce after the
+        // kernel).  Block xb is finished by rank xb % world:
+        //   other ranks push their partial into the owner's receive slab and raise a flag;
+        //   the owner waits for world-1 flags, adds, runs the ONE inverse transform and
+        //   writes the cropped column block into the spectrum of every rank, then counts the
+        //   block as done on every rank (row_final waits for nxb counts per reduction).
+        const int world = a.p2p_world, me = a.p2p_rank, owner = xb % world;
+        const size_t part = (size_t)P::NKEEP * P::COL_THREADS;             // elements per partial
+        if (owner != me) {
+            cplx<T>* out = a.p2p_recv[owner] + ((size_t)me * g.nxb + xb) * part;
+            cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+                LSTED_UNROLL
+                for (int i = 0; i < P::NKEEP; ++i) out[(size_t)i * P::COL_THREADS + tid] = r.keep[i];
+                sys_fence();
+            });
+            cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
+                (void)r;
+                if (tid == 0) flag_release(a.p2p_flags[owner] + (size_t)me * g.nxb + xb, a.p2p_epoch);
+            });
+            return;
+        }
+        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+            (void)r;
+            if (tid < world && tid != me)
+                flag_wait(a.p2p_flags[me] + (size_t)tid * g.nxb + xb, a.p2p_epoch);
+        });
+        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+            LSTED_COL_IDS
+            for (int src = 0; src < world; ++src) {
+                if (src == me) continue;
+                const cplx<T>* in = a.p2p_recv[me] + ((size_t)src * g.nxb + xb) * part;
+                LSTED_UNROLL
+                for (int i = 0; i < P::NKEEP; ++i)
+                    r.keep[i] = r.keep[i] + load_l2(in + (size_t)i * P::COL_THREADS + tid);
+            }
+            LSTED_UNROLL
+            for (int i = 0; i < P::NKEEP; ++i) r.v[i] = r.keep[i];
+            I::pass_a(r.v, t, s0);
+        });
+    }
     cplx<T>* dst = a.dst + (size_t)xb * slab_ny;
     cx.phase(regs, [&](int tid, ColRegs<P>& r) {
         LSTED_COL_IDS
         I::load_b(r.v, t, s0, tw);
         I::pass_b(r.v, t, s1);
     });
-    cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
+    if (!p2p) {
+        cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
+            LSTED_COL_IDS
+            I::pass_c(r.v, t, s1, tw);
+            col_store_inv_c<P>(r.v, t, c, dst, sy, Ny);
+        });
+        return;
+    }
+    cx.phase(regs, [&](int tid, ColRegs<P>& r) {
         LSTED_COL_IDS
         I::pass_c(r.v, t, s1, tw);
-        col_store_inv_c<P>(r.v, t, c, dst, sy, Ny);
+        for (int peer = 0; peer < a.p2p_world; ++peer)
+            col_store_inv_c<P>(r.v, t, c, a.p2p_spec[peer] + (size_t)xb * slab_ny, sy, Ny);
+        sys_fence();
+    });
+    cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
+        (void)r;
+        if (tid < a.p2p_world) sys_counter_add(a.p2p_done[tid], 1u);
     });
 #undef LSTED_COL_IDS
 }

@@ -46,6 +46,8 @@ class EngineBase {
     virtual void forget_normalization() = 0;
     virtual void set_sharding(int rank, int world, int k_offset) = 0;
     virtual void set_exact_clip(bool on) = 0;
+    virtual void p2p_export(char* handles_out) = 0;                       // kIpcBytes
+    virtual void p2p_attach(const char* all_handles) = 0;                 // [world][kIpcBytes]
     virtual void info(EngineInfo* out) = 0;
 };
 
@@ -59,7 +61,8 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
 
     DeconvEngine(BK& backend, int K_, int ny_, int nx_, int Ny, int Nx, int force_L = 0)
         : K(K_), ny(ny_), nx(nx_), iterations_done(0), have_norm(false), have_estimate(false),
-          exact_clip(false), rank(0), world(1), k_offset(0), bk(backend), tmpK(0) {
+          exact_clip(false), rank(0), world(1), k_offset(0), bk(backend), tmpK(0), p2p_recv(0),
+          p2p_flags(0), p2p_words(0) {
         const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g, &BK::fast_cols, force_L);
         if (why[0]) throw std::string(why);
         npix = (size_t)Ny * Nx;
@@ -85,7 +88,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     }
     ~DeconvEngine() {
         void* all[] = {tw_x, tw_y, otf, spec1, specK, true_object, estimate, norm,
-                       scratch, noiseless, noisy, stage64, object64, partial, tmpK};
+                       scratch, noiseless, noisy, stage64, object64, partial, tmpK, p2p_recv, p2p_flags};
         for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) bk.free(all[i]);
     }
 
@@ -182,6 +185,21 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         rank = rank_; world = world_; k_offset = k_offset_;
         have_norm = false;
     }
+    // Fused cross-GPU H_t reduction (fast path only): receive slabs for the partial sums of
+    // every (source rank, column block) and the flag / counter words, exported to the peers.
+    void p2p_export(char* out) {
+        if (world < 2) throw std::string("p2p_export: shard the handle first");
+        if (!p2p_recv) {
+            const size_t part = (size_t)g.C * g.Ly;
+            p2p_recv = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * part * g.nxb * world);
+            p2p_words = (size_t)world * g.nxb;
+            p2p_flags = (unsigned*)bk.alloc(sizeof(unsigned) * (p2p_words + 32));
+            bk.zero_bytes(p2p_flags, sizeof(unsigned) * (p2p_words + 32));
+            bk.sync();
+        }
+        bk.p2p_export(p2p_recv, p2p_flags, spec1, out);
+    }
+    void p2p_attach(const char* all) { bk.p2p_attach(rank, world, all, p2p_words); }
     void reduce_over_ranks(cplx<T>* spec) {
         if (world > 1) bk.all_reduce_sum((T*)spec, 2 * spec_elems(g, g.Ny));
     }
@@ -206,8 +224,15 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
             if (!exact_clip) {
                 ColArgs<T> ct = col_args(g);
                 ct.src = specK; ct.dst = spec1; ct.K = K;
-                bk.template launch_col<COL_HT, T>(g.nxb, ct);
-                reduce_over_ranks(spec1);   // orientation shards: sum of partial spectra
+                if (world > 1 && bk.p2p_ready(g, (int)sizeof(cplx<T>))) {
+                    // orientation shards: the sum over ranks happens inside the kernel (peer memory)
+                    bk.p2p_fill(ct);
+                    bk.template launch_col<COL_HT, T>(g.nxb, ct);
+                    bk.p2p_wait(g.nxb);
+                } else {
+                    bk.template launch_col<COL_HT, T>(g.nxb, ct);
+                    reduce_over_ranks(spec1);   // orientation shards: NCCL sum of partial spectra
+                }
                 RowArgs<T> rf = row_args(g);
                 rf.nimg = 1; rf.spec_in = spec1; rf.spec_out = spec1;
                 rf.real_out = estimate; rf.aux = norm;
@@ -285,6 +310,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     T *true_object, *estimate, *norm, *scratch, *noiseless, *noisy;
     double *stage64, *object64, *partial;
     T* tmpK;  // K images, allocated on first use by the host-array forms of H / H_t
+    cplx<T>* p2p_recv; unsigned* p2p_flags; size_t p2p_words;
     T* tmp_images() {
         if (!tmpK) tmpK = (T*)bk.alloc(sizeof(T) * npix * K);
         return tmpK;

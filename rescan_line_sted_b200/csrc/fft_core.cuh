@@ -149,6 +149,61 @@ LSTED_HD void store_pair(cplx<float>* p, cplx<float> a, cplx<float> b) {
     *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
 }
 #endif
+// System-scope (cross-GPU, NVLink peer memory) synchronisation primitives of the fused
+// H_t reduction (conv_fast.cuh, COL_HT with P2P): release/acquire flags and counters that
+// live in one GPU's memory and are written by kernels running on its peers.
+LSTED_HD void sys_fence() {
+#ifdef __CUDA_ARCH__
+    __threadfence_system();
+#endif
+}
+LSTED_HD void flag_release(unsigned* p, unsigned v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+LSTED_HD unsigned flag_acquire(const unsigned* p) {
+#ifdef __CUDA_ARCH__
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+// spin until the counter has reached `target` (wrap-around safe)
+LSTED_HD void flag_wait(const unsigned* p, unsigned target) {
+#ifdef __CUDA_ARCH__
+    while ((int)(flag_acquire(p) - target) < 0) __nanosleep(64);
+#else
+    (void)p; (void)target;
+#endif
+}
+LSTED_HD void sys_counter_add(unsigned* p, unsigned v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    *p += v;
+#endif
+}
+// load that bypasses L1 (data written by a peer GPU during this kernel)
+template <typename T> LSTED_HD cplx<T> load_l2(const cplx<T>* p) {
+#ifdef __CUDA_ARCH__
+    cplx<T> r;
+    if (sizeof(T) == 4) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+        r.x = (T)v.x; r.y = (T)v.y;
+    } else {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+        r.x = (T)v.x; r.y = (T)v.y;
+    }
+    return r;
+#else
+    return *p;
+#endif
+}
 // CTA-wide counter in shared memory (host replay: threads run one after another)
 LSTED_HD int smem_counter_next(int* counter) {
 #ifdef __CUDA_ARCH__

@@ -137,6 +137,13 @@ __global__ void __launch_bounds__(kEwThreads) win_kernel(const lsted::WinArgs<T>
         lsted::win_apply<OP, T>(a, e);
 }
 
+// Fused cross-GPU H_t reduction (conv_fast.cuh): the kernels after it on this stream may read
+// the spectrum only when all column blocks -- finished by their owner ranks, over NVLink --
+// have been counted.
+__global__ void p2p_wait_kernel(const unsigned* done, unsigned target) {
+    if (threadIdx.x == 0) lsted::flag_wait(done, target);
+}
+
 // Two-stage deterministic sum in double: per-block partials, then block 0.
 __global__ void __launch_bounds__(256) sum_partial_kernel(const double* x, size_t n, double* partial) {
     __shared__ double sh[256];
@@ -243,6 +250,7 @@ class CudaBackend {
     }
     ~CudaBackend() {
         cudaSetDevice(device_);
+        for (size_t i = 0; i < p2p_opened_.size(); ++i) cudaIpcCloseMemHandle(p2p_opened_[i]);
         if (comm_) nccl_api().CommDestroy(comm_);
         for (size_t i = 0; i < ev_pool_.size(); ++i) cudaEventDestroy(ev_pool_[i]);
         if (t0_) cudaEventDestroy(t0_);
@@ -280,6 +288,59 @@ class CudaBackend {
         NCCL_CHECK(nccl_api().Broadcast(p, p, n, ncclDouble, root, comm_, stream_));
         after();
     }
+    // ---- fused cross-GPU reduction over peer memory (orientation sharding, fast path) ----
+    // Buffers are plain cudaMalloc allocations exported / opened with CUDA IPC (one process
+    // per GPU); `handles` = [world][3] cudaIpcMemHandle_t: receive slabs, flags, spectrum.
+    enum { kIpcBytes = 3 * (int)sizeof(cudaIpcMemHandle_t) };
+    void p2p_export(void* recv, void* flags, void* spec, char* out) {
+        void* ptrs[3] = {recv, flags, spec};
+        for (int i = 0; i < 3; ++i) {
+            cudaIpcMemHandle_t h;
+            CUDA_CHECK(cudaIpcGetMemHandle(&h, ptrs[i]));
+            memcpy(out + i * sizeof(h), &h, sizeof(h));
+        }
+        p2p_local_[0] = recv; p2p_local_[1] = flags; p2p_local_[2] = spec;
+    }
+    void p2p_attach(int rank, int world, const char* handles, size_t done_offset_words) {
+        if (world > lsted::kMaxPeers) {
+            lsted::ApiError e; e.code = LSTED_ERR_ARG; e.msg = "too many ranks for the peer-memory reduction"; throw e;
+        }
+        for (int r = 0; r < world; ++r) {
+            void* ptrs[3];
+            for (int i = 0; i < 3; ++i) {
+                if (r == rank) { ptrs[i] = p2p_local_[i]; continue; }
+                cudaIpcMemHandle_t h;
+                memcpy(&h, handles + ((size_t)r * 3 + i) * sizeof(h), sizeof(h));
+                CUDA_CHECK(cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
+                p2p_opened_.push_back(ptrs[i]);
+            }
+            p2p_recv_[r] = ptrs[0];
+            p2p_flags_[r] = (unsigned*)ptrs[1];
+            p2p_done_[r] = (unsigned*)ptrs[1] + done_offset_words;
+            p2p_spec_[r] = ptrs[2];
+        }
+        p2p_rank_ = rank; p2p_world_ = world; p2p_epoch_ = 0;
+    }
+    bool p2p_ready(const lsted::ConvGeom& g, int cplx_bytes) const {
+        return p2p_world_ > 1 && use_fast_ &&
+               (cplx_bytes == 8 ? plan_fits_cols<Plan2160f>(g) : plan_fits_cols<Plan2160d>(g));
+    }
+    template <typename T> void p2p_fill(lsted::ColArgs<T>& a) {
+        a.p2p_world = p2p_world_; a.p2p_rank = p2p_rank_; a.p2p_epoch = ++p2p_epoch_;
+        for (int r = 0; r < p2p_world_; ++r) {
+            a.p2p_recv[r] = (lsted::cplx<T>*)p2p_recv_[r];
+            a.p2p_flags[r] = p2p_flags_[r];
+            a.p2p_spec[r] = (lsted::cplx<T>*)p2p_spec_[r];
+            a.p2p_done[r] = p2p_done_[r];
+        }
+    }
+    // blocks counted on this rank so far = epoch * nxb
+    void p2p_wait(int nxb) {
+        before(KK_EW);
+        p2p_wait_kernel<<<1, 32, 0, stream_>>>(p2p_done_[p2p_rank_], p2p_epoch_ * (unsigned)nxb);
+        after();
+    }
+    void zero_bytes(void* p, size_t n) { CUDA_CHECK(cudaMemsetAsync(p, 0, n, stream_)); }
     void fill_double(double* p, size_t n, double v) {
         if (v != 0.0) { lsted::ApiError e; e.code = LSTED_ERR_ARG; e.msg = "fill_double: zero only"; throw e; }
         CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(double), stream_));
@@ -532,6 +593,11 @@ class CudaBackend {
     size_t bytes_;
     bool profile_, use_fast_;
     std::map<void*, size_t> sizes_;   // live allocations (for lsted_deconv_info)
+    void* p2p_local_[3] = {0, 0, 0};
+    void* p2p_recv_[lsted::kMaxPeers]; unsigned* p2p_flags_[lsted::kMaxPeers];
+    void* p2p_spec_[lsted::kMaxPeers]; unsigned* p2p_done_[lsted::kMaxPeers];
+    std::vector<void*> p2p_opened_;
+    int p2p_rank_ = 0, p2p_world_ = 1; unsigned p2p_epoch_ = 0;
     bool prefetch_ = true;
     bool row_dual_ = false;   // measured: 0.326 ms vs 0.311 ms for the single-pair kernel (L1TEX-bound either way)
     ncclComm_t comm_ = 0;

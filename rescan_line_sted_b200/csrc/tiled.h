@@ -53,6 +53,8 @@ template <typename T, class BK> class TiledEngine : public EngineBase {
 
     void set_psfs(const double* psfs_host) { tile.set_psfs(psfs_host); have_norm = false; }
     void set_exact_clip(bool on) { tile.set_exact_clip(on); have_norm = false; }
+    void p2p_export(char*) { throw std::string("the peer-memory reduction applies to orientation sharding, not to tiles"); }
+    void p2p_attach(const char*) { throw std::string("the peer-memory reduction applies to orientation sharding, not to tiles"); }
     void forget_normalization() { have_norm = false; }
     // Sharding of a tiled object = horizontal bands ("object tiles with
     // halo"): rank r owns image rows [o0, o1) and keeps measurements / ratios on that

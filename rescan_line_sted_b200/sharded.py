@@ -9,6 +9,8 @@ plumbing:
 * `shard_items` / `gather_reports` -- independent units (frames, sweep
   points of `psf_report_batch`) dealt round-robin, results gathered once.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -68,6 +70,19 @@ class OrientationShardedDeconvolver:
                 unique_id[0] = _lib.nccl_unique_id(lib)
             dist.broadcast_object_list(unique_id, src=0, group=group)
         self.handle.shard(self.rank, self.world, self.k0, unique_id[0])
+        # Fast path (2160-point transforms): the per-iteration sum over ranks runs inside the
+        # column kernel over NVLink peer memory; the CUDA-IPC handles travel through the
+        # process group.  LSTED_P2P=0 keeps the NCCL all-reduce.
+        self.p2p = False
+        info = self.handle.info()
+        if (self.world > 1 and os.environ.get('LSTED_P2P', '1') != '0'
+                and info.Ly == 2160 and info.tiles_y * info.tiles_x == 1):
+            mine = self.handle.p2p_export()
+            parts = [None] * self.world
+            dist.all_gather_object(parts, mine, group=group)
+            self.handle.p2p_attach(b''.join(parts), self.world)
+            dist.barrier(group=group)
+            self.p2p = True
 
     def create_data(self, obj, total_brightness, seed):
         """Each rank simulates only its orientations; the Poisson streams are

@@ -44,6 +44,34 @@ def main():
         out[tag]['noise_independent_of_world'] = bool(same)
         single.close()
         d.close()
+    # 2160-point fast path: the sum over ranks runs inside the column kernel over NVLink peer
+    # memory (CUDA IPC); against one GPU and against the NCCL all-reduce variant
+    rng = np.random.default_rng(11)
+    psfs = rng.random((6, 9, 11))
+    obj = rng.random((1, 2100, 2100)) + 0.1
+    for precision, tag, tol in ((32, 'p2p_fp32', 1e-5), (64, 'p2p_fp64', 1e-12)):
+        single = _lib.DeconvHandle(_lib.get(), psfs, (2100, 2100), precision=precision, device=local)
+        single.create_data(obj, 1e10, 3)
+        single.iterate(3)
+        want = single.get(_lib.ESTIMATE)
+        res = {}
+        for mode in ('1', '0'):
+            os.environ['LSTED_P2P'] = mode
+            d = sharded.OrientationShardedDeconvolver(psfs, (2100, 2100), precision=precision,
+                                                      device=local)
+            assert d.p2p == (mode == '1')
+            d.create_data(obj, 1e10, 3)
+            d.iterate(3)
+            est = d.estimate
+            res[mode] = float(np.linalg.norm(est - want) / np.linalg.norm(want))
+            t = torch.from_numpy(est.copy()).cuda()
+            ref = t.clone()
+            dist.broadcast(ref, src=0)
+            res[mode + '_replica_diff'] = float((t - ref).abs().max() / ref.abs().max())
+            d.close()
+        os.environ.pop('LSTED_P2P', None)
+        out[tag] = dict(res, tol=tol)
+        single.close()
     # tiled object, row bands over the GPUs, 2160-point tiles (fast path), fp64
     rng = np.random.default_rng(4)
     psfs = rng.random((2, 9, 11))

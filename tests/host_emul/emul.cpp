@@ -93,6 +93,13 @@ class HostBackend {
         for (size_t i = 0; i < n; ++i) p[i] = (float)tmp[i];
     }
     void fill_double(double* p, size_t n, double v) { for (size_t i = 0; i < n; ++i) p[i] = v; }
+    // peer-memory reduction: GPU only (the CPU replay reduces through the callback)
+    void zero_bytes(void* p, size_t n) { memset(p, 0, n); }
+    void p2p_export(void*, void*, void*, char*) { throw std::string("peer memory needs GPUs"); }
+    void p2p_attach(int, int, const char*, size_t) { throw std::string("peer memory needs GPUs"); }
+    bool p2p_ready(const lsted::ConvGeom&, int) const { return false; }
+    template <typename T> void p2p_fill(lsted::ColArgs<T>&) {}
+    void p2p_wait(int) {}
     void set_profile(bool) {}
     void timer_start() {}
     float timer_stop() { return 0.f; }

@@ -38,3 +38,8 @@ def test_orientation_sharding_nccl(tmp_path):
     for tag in ('fp64', 'fp32'):
         assert r[tag]['replica_diff'] == 0.0
         assert r[tag]['noise_independent_of_world']
+    # fast path: fused peer-memory reduction ('1') and NCCL all-reduce ('0') against one GPU
+    for tag in ('p2p_fp32', 'p2p_fp64'):
+        for mode in ('1', '0'):
+            assert r[tag][mode] < 10 * r[tag]['tol'], (tag, mode, r[tag])
+            assert r[tag][mode + '_replica_diff'] == 0.0, (tag, mode, r[tag])
