@@ -200,7 +200,6 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     // orientation k+1 is requested as soon as every thread is done with slab k and
     // lands while the transform of k runs (no registers, no per-thread copy work).
     const bool stage = LSTED_COL_STAGE_OTF != 0;
-    const bool p2p = MODE == COL_HT && a.p2p_world > 1;   // fused cross-GPU reduction (below)
     cplx<T>* const otf_s = tw_s + P::COL_TW;
     mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
     const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(cplx<T>));
@@ -292,7 +291,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
             if (k < K) {
                 col_load_fwd_a<P>(r.v, t, c, src0 + (a.src_same ? 0 : (size_t)k * img_ny), Ny);
                 F::pass_a(r.v, t, s0);
-            } else if (!p2p) {
+            } else {
                 LSTED_UNROLL
                 for (int i = 0; i < P::NKEEP; ++i) r.v[i] = r.keep[i];
                 I::pass_a(r.v, t, s0);
@@ -307,34 +306,149 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
             F::pass_b(r.v, t, s1);
         });
     }
-    if (p2p) {
-        // Orientations sharded over GPUs: `keep` is this rank's partial Fourier-domain sum.
-        // The cross-GPU sum runs inside this kernel over NVLink peer memory, block by
-        // block, overlapped with the transforms of the other blocks (no all-reduce after the
-        // kernel).  Block xb is finished by rank xb % world:
-        //   other ranks push their partial into the owner's receive slab and raise a flag;
-        //   the owner waits for world-1 flags, adds, runs the ONE inverse transform and
-        //   writes the cropped column block into the spectrum of every rank, then counts the
-        //   block as done on every rank (row_final waits for nxb counts per reduction).
-        const int world = a.p2p_world, me = a.p2p_rank, owner = xb % world;
-        const size_t part = (size_t)P::NKEEP * P::COL_THREADS;             // elements per partial
-        if (owner != me) {
-            cplx<T>* out = a.p2p_recv[owner] + ((size_t)me * g.nxb + xb) * part;
+    cplx<T>* dst = a.dst + (size_t)xb * slab_ny;
+    cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+        LSTED_COL_IDS
+        I::load_b(r.v, t, s0, tw);
+        I::pass_b(r.v, t, s1);
+    });
+    cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
+        LSTED_COL_IDS
+        I::pass_c(r.v, t, s1, tw);
+        col_store_inv_c<P>(r.v, t, c, dst, sy, Ny);
+    });
+#undef LSTED_COL_IDS
+}
+
+// ---------------------------------------------------------------------------
+// COL_HT with the orientations sharded over GPUs: the sum of the ranks' partial spectra
+// runs INSIDE the kernel over NVLink peer memory (no all-reduce after it).
+//
+//   * block xb is finished by its owner rank xb % world: the other ranks push their
+//     partial Fourier-domain sum (the `keep` registers, 69 KB) into the owner's receive
+//     slab and raise a flag; the owner waits for world-1 flags, adds, runs the ONE inverse
+//     transform and writes the cropped column block into the spectrum of EVERY rank;
+//   * the kernel is persistent (one CTA per SM walks several blocks) and every rank walks
+//     the blocks it does NOT own first: a partial is pushed with plain posted stores and
+//     its flag is released only two orientations into the NEXT block, when those stores
+//     have long drained, so neither the NVLink burst nor the fence sits on the critical
+//     path; by the time a rank reaches the blocks it owns, the peers' partials are there;
+//   * `p2p_done` counts finished blocks on every rank; the next kernel on the stream is
+//     held back by a one-thread wait until nxb blocks of this reduction are counted.
+// ---------------------------------------------------------------------------
+LSTED_HD int p2p_block_at(int pos, int me, int world, int nxb) {
+    // positions 0 .. : the blocks with xb % world != me in ascending order, then the owned ones
+    const int owned = (nxb - me + world - 1) / world;          // #{xb < nxb : xb % world == me}
+    const int others = nxb - owned;
+    if (pos >= others) return me + (pos - others) * world;
+    // pos-th block that is not congruent to me: every run of `world` blocks holds world-1 of them
+    const int run = pos / (world - 1), off = pos - run * (world - 1);
+    return run * world + (off < me ? off : off + 1);
+}
+
+template <class P, class Ctx, class G = ColGeomRuntime>
+LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename P::T>& a,
+                              cplx<typename P::T>* smem, ColRegs<P>* regs, G = G()) {
+    typedef typename P::T T;
+    typedef typename P::Fwd F;
+    typedef typename P::Inv I;
+    const ConvGeom& g = a.g;
+    const int Ny = G::NY ? (int)G::NY : g.Ny, Ly = P::L;
+    const int sy = G::NY ? (int)G::SY : g.sy;
+    const size_t slab_ly = (size_t)P::C * Ly, img_ly = (size_t)g.nxb * slab_ly;
+    const size_t slab_ny = (size_t)P::C * even_rows(Ny), img_ny = (size_t)g.nxb * slab_ny;
+    cplx<T>* const tw_s = smem + (size_t)P::COL_SMEM_ELEMS;
+    const cplx<T>* tw = tw_s;
+    cplx<T>* const buf0 = smem;
+    cplx<T>* const buf1 = smem + (size_t)P::C * P::LSM_COL;
+    cplx<T>* const otf_s = tw_s + P::COL_TW;
+    mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
+    const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(cplx<T>));
+    const int K = a.K, world = a.p2p_world, me = a.p2p_rank;
+    const size_t part = (size_t)P::NKEEP * P::COL_THREADS;     // elements of one partial sum
+
+#define LSTED_COL_IDS                                          \
+    const int t = tid / P::C, c = tid - t * P::C;              \
+    cplx<T>* const s0 = buf0 + c * P::LSM_COL;                 \
+    cplx<T>* const s1 = buf1 + c * P::LSM_COL;
+
+    cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+        (void)r;
+        if (tid < P::COL_TW) tw_s[tid] = a.tw[tid];
+        if (tid == 0) mbar_init(mbar);
+    });
+    unsigned seq = 0;                  // OTF slabs consumed so far (mbarrier phase parity)
+    unsigned* pending = 0;             // flag of the last pushed partial, not yet released
+    unsigned finished = 0;             // owned blocks this CTA has written to every rank
+    for (int pos = cta; pos < g.nxb; pos += ncta) {
+        const int xb = p2p_block_at(pos, me, world, g.nxb);
+        const int owner = xb % world;
+        const cplx<T>* src0 = a.src + (size_t)xb * slab_ny;
+        const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
+        for (int k = 0; k <= K; ++k) {
             cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+                LSTED_COL_IDS
+                if (k + 1 < K)
+                    prefetch_l2_range(src0 + (size_t)(k + 1) * img_ny, slab_ny * sizeof(cplx<T>), tid,
+                                      P::COL_THREADS);
+                if (k + 1 < K) prefetch_l2_range(otf0 + (size_t)(k + 1) * img_ly, slab_bytes, tid, P::COL_THREADS);
+                if (k == 0) {
+                    if (tid == 0) bulk_load(otf_s, otf0, slab_bytes, mbar);
+                    LSTED_UNROLL
+                    for (int i = 0; i < P::NKEEP; ++i) r.keep[i] = mk<T>(0, 0);
+                }
+                if (k == 2 && pending) sys_fence();     // the previous block's pushes have drained
+                if (k > 0) {
+                    F::pass_c(r.v, t, s1, tw);
+                    mbar_wait(mbar, (seq + (unsigned)(k - 1)) & 1u);
+                    col_otf_product<P, true>(r, t, c, otf_s, k == 1);
+                }
+                if (k < K) {
+                    col_load_fwd_a<P>(r.v, t, c, src0 + (size_t)k * img_ny, Ny);
+                    F::pass_a(r.v, t, s0);
+                }
+            });
+            if (k == K) break;
+            cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+                LSTED_COL_IDS
+                if (tid == 0 && k > 0 && k < K)
+                    bulk_load(otf_s, otf0 + (size_t)k * img_ly, slab_bytes, mbar);
+                if (tid == 0 && k == 2 && pending) flag_release(pending, a.p2p_epoch);
+                F::load_b(r.v, t, s0, tw);
+                F::pass_b(r.v, t, s1);
+            });
+            if (k == 2) pending = 0;
+        }
+        seq += (unsigned)K;
+        if (owner != me) {
+            // push the partial sum: posted stores, released later (k == 2 of the next block / exit)
+            if (pending) {   // (K < 3: the previous flag is still held back)
+                cx.phase(regs, [&](int tid, ColRegs<P>& r) { (void)r; (void)tid; sys_fence(); });
+                cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+                    (void)r;
+                    if (tid == 0) flag_release(pending, a.p2p_epoch);
+                });
+            }
+            cplx<T>* out = a.p2p_recv[owner] + ((size_t)me * g.nxb + xb) * part;
+            cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
                 LSTED_UNROLL
                 for (int i = 0; i < P::NKEEP; ++i) out[(size_t)i * P::COL_THREADS + tid] = r.keep[i];
-                sys_fence();
             });
-            cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
+            pending = a.p2p_flags[owner] + (size_t)me * g.nxb + xb;
+            continue;
+        }
+        // owned block: wait for the peers' partials, add, ONE inverse transform, write everywhere
+        if (pending) {   // never wait while holding back a flag a peer may be waiting for
+            cx.phase(regs, [&](int tid, ColRegs<P>& r) { (void)r; (void)tid; sys_fence(); });
+            cx.phase(regs, [&](int tid, ColRegs<P>& r) {
                 (void)r;
-                if (tid == 0) flag_release(a.p2p_flags[owner] + (size_t)me * g.nxb + xb, a.p2p_epoch);
+                if (tid == 0) flag_release(pending, a.p2p_epoch);
             });
-            return;
+            pending = 0;
         }
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
             (void)r;
-            if (tid < world && tid != me)
-                flag_wait(a.p2p_flags[me] + (size_t)tid * g.nxb + xb, a.p2p_epoch);
+            if (tid < world && tid != me) flag_wait(a.p2p_flags[me] + (size_t)tid * g.nxb + xb, a.p2p_epoch);
         });
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
             LSTED_COL_IDS
@@ -349,31 +463,25 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
             for (int i = 0; i < P::NKEEP; ++i) r.v[i] = r.keep[i];
             I::pass_a(r.v, t, s0);
         });
-    }
-    cplx<T>* dst = a.dst + (size_t)xb * slab_ny;
-    cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-        LSTED_COL_IDS
-        I::load_b(r.v, t, s0, tw);
-        I::pass_b(r.v, t, s1);
-    });
-    if (!p2p) {
-        cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
+        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
+            LSTED_COL_IDS
+            I::load_b(r.v, t, s0, tw);
+            I::pass_b(r.v, t, s1);
+        });
+        cx.phase(regs, [&](int tid, ColRegs<P>& r) {
             LSTED_COL_IDS
             I::pass_c(r.v, t, s1, tw);
-            col_store_inv_c<P>(r.v, t, c, dst, sy, Ny);
+            for (int peer = 0; peer < world; ++peer)
+                col_store_inv_c<P>(r.v, t, c, a.p2p_spec[peer] + (size_t)xb * slab_ny, sy, Ny);
         });
-        return;
+        ++finished;
     }
-    cx.phase(regs, [&](int tid, ColRegs<P>& r) {
-        LSTED_COL_IDS
-        I::pass_c(r.v, t, s1, tw);
-        for (int peer = 0; peer < a.p2p_world; ++peer)
-            col_store_inv_c<P>(r.v, t, c, a.p2p_spec[peer] + (size_t)xb * slab_ny, sy, Ny);
-        sys_fence();
-    });
+    // everything this CTA sent has to be visible before its last flag and its counts
+    cx.phase(regs, [&](int tid, ColRegs<P>& r) { (void)r; (void)tid; sys_fence(); });
     cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
         (void)r;
-        if (tid < a.p2p_world) sys_counter_add(a.p2p_done[tid], 1u);
+        if (tid == 0 && pending) flag_release(pending, a.p2p_epoch);
+        if (tid < world && finished) sys_counter_add(a.p2p_done[tid], finished);
     });
 #undef LSTED_COL_IDS
 }

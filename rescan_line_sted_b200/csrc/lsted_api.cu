@@ -104,6 +104,17 @@ col_fast_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
                                   reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
 }
 
+// COL_HT with the cross-GPU sum fused in (persistent: one CTA per SM walks several blocks)
+template <class P, class G = lsted::ColGeomRuntime>
+__global__ void __launch_bounds__(P::COL_THREADS, 1)
+col_ht_p2p_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DeviceCtx cx;
+    lsted::ColRegs<P> r;
+    lsted::col_ht_p2p_body<P, DeviceCtx, G>(cx, blockIdx.x, gridDim.x, a,
+                                  reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
+}
+
 enum { kRowThreads = 256, kColThreads32 = 512, kColThreads64 = 256, kEwThreads = 256 };
 
 template <int MODE, typename T>
@@ -445,6 +456,19 @@ class CudaBackend {
                 CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P, ColGeom2048>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
+        }
+        if (MODE == lsted::COL_HT && a.p2p_world > 1) {
+            static bool p2p_configured = false;
+            if (!p2p_configured) {
+                CUDA_CHECK(cudaFuncSetAttribute(col_ht_p2p_kernel<P>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                p2p_configured = true;
+            }
+            const int ncta = grid < num_sms_ ? grid : num_sms_;
+            before(kind);
+            col_ht_p2p_kernel<P><<<ncta, P::COL_THREADS, smem, stream_>>>(a);
+            after();
+            return;
         }
         before(kind);
         if (fixed) col_fast_kernel<MODE, P, ColGeom2048><<<grid, P::COL_THREADS, smem, stream_>>>(a);
