@@ -365,7 +365,10 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
     mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
     const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(cplx<T>));
     const int K = a.K, world = a.p2p_world, me = a.p2p_rank;
-    const size_t part = (size_t)P::NKEEP * P::COL_THREADS;     // elements of one partial sum
+    // one partial sum in the receive slab: pairs of register values, so that a thread moves
+    // 16 bytes per store / load (512 contiguous bytes per warp on the NVLink side)
+    enum { NPAIR = (P::NKEEP + 1) / 2 };
+    const size_t part = (size_t)2 * NPAIR * P::COL_THREADS;
 
 #define LSTED_COL_IDS                                          \
     const int t = tid / P::C, c = tid - t * P::C;              \
@@ -432,7 +435,9 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
             cplx<T>* out = a.p2p_recv[owner] + ((size_t)me * g.nxb + xb) * part;
             cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
                 LSTED_UNROLL
-                for (int i = 0; i < P::NKEEP; ++i) out[(size_t)i * P::COL_THREADS + tid] = r.keep[i];
+                for (int i = 0; i < NPAIR; ++i)
+                    store_pair(out + ((size_t)i * P::COL_THREADS + tid) * 2, r.keep[2 * i],
+                               2 * i + 1 < P::NKEEP ? r.keep[2 * i + 1 < P::NKEEP ? 2 * i + 1 : 0] : mk<T>(0, 0));
             });
             pending = a.p2p_flags[owner] + (size_t)me * g.nxb + xb;
             continue;
@@ -456,8 +461,12 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
                 if (src == me) continue;
                 const cplx<T>* in = a.p2p_recv[me] + ((size_t)src * g.nxb + xb) * part;
                 LSTED_UNROLL
-                for (int i = 0; i < P::NKEEP; ++i)
-                    r.keep[i] = r.keep[i] + load_l2(in + (size_t)i * P::COL_THREADS + tid);
+                for (int i = 0; i < NPAIR; ++i) {
+                    cplx<T> u, w;
+                    load_pair_l2(in + ((size_t)i * P::COL_THREADS + tid) * 2, u, w);
+                    r.keep[2 * i] = r.keep[2 * i] + u;
+                    if (2 * i + 1 < P::NKEEP) r.keep[2 * i + 1 < P::NKEEP ? 2 * i + 1 : 0] = r.keep[2 * i + 1 < P::NKEEP ? 2 * i + 1 : 0] + w;
+                }
             }
             LSTED_UNROLL
             for (int i = 0; i < P::NKEEP; ++i) r.v[i] = r.keep[i];

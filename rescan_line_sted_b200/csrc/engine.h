@@ -190,7 +190,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     void p2p_export(char* out) {
         if (world < 2) throw std::string("p2p_export: shard the handle first");
         if (!p2p_recv) {
-            const size_t part = (size_t)g.C * g.Ly;
+            const size_t part = (size_t)g.C * g.Ly + (size_t)g.C * g.Ly / 8 + 64;   // register pairs, padded
             p2p_recv = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * part * g.nxb * world);
             p2p_words = (size_t)world * g.nxb;
             p2p_flags = (unsigned*)bk.alloc(sizeof(unsigned) * (p2p_words + 32));

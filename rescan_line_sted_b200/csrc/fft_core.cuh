@@ -204,6 +204,16 @@ template <typename T> LSTED_HD cplx<T> load_l2(const cplx<T>* p) {
     return *p;
 #endif
 }
+// load_pair that bypasses L1 (data written by a peer GPU during this kernel)
+template <typename T> LSTED_HD void load_pair_l2(const cplx<T>* p, cplx<T>& a, cplx<T>& b) {
+    a = load_l2(p); b = load_l2(p + 1);
+}
+#ifdef __CUDA_ARCH__
+LSTED_HD void load_pair_l2(const cplx<float>* p, cplx<float>& a, cplx<float>& b) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+    a = mk<float>(v.x, v.y); b = mk<float>(v.z, v.w);
+}
+#endif
 // CTA-wide counter in shared memory (host replay: threads run one after another)
 LSTED_HD int smem_counter_next(int* counter) {
 #ifdef __CUDA_ARCH__
