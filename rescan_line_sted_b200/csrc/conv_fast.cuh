@@ -986,3 +986,293 @@ LSTED_HD void row_mid_dual_body(Ctx& cx, int block, const RowArgs<typename P::T>
 }
 
 }  // namespace lsted
+
+namespace lsted {
+
+// ---------------------------------------------------------------------------
+// Row kernels on the two-pass plan (Fft2E): L = RA*RC = 48*45 for 2160.
+// 48 threads per row pair hold a whole butterfly leg (45 / 48 complex values) in registers;
+// a transform costs ONE shared-memory exchange and ONE twiddle stage, the pair needs one
+// exchange buffer + one staging buffer (33.8 KB: six pairs per SM), and a CTA of PR = 2
+// pairs is three full warps.  Same operators, HBM layouts and pointwise arithmetic as
+// row_fast_body; per thread the bins are t + q*48 (q < 45) and the pixels t + q*45 (q < 48).
+// ---------------------------------------------------------------------------
+template <typename T_, int RA_, int RC_, int C_, int PR_> struct FastPlan2 {
+    typedef T_ T;
+    enum { NT = imax(RA_, RC_) };
+    typedef Fft2E<cplx<T>, -1, RA_, RC_, NT> Fwd;
+    typedef Fft2E<cplx<T>, +1, RC_, RA_, NT> Inv;
+    enum {
+        L = RA_ * RC_, C = C_, PR = PR_,
+        SEQ = imax(Fwd::SEQ, Inv::SEQ),
+        LSM_ROW = (SEQ + 15) / 16 * 16 + 8,
+        ROW_THREADS = NT * PR_,
+        VREG = imax(Fwd::VREG, Inv::VREG),
+        NC = Fwd::NC, RCF = Fwd::RC, QH = (Fwd::RC - 1) / 2, PX = Fwd::NC + 1
+    };
+    static_assert((int)Fwd::NC == (int)NT && (int)Inv::NA == (int)NT, "bins: one leg per thread, stride NT");
+    static_assert((int)Fwd::NA == (int)Inv::NC, "pixels: forward pass A takes what inverse pass C leaves");
+    static_assert(Fwd::RC % 2 == 1, "row split assumes an odd last radix");
+    static_assert((Fwd::RC - QH) * PX <= LSM_ROW, "mirror exchange must fit one buffer");
+    static_assert(NT % C_ == 0, "column blocks must not straddle thread legs");
+};
+template <class P> struct Row2Regs {
+    cplx<typename P::T> v[P::VREG];
+    typename P::Fwd::Tw twf;
+    typename P::Inv::Tw twi;
+    cplx<typename P::T> ramp0;
+};
+// exchange buffer + staging buffer (+ estimate rows for ROW_FINAL) per pair
+template <class P> LSTED_HD size_t fast_row2_smem_bytes(int mode) {
+    return sizeof(cplx<typename P::T>) * (size_t)(mode == ROW_FINAL ? 3 : 2) * P::PR * P::LSM_ROW;
+}
+
+template <int MODE, class P, class Ctx, class G = RowGeomRuntime>
+LSTED_HD void row2_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
+                             cplx<typename P::T>* smem, Row2Regs<P>* regs, G = G()) {
+    typedef typename P::T T;
+    typedef typename P::Fwd F;
+    typedef typename P::Inv I;
+    typedef Row2Regs<P> R;
+    const ConvGeom& g = a.g;
+    const int Ny = g.Ny, Nx = G::NX ? (int)G::NX : g.Nx;
+    const int Lx = P::L, C = P::C;
+    const int Py = (Ny + 1) / 2;
+    const int bpi = (Py + P::PR - 1) / P::PR;
+    const int img = block / bpi;
+    const int pair0 = (block - img * bpi) * P::PR;
+    const size_t real_off = (size_t)img * Ny * Nx;
+    const int Nye = even_rows(Ny);
+    const size_t spec_off = (size_t)img * g.nxb * C * Nye;
+    const cplx<T>* tw = a.tw;
+    const int shift = (MODE == ROW_FWD) ? 0 : (G::NX ? (int)G::SX : g.sx);
+    const size_t xb_stride = (size_t)Nye * C;
+    const int NBUF = MODE == ROW_FINAL ? 3 : 2;
+
+#define LSTED_ROW2_IDS                                     \
+    const int f = tid / P::NT, t = tid - f * P::NT;        \
+    const int pair = pair0 + f;                            \
+    const bool live = pair < Py;                           \
+    const int y = 2 * pair;                                \
+    const bool two = y + 1 < Ny;                           \
+    cplx<T>* const s0 = smem + (size_t)(NBUF * f) * P::LSM_ROW;      \
+    cplx<T>* const sx = smem + (size_t)(NBUF * f + 1) * P::LSM_ROW;  /* staging / mirror */ \
+    T* const stage = (T*)sx;                               \
+    T* const stage2 = (T*)(smem + (size_t)(NBUF * f + 2) * P::LSM_ROW); /* ROW_FINAL only */ \
+    (void)s0; (void)sx; (void)stage; (void)stage2; (void)y; (void)live; (void)two;
+
+    if (MODE == ROW_MID || MODE == ROW_FINAL) {
+        const int ahead = block + a.prefetch_ahead;
+        const int img2 = ahead / bpi;
+        const int pair2 = (ahead - img2 * bpi) * P::PR;
+        if (a.prefetch_ahead > 0 && img2 < a.nimg && pair2 < Py) {
+            const int y2 = 2 * pair2;
+            const int rows2 = (Ny - y2) < 2 * P::PR ? (Ny - y2) : 2 * P::PR;
+            const cplx<T>* sp = a.spec_in + (size_t)img2 * g.nxb * C * Nye + (size_t)y2 * C;
+            const T* ax = (MODE == ROW_MID ? a.aux + (size_t)img2 * Ny * Nx : a.aux) + (size_t)y2 * Nx;
+            cx.phase_nosync(regs, [&](int tid, R& r) {
+                (void)r;
+                for (int xb = tid; xb < g.nxb; xb += P::ROW_THREADS)
+                    prefetch_chunk(sp + (size_t)xb * xb_stride, (unsigned)(2 * P::PR * C * sizeof(cplx<T>)));
+                prefetch_l2_range(ax, (size_t)rows2 * Nx * sizeof(T), tid, P::ROW_THREADS);
+                if (MODE == ROW_FINAL)
+                    prefetch_l2_range(a.real_out + (size_t)y2 * Nx, (size_t)rows2 * Nx * sizeof(T), tid,
+                                      P::ROW_THREADS);
+            });
+        }
+    }
+    if (MODE == ROW_FWD) {
+        const T* src = a.real_in + real_off;
+        cx.phase(regs, [&](int tid, R& r) {
+            LSTED_ROW2_IDS
+            if (!live) return;
+            F::load_tw(r.twf, t, tw);
+            if (t < F::NA) {
+                LSTED_UNROLL
+                for (int q = 0; q < F::RA; ++q) {
+                    const int i = t + q * F::NA;
+                    T va = 0, vb = 0;
+                    if (i < Nx) {
+                        va = src[(size_t)y * Nx + i];
+                        if (two) vb = src[(size_t)(y + 1) * Nx + i];
+                    }
+                    r.v[q] = mk<T>(va, vb);
+                }
+            }
+            F::pass_a(r.v, t, s0);
+        });
+    } else {
+        const cplx<T>* src = a.spec_in + spec_off;
+        cx.phase(regs, [&](int tid, R& r) {
+            LSTED_ROW2_IDS
+            if ((MODE == ROW_MID || MODE == ROW_FINAL) && live) {
+                const T* m0 = (MODE == ROW_MID ? a.aux + real_off : a.aux) + (size_t)y * Nx;
+                async_copy_row(stage, m0, Nx, t, P::NT);
+                if (two) async_copy_row(stage + P::L, m0 + Nx, Nx, t, P::NT);
+                if (MODE == ROW_FINAL) {
+                    const T* e0 = a.real_out + (size_t)y * Nx;
+                    async_copy_row(stage2, e0, Nx, t, P::NT);
+                    if (two) async_copy_row(stage2 + P::L, e0 + Nx, Nx, t, P::NT);
+                }
+            }
+            if (MODE == ROW_INV_SIM && t == 0) *(int*)stage = 0;   // noise queue (below)
+            if (!live) return;
+            I::load_tw(r.twi, t, tw);
+            if (MODE == ROW_MID || MODE == ROW_FINAL) {
+                F::load_tw(r.twf, t, tw);
+                r.ramp0 = tw[(t * shift) % Lx];
+            }
+            // Hermitian unpack into the inverse pass-A leg (bins t + q*NC)
+            const cplx<T>* lo = src + ((size_t)(t / C) * Nye + y) * C + 2 * (t % C);
+            const int tm = Lx - t;
+            LSTED_UNROLL
+            for (int q = 0; q < I::RA; ++q) {
+                const int i = t + q * P::NC;
+                bool upper = q > P::QH;
+                if (q == P::QH) upper = 2 * i > Lx;
+                const cplx<T>* p;
+                if (q < P::QH || (q == P::QH && !upper)) {
+                    p = lo + (size_t)(q * (P::NC / C)) * xb_stride;
+                } else {
+                    const int k = tm - q * P::NC;
+                    p = src + ((size_t)(k / C) * Nye + y) * C + 2 * (k % C);
+                }
+                cplx<T> A, B;
+                load_pair(p, A, B);
+                if (!two) B = mk<T>(0, 0);
+                if ((q == 0 && t == 0) || 2 * i == Lx) { A.y = 0; B.y = 0; }
+                r.v[q] = upper ? mk<T>(A.x + B.y, B.x - A.y) : mk<T>(A.x - B.y, A.y + B.x);
+            }
+            I::pass_a(r.v, t, s0);
+            if (MODE == ROW_MID || MODE == ROW_FINAL) async_copy_wait_all();   // visible after the barrier
+        });
+        // inverse pass C and the pointwise step on registers (logical position idx = t + q*NC'
+        // holds pixel idx - shift of rows y (re) and y+1 (im))
+        T* out = (MODE == ROW_FINAL) ? a.real_out : a.real_out + real_off;
+        T* out2 = (MODE == ROW_INV_SIM) ? a.real_out2 + real_off : 0;
+        cx.phase(regs, [&](int tid, R& r) {
+            LSTED_ROW2_IDS
+            if (!live) return;
+            I::pass_c(r.v, t, s0, r.twi);
+            if (t < I::NC) {
+                LSTED_UNROLL
+                for (int q = 0; q < I::RC; ++q) {
+                    const int i = t + q * I::NC - shift;
+                    cplx<T> z = r.v[q];
+                    cplx<T> w = mk<T>(0, 0);
+                    if (i >= 0 && i < Nx) {
+                        const size_t o = (size_t)y * Nx + i;
+                        if (MODE == ROW_INV_STORE) {
+                            if (a.clip) { z.x = clip0(z.x); z.y = clip0(z.y); }
+                            out[o] = a.accumulate ? out[o] + z.x : z.x;
+                            if (two) out[o + Nx] = a.accumulate ? out[o + Nx] + z.y : z.y;
+                        } else if (MODE == ROW_INV_SIM) {
+                            out[o] = clip0(z.x);
+                            if (two) out[o + Nx] = clip0(z.y);
+                        } else if (MODE == ROW_MID) {
+                            w.x = fast_div(stage[i], clip0(z.x));
+                            if (two) w.y = fast_div(stage[P::L + i], clip0(z.y));
+                        } else {  // ROW_FINAL
+                            w.x = stage2[i] * fast_div(clip0(z.x), stage[i]);
+                            out[o] = w.x;
+                            if (two) {
+                                w.y = stage2[P::L + i] * fast_div(clip0(z.y), stage[P::L + i]);
+                                out[o + Nx] = w.y;
+                            }
+                        }
+                    }
+                    r.v[q] = w;
+                }
+            }
+        });
+        if (MODE == ROW_INV_SIM) {
+            cx.phase(regs, [&](int tid, R& r) {
+                LSTED_ROW2_IDS
+                (void)r;
+                if (!live || t >= I::NC) return;
+                int* const queue = (int*)stage;
+                const int nr = two ? 2 : 1;
+                LSTED_NOUNROLL
+                for (int e = 0; e < I::RC * 2; ++e) {
+                    const int rr = e & 1, q = e >> 1;
+                    const int i = t + q * I::NC - shift;
+                    if (rr < nr && i >= 0 && i < Nx) {
+                        const size_t o = (size_t)(y + rr) * Nx + i;
+                        const double lam = (double)out[o];
+                        double k;
+                        if (!(lam >= 10.0)) {
+                            out2[o] = (T)(poisson_sample(lam, a.seed, o, a.img0 + img) + 1e-9);
+                        } else if (poisson_fast_ptrs(lam, a.seed, o, a.img0 + img, k)) {
+                            out2[o] = (T)(k + 1e-9);
+                        } else {
+                            queue[1 + smem_counter_next(queue)] = rr * Nx + i;
+                        }
+                    }
+                }
+            });
+            cx.phase_nosync(regs, [&](int tid, R& r) {
+                LSTED_ROW2_IDS
+                (void)r;
+                if (!live) return;
+                const int* const queue = (const int*)stage;
+                const int n = queue[0];
+                LSTED_NOUNROLL
+                for (int e = t; e < n; e += P::NT) {
+                    const size_t o = (size_t)y * Nx + queue[1 + e];
+                    out2[o] = (T)(poisson_sample((double)out[o], a.seed, o, a.img0 + img) + 1e-9);
+                }
+            });
+        }
+        if (MODE == ROW_INV_STORE || MODE == ROW_INV_SIM) return;
+        // every thread is done reading the exchange buffer: forward pass A may overwrite it
+        cx.phase(regs, [&](int tid, R& r) {
+            LSTED_ROW2_IDS
+            if (!live) return;
+            F::pass_a(r.v, t, s0);
+        });
+    }
+    // Forward pass C; the upper half of the spectrum goes to the mirror thread through the
+    // staging buffer (its rows were consumed by the pointwise step)
+    cx.phase(regs, [&](int tid, R& r) {
+        LSTED_ROW2_IDS
+        if (!live) return;
+        F::pass_c(r.v, t, s0, r.twf);
+        LSTED_UNROLL
+        for (int q = P::QH; q < P::RCF; ++q) sx[(q - P::QH) * P::PX + t] = r.v[q];
+    });
+    cplx<T>* dst = a.spec_out + spec_off;
+    cx.phase_nosync(regs, [&](int tid, R& r) {
+        LSTED_ROW2_IDS
+        if (!live) return;
+        const int tp = t == 0 ? 0 : P::NC - t;
+        const int qoff = t == 0 ? 1 : 0;
+        cplx<T>* pk = dst + ((size_t)(t / C) * Nye + y) * C + 2 * (t % C);
+        cplx<T> dq[P::QH + 2];
+        if (shift) F::template twiddle_powers<P::QH>(tw[(P::NC * shift) % Lx], dq);
+        LSTED_UNROLL
+        for (int q = 0; q <= P::QH; ++q) {
+            const int k = t + q * P::NC;
+            if (q == P::QH && 2 * k > Lx) {
+                if (k < g.nxb * C)
+                    store_pair(pk + (size_t)(q * (P::NC / C)) * xb_stride, mk<T>(0, 0), mk<T>(0, 0));
+                continue;
+            }
+            const cplx<T> z1 = r.v[q];
+            cplx<T> z2;
+            const int qm = P::RCF - 1 - q + qoff;
+            if (t == 0 && q == 0) z2 = z1;
+            else z2 = sx[(qm - P::QH) * P::PX + tp];
+            cplx<T> oa = mk<T>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y - z2.y));
+            cplx<T> ob = mk<T>((T)0.5 * (z1.y + z2.y), (T)0.5 * (z2.x - z1.x));
+            if (shift) {
+                const cplx<T> ph = conj(q == 0 ? r.ramp0 : r.ramp0 * dq[q]);
+                oa = oa * ph;
+                ob = ob * ph;
+            }
+            store_pair(pk + (size_t)(q * (P::NC / C)) * xb_stride, oa, two ? ob : mk<T>(0, 0));
+        }
+    });
+#undef LSTED_ROW2_IDS
+}
+
+}  // namespace lsted

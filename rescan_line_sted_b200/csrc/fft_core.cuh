@@ -475,6 +475,37 @@ template <int DIR, class V> struct DftE<15, DIR, V> {
     }
 };
 
+// R = R1*R2 with coprime factors by the Good-Thomas map (no internal twiddles):
+// n = (R2*n1 + R1*n2) mod R,  k = (R2*(R2^-1 mod R1)*k1 + R1*(R1^-1 mod R2)*k2) mod R.
+constexpr int mod_inverse(int a, int m) {
+    int r = 1;
+    while ((a * r) % m != 1) ++r;
+    return r;
+}
+template <int R, int R1, int R2, int DIR, class V> struct DftPFA {
+    static LSTED_HD void run(V* v) {
+        constexpr int E1 = R2 * mod_inverse(R2 % R1, R1), E2 = R1 * mod_inverse(R1 % R2, R2);
+        V y[R2][R1];
+        LSTED_UNROLL
+        for (int n2 = 0; n2 < R2; ++n2) {
+            LSTED_UNROLL
+            for (int n1 = 0; n1 < R1; ++n1) y[n2][n1] = v[(R2 * n1 + R1 * n2) % R];
+            DftE<R1, DIR, V>::run(y[n2]);
+        }
+        LSTED_UNROLL
+        for (int k1 = 0; k1 < R1; ++k1) {
+            V z[R2];
+            LSTED_UNROLL
+            for (int n2 = 0; n2 < R2; ++n2) z[n2] = y[n2][k1];
+            DftE<R2, DIR, V>::run(z);
+            LSTED_UNROLL
+            for (int k2 = 0; k2 < R2; ++k2) v[(E1 * k1 + E2 * k2) % R] = z[k2];
+        }
+    }
+};
+template <int DIR, class V> struct DftE<45, DIR, V> : DftPFA<45, 9, 5, DIR, V> {};
+template <int DIR, class V> struct DftE<48, DIR, V> : DftPFA<48, 3, 16, DIR, V> {};
+
 // historical spelling: DFT on cplx<T>
 template <int R, int DIR, typename T> struct Dft : DftE<R, DIR, cplx<T> > {};
 

@@ -148,6 +148,56 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
         pass_c(v, t, sm, bw);
     }
 };
+// Two-pass variant: L = RA*RC, ONE shared-memory exchange and ONE twiddle stage per
+// transform.  max(RA, RC) threads cooperate on a sequence; thread t owns butterfly t of
+// each pass and RA (RC) operands in registers:
+//   pass A: in  logical  t + q*NA  (NA = RC butterflies of radix RA), out position q*PA + t
+//   pass C: in  position t*PA + q  (NC = RA butterflies of radix RC), twiddle w^(q*t),
+//           out logical  t + q*NC  (natural order, stays in registers)
+// As for Fft3E the inverse uses the reversed radix order, so forward pass-C results are the
+// inverse pass-A operands.  PA odd: the strided pass-C loads are conflict-free.
+template <class V, int DIR, int RA_, int RC_, int NT_> struct Fft2E {
+    typedef typename ScalarOf<V>::type T;
+    typedef cplx<T> W;
+    enum {
+        RA = RA_, RC = RC_, NT = NT_,
+        L = RA * RC,
+        NA = RC, NC = RA,
+        PA = (NA % 2) ? NA : NA + 1,
+        SEQ = imax(RA * PA, L),
+        VREG = imax(RA, RC)
+    };
+    static_assert(NA <= NT_ && NC <= NT_, "one butterfly per thread and pass");
+    struct Tw { W c[1]; };
+    static LSTED_HD void load_tw(Tw& w, int t, const W* tw) { w.c[0] = tw[(t < NC) ? t : 0]; }
+    template <int N> static LSTED_HD void twiddle_powers(W w1, W* w) {
+        w[1] = w1;
+        LSTED_UNROLL
+        for (int q = 2; q <= N; ++q) w[q] = w[q / 2] * w[q - q / 2];
+    }
+    static LSTED_HD void pass_a(V* v, int t, V* sm) {
+        if (t < NA) {
+            DftE<RA, DIR, V>::run(v);
+            LSTED_UNROLL
+            for (int q = 0; q < RA; ++q) sm[q * PA + t] = v[q];
+        }
+    }
+    static LSTED_HD void pass_c(V* v, int t, const V* sm, const Tw& bw) {
+        if (t < NC) {
+            // operand q of butterfly t is output t of pass-A butterfly q
+            W w[RC];
+            twiddle_powers<RC - 1>(bw.c[0], w);
+            LSTED_UNROLL
+            for (int q = 0; q < RC; ++q) {
+                V x = sm[t * PA + q];
+                if (q > 0) x = mul_tw<DIR>(x, w[q]);
+                v[q] = x;
+            }
+            DftE<RC, DIR, V>::run(v);
+        }
+    }
+};
+
 template <typename T, int DIR, int RA, int RB, int RC, int NT> struct Fft3 : Fft3E<cplx<T>, DIR, RA, RB, RC, NT> {};
 
 }  // namespace lsted

@@ -83,6 +83,21 @@ row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
                                   reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
 }
 
+// Row kernels on the two-pass plan 2160 = 48 x 45 (conv_fast.cuh: row2_fast_body), fp32
+#ifndef LSTED_ROW2_CTAS
+#define LSTED_ROW2_CTAS 3
+#endif
+typedef lsted::FastPlan2<float, 48, 45, LSTED_FAST_C32, 2> Plan2160f2;
+template <int MODE, class P, class G = lsted::RowGeomRuntime>
+__global__ void __launch_bounds__(P::ROW_THREADS, LSTED_ROW2_CTAS)
+row2_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DeviceCtx cx;
+    lsted::Row2Regs<P> r;
+    lsted::row2_fast_body<MODE, P, DeviceCtx, G>(cx, blockIdx.x, a,
+                                  reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
+}
+
 // ROW_MID with two row pairs per thread group (conv_fast.cuh: row_mid_dual_body)
 template <class P>
 __global__ void __launch_bounds__(lsted::RowDual<P>::THREADS, 2)
@@ -258,6 +273,8 @@ class CudaBackend {
         memset(prof_n_, 0, sizeof(prof_n_));
         const char* dual = getenv("LSTED_ROW_DUAL");   // A/B switch, same as option "row_dual"
         if (dual) row_dual_ = atoi(dual) != 0;
+        const char* plan2 = getenv("LSTED_ROW_PLAN2");  // A/B switch, same as option "row_plan2"
+        if (plan2) row_plan2_ = atoi(plan2) != 0;
     }
     ~CudaBackend() {
         cudaSetDevice(device_);
@@ -392,6 +409,7 @@ class CudaBackend {
     void set_profile(bool on) { profile_ = on; }
     void set_fast_path(bool on) { use_fast_ = on; }
     void set_row_dual(bool on) { row_dual_ = on; }
+    void set_row_plan2(bool on) { row_plan2_ = on; }
     // row CTAs resident at once (4 per SM): prefetch for the CTA one wave ahead
     int row_prefetch_distance() const { return prefetch_ ? num_sms_ * 4 : 0; }
     void set_prefetch(bool on) { prefetch_ = on; }
@@ -475,8 +493,25 @@ class CudaBackend {
         else col_fast_kernel<MODE, P><<<grid, P::COL_THREADS, smem, stream_>>>(a);
         after();
     }
+    template <int MODE> void launch_row2(const lsted::RowArgs<float>& a, int kind) {
+        typedef Plan2160f2 P;
+        const size_t smem = lsted::fast_row2_smem_bytes<P>(MODE);
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(row2_fast_kernel<MODE, P>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        lsted::RowArgs<float> b = a;
+        if (b.prefetch_ahead > 0) b.prefetch_ahead = num_sms_ * LSTED_ROW2_CTAS;
+        const int fast_grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
+        before(kind);
+        row2_fast_kernel<MODE, P><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(b);
+        after();
+    }
     template <int MODE> bool try_fast_row(int grid, const lsted::RowArgs<float>& a, int kind) {
         if (!plan_fits_rows<Plan2160f>(a.g)) return false;
+        if (row_plan2_) { launch_row2<MODE>(a, kind); return true; }
         if (MODE == lsted::ROW_MID && row_dual_ && a.g.Ny % 4 == 0) {
             typedef lsted::RowDual<Plan2160f> D;
             const size_t smem = D::smem_bytes();
@@ -623,6 +658,10 @@ class CudaBackend {
     std::vector<void*> p2p_opened_;
     int p2p_rank_ = 0, p2p_world_ = 1; unsigned p2p_epoch_ = 0;
     bool prefetch_ = true;
+    // two-pass 48 x 45 row kernels (fp32): 35 % fewer warp instructions and half the shared-memory
+    // wavefronts, but 0.334 ms vs 0.283 ms for ROW_MID: 4792 straight-line instructions run by
+    // 9 warps per SM stall on instruction fetch (ncu: no_inst 32 %).  Kept behind this switch.
+    bool row_plan2_ = false;
     bool row_dual_ = false;   // measured: 0.326 ms vs 0.311 ms for the single-pair kernel (L1TEX-bound either way)
     ncclComm_t comm_ = 0;
     cudaEvent_t t0_, t1_;

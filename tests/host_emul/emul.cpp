@@ -52,6 +52,8 @@ extern "C" void emul_set_allreduce(allreduce_cb cb) { g_allreduce = cb; }
 extern "C" void emul_set_broadcast(broadcast_cb cb) { g_broadcast = cb; }
 
 static int g_dual_launches = 0;
+static int g_row2_launches = 0;
+extern "C" int emul_row2_launches(void) { return g_row2_launches; }
 extern "C" int emul_dual_launches(void) { return g_dual_launches; }
 
 class HostBackend {
@@ -59,6 +61,7 @@ class HostBackend {
     explicit HostBackend(int) : bytes_(0), use_fast_(true) {}
     void set_fast_path(bool on) { use_fast_ = on; }
     void set_row_dual(bool on) { row_dual_ = on; }
+    void set_row_plan2(bool on) { row_plan2_ = on; }
     int row_prefetch_distance() const { return 3; }
     void set_prefetch(bool) {}
     static int fast_cols(int L, int cplx_bytes) {
@@ -110,6 +113,7 @@ class HostBackend {
 
     template <int MODE, typename T> void launch_row(int grid, const lsted::RowArgs<T>& a) {
         typedef typename PlanFor<T>::type P;
+        if (use_fast_ && row_plan2_ && a.g.Lx == P::L && a.g.C == P::C && launch_row2<MODE>(a)) return;
         if (use_fast_ && row_dual_ && MODE == lsted::ROW_MID && a.g.Lx == P::L && a.g.C == P::C &&
             a.g.Ny % 4 == 0 && launch_row_mid_dual(a))
             return;
@@ -141,6 +145,29 @@ class HostBackend {
 #pragma omp for schedule(dynamic)
             for (int b = 0; b < grid; ++b) lsted::row_body<MODE, T>(cx, b, a, smem.data());
         }
+    }
+    template <int MODE> bool launch_row2(const lsted::RowArgs<double>&) { return false; }
+    template <int MODE> bool launch_row2(const lsted::RowArgs<float>& a) {
+        typedef lsted::FastPlan2<float, 48, 45, 4, 2> P;
+        const int grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
+        ++g_row2_launches;
+#pragma omp parallel
+        {
+            std::vector<lsted::cplx<float> > smem(lsted::fast_row2_smem_bytes<P>(MODE) / sizeof(lsted::cplx<float>));
+            std::vector<lsted::Row2Regs<P> > regs(P::ROW_THREADS);
+            HostCtx cx;
+            cx.nthreads = P::ROW_THREADS;
+            const bool fixed = MODE != lsted::ROW_FWD && a.g.Nx == 2048 && a.g.sx == 53;
+#pragma omp for schedule(dynamic)
+            for (int b = 0; b < grid; ++b) {
+                if (fixed)
+                    lsted::row2_fast_body<MODE, P, HostCtx, lsted::RowGeomFixed<2048, 53> >(
+                        cx, b, a, smem.data(), regs.data());
+                else
+                    lsted::row2_fast_body<MODE, P>(cx, b, a, smem.data(), regs.data());
+            }
+        }
+        return true;
     }
     bool launch_row_mid_dual(const lsted::RowArgs<double>&) { return false; }
     bool launch_row_mid_dual(const lsted::RowArgs<float>& a) {
@@ -226,6 +253,7 @@ class HostBackend {
     size_t bytes_;
     bool use_fast_;
     bool row_dual_ = false;
+    bool row_plan2_ = false;
 };
 
 #define LSTED_BACKEND HostBackend
@@ -330,5 +358,36 @@ extern "C" int lsted_psf_rotate(int, int batch, int n0, int n1, const double* pl
     a.coef = coef.data(); a.out = out;
     HostCtx cx;
     for (int b = 0; b < batch; ++b) lsted::psf_rotate_body(cx, b, a);
+    return 0;
+}
+
+// Two-pass plan (fft_static.cuh: Fft2E) of the row kernels, 2160 = 48 x 45: one sequence,
+// threads replayed one after another.  in/out: [2160] interleaved (re, im) float64.
+template <typename T, int DIR, int RA, int RC>
+static void run_fft2(const double* in, double* out) {
+    typedef lsted::Fft2E<lsted::cplx<T>, DIR, RA, RC, 48> F;
+    std::vector<lsted::cplx<T> > tw(F::L), sm(F::SEQ + 8);
+    lsted::fill_twiddles<T>(F::L, tw.data());
+    std::vector<std::vector<lsted::cplx<T> > > regs(48, std::vector<lsted::cplx<T> >(F::VREG));
+    for (int t = 0; t < 48; ++t) {
+        if (t < F::NA)
+            for (int q = 0; q < F::RA; ++q)
+                regs[t][q] = lsted::mk<T>((T)in[2 * (t + q * F::NA)], (T)in[2 * (t + q * F::NA) + 1]);
+        F::pass_a(regs[t].data(), t, sm.data());
+    }
+    for (int t = 0; t < 48; ++t) {
+        typename F::Tw w;
+        F::load_tw(w, t, tw.data());
+        F::pass_c(regs[t].data(), t, sm.data(), w);
+        if (t < F::NC)
+            for (int q = 0; q < F::RC; ++q) {
+                out[2 * (t + q * F::NC)] = (double)regs[t][q].x;
+                out[2 * (t + q * F::NC) + 1] = (double)regs[t][q].y;
+            }
+    }
+}
+extern "C" int emul_fft2_2160(int dir, int precision, const double* in, double* out) {
+    if (precision == 32) { if (dir < 0) run_fft2<float, -1, 48, 45>(in, out); else run_fft2<float, +1, 45, 48>(in, out); }
+    else { if (dir < 0) run_fft2<double, -1, 48, 45>(in, out); else run_fft2<double, +1, 45, 48>(in, out); }
     return 0;
 }

@@ -202,6 +202,7 @@ def test_dual_row_mid_matches_single_pair_kernel_and_oracle(lib):
     for dual in (1, 0):
         before = lib.cdll.emul_dual_launches()
         h = _lib.DeconvHandle(lib, psfs, (ny, nx), precision=32)
+        h.set_option('row_plan2', 0)        # the three-pass row kernels
         h.set_option('row_dual', dual)
         h.create_data(obj, 1e7, 1)
         assert h.info().Lx == 2160
@@ -243,3 +244,56 @@ def test_fast_rows_odd_and_ragged_shapes(lib, shape):
         o.iterate(); o.iterate()
         assert rel_l2(h.get(_lib.ESTIMATE), o.estimate) < 10 * tol
         h.close()
+
+
+def test_two_pass_plan_48x45_matches_numpy(lib):
+    """Fft2E (one exchange, one twiddle stage; Good-Thomas 3x16 and 9x5 butterflies)."""
+    rng = np.random.default_rng(2160)
+    x = rng.standard_normal(2160) + 1j * rng.standard_normal(2160)
+    xin = np.ascontiguousarray(x)
+    out = np.empty_like(xin)
+    for d, ref in ((-1, np.fft.fft(x)), (+1, np.fft.ifft(x) * 2160)):
+        for precision, tol in ((64, 1e-13), (32, 3e-6)):
+            assert lib.cdll.emul_fft2_2160(d, precision, xin.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+            assert np.abs(out - ref).max() < tol * np.abs(ref).max(), (d, precision)
+
+
+@pytest.mark.parametrize('shape', [(8, 2048), (5, 2100), (2, 2101)])
+def test_two_pass_row_kernels_match_three_pass_and_oracle(lib, shape):
+    """row2_fast_body (48 x 45 plan, 48 threads per row pair, all five row modes) against
+    the three-pass row kernels and the oracle: forward model + noise field + 2 RL
+    iterations + H / H_t, fp32."""
+    rng = np.random.default_rng(21)
+    ny, nx = shape
+    psfs = rng.random((3, 3, 107)) + 0.1
+    psfs /= psfs.sum(axis=(1, 2), keepdims=True)
+    obj = rng.random((1, ny, nx)) + 0.05
+    y = rng.random((3, ny, nx)) + 0.1
+    res = {}
+    for plan2 in (1, 0):
+        before = lib.cdll.emul_row2_launches()
+        h = _lib.DeconvHandle(lib, psfs, shape, precision=32)
+        h.set_option('row_plan2', plan2)
+        assert h.info().Lx == 2160
+        h.create_data(obj, 1e5 * obj.size, 4)
+        noisy = np.stack([h.get(_lib.NOISY, k) for k in range(3)])
+        noiseless = np.stack([h.get(_lib.NOISELESS, k) for k in range(3)])
+        h.iterate(2)
+        res[plan2] = dict(noisy=noisy, noiseless=noiseless, est=h.get(_lib.ESTIMATE),
+                          H=h.H(obj), Ht=h.Ht(y, True),
+                          launches=lib.cdll.emul_row2_launches() - before)
+        h.close()
+    # (the PSF rows are transformed at handle creation, before the option is read: 1 launch)
+    assert res[1]['launches'] > 8 and res[0]['launches'] <= 1
+    o = orc.Deconvolver([p[None] for p in psfs])
+    o.create_data_from_object(obj, total_brightness=1e5 * obj.size, random_seed=4)
+    assert rel_l2(res[1]['noiseless'], np.concatenate(o.noiseless_measurement)[:, None]) < 1e-5
+    assert rel_l2(res[1]['noiseless'], res[0]['noiseless']) < 2e-6
+    # same noiseless image up to rounding -> same Poisson field except where lambda differs in
+    # the last bits; compare the iterated estimates on the two-pass kernel's own field
+    o.noisy_measurement = [v for v in res[1]['noisy']]
+    o.iterate(); o.iterate()
+    assert rel_l2(res[1]['est'], o.estimate) < 1e-4
+    assert rel_l2(res[1]['H'], np.concatenate(o.H(obj))) < 1e-5
+    assert rel_l2(res[1]['Ht'], o.H_t([v[None] for v in y])) < 1e-5
+    assert rel_l2(res[1]['H'], res[0]['H']) < 2e-6
