@@ -275,6 +275,10 @@ class CudaBackend {
         if (dual) row_dual_ = atoi(dual) != 0;
         const char* plan2 = getenv("LSTED_ROW_PLAN2");  // A/B switch, same as option "row_plan2"
         if (plan2) row_plan2_ = atoi(plan2) != 0;
+        const char* pf = getenv("LSTED_PREFETCH");      // A/B switch, same as option "prefetch"
+        if (pf) prefetch_ = atoi(pf) != 0;
+        const char* pq = getenv("LSTED_PREFETCH_CTAS_PER_SM");   // prefetch distance in CTAs per SM
+        if (pq && atoi(pq) > 0) prefetch_quarters_ = atoi(pq);
     }
     ~CudaBackend() {
         cudaSetDevice(device_);
@@ -411,7 +415,7 @@ class CudaBackend {
     void set_row_dual(bool on) { row_dual_ = on; }
     void set_row_plan2(bool on) { row_plan2_ = on; }
     // row CTAs resident at once (4 per SM): prefetch for the CTA one wave ahead
-    int row_prefetch_distance() const { return prefetch_ ? num_sms_ * 4 : 0; }
+    int row_prefetch_distance() const { return prefetch_ ? (num_sms_ * prefetch_quarters_) : 0; }
     void set_prefetch(bool on) { prefetch_ = on; }
     void profile_reset() {
         profile_drain();
@@ -658,6 +662,9 @@ class CudaBackend {
     std::vector<void*> p2p_opened_;
     int p2p_rank_ = 0, p2p_world_ = 1; unsigned p2p_epoch_ = 0;
     bool prefetch_ = true;
+    int prefetch_quarters_ = 2;   // row-kernel L2 prefetch distance in CTAs per SM (half a wave of the
+                                  // 4 resident CTAs; measured 1: 0.280, 2: 0.281, 4: 0.283, 8: 0.321,
+                                  // off: 0.330 ms for row_mid)
     // two-pass 48 x 45 row kernels (fp32): 35 % fewer warp instructions and half the shared-memory
     // wavefronts, but 0.334 ms vs 0.283 ms for ROW_MID: 4792 straight-line instructions run by
     // 9 warps per SM stall on instruction fetch (ncu: no_inst 32 %).  Kept behind this switch.
