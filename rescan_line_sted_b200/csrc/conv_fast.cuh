@@ -702,19 +702,30 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 int* const queue = (int*)stage;       // [0] = count, [1..] = pixel offsets
                 const int nr = two ? 2 : 1;
                 LSTED_NOUNROLL
-                for (int e = 0; e < I::MC * I::RC * 2; ++e) {
-                    const int rr = e & 1, mq = e >> 1;
+                for (int mq = 0; mq < I::MC * I::RC; ++mq) {
                     const int m = mq / I::RC, q = mq - m * I::RC;
                     const int j = t + m * P::NT;
                     const int i = j + q * I::NC - shift;
-                    if (j < I::NC && rr < nr && i >= 0 && i < Nx) {
-                        const size_t o = (size_t)(y + rr) * Nx + i;
-                        const double lam = (double)out[o];
-                        double k;
-                        if (!(lam >= 10.0)) {
-                            out2[o] = (T)(poisson_sample(lam, a.seed, o, a.img0 + img) + 1e-9);
-                        } else if (poisson_fast_ptrs(lam, a.seed, o, a.img0 + img, k)) {
-                            out2[o] = (T)(k + 1e-9);
+                    if (!(j < I::NC && i >= 0 && i < Nx)) continue;
+                    // both rows of the pair: two independent straight-line attempts the
+                    // compiler interleaves (the fp64 sqrt / divisions are latency chains)
+                    size_t o[2];
+                    double lam[2], k[2];
+                    bool ok[2];
+                    LSTED_UNROLL
+                    for (int rr = 0; rr < 2; ++rr) {
+                        o[rr] = (size_t)(y + (rr < nr ? rr : 0)) * Nx + i;
+                        lam[rr] = (double)out[o[rr]];
+                        ok[rr] = poisson_fast_ptrs(lam[rr] >= 10.0 ? lam[rr] : 10.0, a.seed, o[rr],
+                                                   a.img0 + img, k[rr]);
+                    }
+                    LSTED_UNROLL
+                    for (int rr = 0; rr < 2; ++rr) {
+                        if (rr >= nr) continue;
+                        if (!(lam[rr] >= 10.0)) {
+                            out2[o[rr]] = (T)(poisson_sample(lam[rr], a.seed, o[rr], a.img0 + img) + 1e-9);
+                        } else if (ok[rr]) {
+                            out2[o[rr]] = (T)(k[rr] + 1e-9);
                         } else {
                             queue[1 + smem_counter_next(queue)] = rr * Nx + i;
                         }
