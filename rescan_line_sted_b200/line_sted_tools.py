@@ -405,6 +405,7 @@ class Deconvolver:
         self._handle = None
         self._shape = None
         self._have = set()  # which device arrays hold data
+        self._data_version = 0  # bumped whenever true_object changes
 
     # -- device plumbing ----------------------------------------------------
     def _engine(self, shape):
@@ -491,6 +492,7 @@ class Deconvolver:
             random_seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2 ** 31 + \
                 int(np.random.randint(0, 2 ** 31 - 1))
         h.create_data(obj, total_brightness, int(random_seed) % 2 ** 64)
+        self._data_version += 1
         self._have |= {_lib.TRUE_OBJECT, _lib.NOISELESS, _lib.NOISY}
         self._have.discard(_lib.ESTIMATE)
         return None
@@ -527,11 +529,18 @@ class Deconvolver:
         if save_tifs:
             eh = np.squeeze(np.concatenate(self.estimate_history, axis=0))
             np_tif.array_to_tif(eh, self.output_prefix + 'estimate_history.tif')
-            err = eh - self.true_object
-            if err.ndim == 2:
-                err = err.reshape(1, err.shape[0], err.shape[1])
-            spectrum = np.log(1 + np.abs(np.fft.fftshift(
-                np.fft.fftn(err, axes=(1, 2)), axes=(1, 2))))
+            # The reference re-transforms the whole history on every call (ref:539-548);
+            # the spectra of the estimates already saved cannot change, so only the new
+            # ones are computed -- same file, linear instead of quadratic work.
+            cache = self.__dict__.setdefault('_ft_error_history', [])
+            if cache and cache[0][0] != self._data_version:
+                del cache[:]                       # new object: start over
+            if len(cache) < len(self.estimate_history):
+                true_object = self.true_object     # one device read
+                for est in self.estimate_history[len(cache):]:
+                    cache.append((self._data_version, np.log(1 + np.abs(np.fft.fftshift(
+                        np.fft.fftn(est - true_object, axes=(1, 2)), axes=(1, 2))))))
+            spectrum = np.concatenate([c[1] for c in cache], axis=0)
             np_tif.array_to_tif(
                 spectrum, self.output_prefix + 'estimate_FT_error_history.tif')
         return None

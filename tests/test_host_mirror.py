@@ -105,6 +105,27 @@ def test_deconvolver_mirror(st, golden_dir, tmp_path):
     hist = np_tif.tif_to_array(str(tmp_path / 'sub') + '/run_estimate_history.tif')
     assert hist.shape == (1, 128, 128) and hist.dtype == np.float32
     assert d.saved_iterations == [8] and len(d.estimate_history) == 1
+    # the error-spectrum history (ref:539-548) after more saves equals a from-scratch
+    # transform of the whole history (the mirror only transforms the new estimates)
+    d.iterate()
+    d.record_iteration()
+    d.iterate()
+    d.record_iteration()
+    spec = np_tif.tif_to_array(str(tmp_path / 'sub') + '/run_estimate_FT_error_history.tif')
+    eh = np.concatenate(d.estimate_history, axis=0)
+    want = np.log(1 + np.abs(np.fft.fftshift(np.fft.fftn(eh - d.true_object, axes=(1, 2)),
+                                             axes=(1, 2))))
+    assert spec.shape == (3, 128, 128)
+    assert np.allclose(spec, want.astype(np.float32), rtol=1e-6)
+    d.create_data_from_object(g['object_u8'].astype(np.float64) * 2, total_brightness=5e10,
+                              random_seed=1)                      # new object: cache restarts
+    d.estimate_history, d.saved_iterations = [], []
+    d.iterate()
+    d.record_iteration()
+    spec = np_tif.tif_to_array(str(tmp_path / 'sub') + '/run_estimate_FT_error_history.tif')
+    want = np.log(1 + np.abs(np.fft.fftshift(np.fft.fftn(d.estimate - d.true_object, axes=(1, 2)),
+                                             axes=(1, 2))))
+    assert spec.shape == (1, 128, 128) and np.allclose(spec, want.astype(np.float32), rtol=1e-6)
     # load_data_from_tif round trip (dead code in the reference, works here)
     d2 = st.Deconvolver([p[None] for p in g['psfs']], output_prefix=str(tmp_path) + '/l_',
                         verbose=False)
