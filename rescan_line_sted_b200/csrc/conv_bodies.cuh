@@ -216,6 +216,8 @@ template <typename T> struct ColArgs {
     const cplx<T>* tw;      // exp(-2 pi i m / Ly)
     const cplx<T>* src;     // OTF: [K] XB(rows_in); H: XB(Ny); HT: [K] XB(Ny)
     const cplx<T>* otf;     // [K] XB(rows = Ly)
+    const T* otf_real;      // same layout, real part only: set when every PSF is point-symmetric
+                            // and the OTFs are stored centred (then they are real; sy = sx = 0)
     cplx<T>* dst;           // OTF: [K] XB(Ly); H: [K] XB(Ny); HT: XB(Ny)
     int K;
     int rows_in;            // valid input rows (zero padded up to Ly)
@@ -313,6 +315,31 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
         const int y = w / C, c = w - y * C;
         dst[slab2_index(y, c, C)] = z[c * Lp + pad<T>(g.sy + y)];
     });
+}
+
+// Centring of the OTFs of point-symmetric PSFs.  psf[c + a] == psf[c - a] about the centre
+// pixel c = ((ny-1)/2, (nx-1)/2) makes OTF(f) * exp(+2 pi i (fy cy / Ly + fx cx / Lx)) REAL: the
+// phase ramp is exactly the 'same' crop offset (s = c), so with the centred OTF the convolution
+// lands at offset 0 (geometry sy = sx = 0, no phase ramp in the row kernels) and only the real
+// part has to be stored and streamed (half the OTF bytes of the column kernels).
+template <typename T> struct OtfCenterArgs {
+    cplx<T>* otf;         // in/out: [K][nxb][Ly][C]
+    T* otf_real;          // out: real part, same indexing
+    const cplx<T>* tw_y;  // exp(-2 pi i m / Ly)
+    const cplx<T>* tw_x;  // exp(-2 pi i m / Lx)
+    int nxb, Ly, Lx, C, cy, cx;
+    size_t n;             // K * nxb * Ly * C
+};
+template <typename T> LSTED_HD void otf_center_apply(const OtfCenterArgs<T>& a, size_t i) {
+    const int c = (int)(i % a.C);
+    size_t r = i / a.C;
+    const int y = (int)(r % a.Ly);
+    r /= a.Ly;
+    const int x = (int)(r % a.nxb) * a.C + c;
+    const cplx<T> ph = conj(a.tw_y[((size_t)y * a.cy) % a.Ly] * a.tw_x[((size_t)x * a.cx) % a.Lx]);
+    const cplx<T> v = a.otf[i] * ph;
+    a.otf[i] = v;
+    a.otf_real[i] = v.x;
 }
 
 }  // namespace lsted

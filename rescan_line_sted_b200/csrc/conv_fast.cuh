@@ -19,6 +19,7 @@
 // Bodies are written as per-thread phases separated by CTA barriers
 // (`cx.phase(regs, f)`), so tests/host_emul can replay them thread by thread.
 #pragma once
+#include <type_traits>
 #include "conv_bodies.cuh"
 #include "fft_static.cuh"
 
@@ -168,12 +169,32 @@ LSTED_HD void col_otf_product(ColRegs<P>& r, int t, int c, const cplx<typename P
     }
 }
 
+// the same with a REAL (centred, point-symmetric PSF) OTF: a real scaling / real FMA per element
+template <class P, bool ACCUMULATE>
+LSTED_HD void col_otf_product_real(ColRegs<P>& r, int t, int c, const typename P::T* otf) {
+    typedef typename P::Fwd F;
+    typedef typename P::T T;
+    LSTED_UNROLL
+    for (int m = 0; m < F::MC; ++m) {
+        const int j = t + m * P::NT;
+        if (j < F::NC) {
+            LSTED_UNROLL
+            for (int q = 0; q < F::RC; ++q) {
+                const T o = otf[(size_t)(j + q * F::NC) * P::C + c];
+                if (ACCUMULATE) r.keep[m * F::RC + q] = fma_real(r.v[m * F::RC + q], o, r.keep[m * F::RC + q]);
+                else r.v[m * F::RC + q] = scale(r.keep[m * F::RC + q], o);
+            }
+        }
+    }
+}
+
 // Compile-time image geometry of the column kernels (rows and crop offset): as for the row
 // kernels, the `0 <= y < Ny` tests then survive only on the first and last butterfly leg.
 struct ColGeomRuntime { enum { NY = 0, SY = 0 }; };
 template <int NY_, int SY_> struct ColGeomFixed { enum { NY = NY_, SY = SY_ }; };
 
-template <int MODE, class P, class Ctx, class G = ColGeomRuntime>
+// RO: the OTFs are real (a.otf_real, see OtfCenterArgs) -- half the bytes to stage and stream
+template <int MODE, class P, class Ctx, class G = ColGeomRuntime, bool RO = false>
 LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                             cplx<typename P::T>* smem, ColRegs<P>* regs, G = G()) {
     typedef typename P::T T;
@@ -202,8 +223,10 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     const bool stage = LSTED_COL_STAGE_OTF != 0;
     cplx<T>* const otf_s = tw_s + P::COL_TW;
     mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
-    const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(cplx<T>));
-    const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
+    // one OTF slab: complex, or real when RO (`otf0` then counts T elements)
+    typedef typename std::conditional<RO, T, cplx<T> >::type OtfT;
+    const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(OtfT));
+    const OtfT* otf0 = (RO ? (const OtfT*)a.otf_real : (const OtfT*)a.otf) + (size_t)xb * slab_ly;
     cx.phase(regs, [&](int tid, ColRegs<P>& r) {
         // (hoisting base twiddles into registers costs spills at 96 registers / 576 threads)
         if (tid < P::COL_TW) tw_s[tid] = a.tw[tid];
@@ -246,9 +269,11 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                 if (k < K) {
                     if (stage) {
                         mbar_wait(mbar, (unsigned)(k & 1));
-                        col_otf_product<P, false>(r, t, c, otf_s, false);
+                        if (RO) col_otf_product_real<P, false>(r, t, c, (const T*)otf_s);
+                        else col_otf_product<P, false>(r, t, c, otf_s, false);
                     } else {
-                        col_otf_product<P, false>(r, t, c, otf0 + (size_t)k * img_ly, false);
+                        if (RO) col_otf_product_real<P, false>(r, t, c, (const T*)(otf0 + (size_t)k * img_ly));
+                        else col_otf_product<P, false>(r, t, c, (const cplx<T>*)(otf0 + (size_t)k * img_ly), false);
                     }
                     I::pass_a(r.v, t, s0);
                 }
@@ -283,9 +308,11 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                 F::pass_c(r.v, t, s1, tw);
                 if (stage) {
                     mbar_wait(mbar, (unsigned)((k - 1) & 1));
-                    col_otf_product<P, true>(r, t, c, otf_s, k == 1);
+                    if (RO) col_otf_product_real<P, true>(r, t, c, (const T*)otf_s);
+                    else col_otf_product<P, true>(r, t, c, otf_s, k == 1);
                 } else {
-                    col_otf_product<P, true>(r, t, c, otf0 + (size_t)(k - 1) * img_ly, k == 1);
+                    if (RO) col_otf_product_real<P, true>(r, t, c, (const T*)(otf0 + (size_t)(k - 1) * img_ly));
+                    else col_otf_product<P, true>(r, t, c, (const cplx<T>*)(otf0 + (size_t)(k - 1) * img_ly), k == 1);
                 }
             }
             if (k < K) {

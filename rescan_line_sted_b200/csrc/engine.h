@@ -54,18 +54,23 @@ class EngineBase {
 template <typename T, class BK> class DeconvEngine : public EngineBase {
   public:
     ConvGeom g;
+    bool allow_centered, centered;   // centred real OTFs of point-symmetric PSFs (see OtfCenterArgs)
+    T* otf_real;
+    int sy0, sx0;                    // the 'same' crop offsets of the un-centred geometry
     int K, ny, nx;
     int iterations_done;
     bool have_norm, have_estimate, exact_clip;
     int rank, world, k_offset;
 
     DeconvEngine(BK& backend, int K_, int ny_, int nx_, int Ny, int Nx, int force_L = 0)
-        : K(K_), ny(ny_), nx(nx_), iterations_done(0), have_norm(false), have_estimate(false),
+        : allow_centered(force_L == 0), centered(false), otf_real(0),
+          K(K_), ny(ny_), nx(nx_), iterations_done(0), have_norm(false), have_estimate(false),
           exact_clip(false), rank(0), world(1), k_offset(0), bk(backend), tmpK(0), p2p_recv(0),
           p2p_flags(0), p2p_words(0) {
         const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g, &BK::fast_cols, force_L);
         if (why[0]) throw std::string(why);
         npix = (size_t)Ny * Nx;
+        sy0 = g.sy; sx0 = g.sx;
         std::vector<cplx<T> > tw;
         tw.resize(g.Lx); fill_twiddles<T>(g.Lx, tw.data());
         tw_x = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * g.Lx);
@@ -88,7 +93,8 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     }
     ~DeconvEngine() {
         void* all[] = {tw_x, tw_y, otf, spec1, specK, true_object, estimate, norm,
-                       scratch, noiseless, noisy, stage64, object64, partial, tmpK, p2p_recv, p2p_flags};
+                       scratch, noiseless, noisy, stage64, object64, partial, tmpK, p2p_recv, p2p_flags,
+                       otf_real};
         for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) bk.free(all[i]);
     }
 
@@ -121,9 +127,42 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         ca.src = rows; ca.dst = otf; ca.K = K; ca.rows_in = ny;
         ca.scale = (T)(1.0 / ((double)g.Lx * (double)g.Ly));
         bk.template launch_col<COL_OTF, T>(g.nxb * K, ca);
+        // Point-symmetric PSFs (every PSF the reference builds is): store the OTFs centred, as
+        // real numbers, and drop the crop offsets from the geometry.  Only where the
+        // compile-time column plan (which reads the real array) exists, and not inside tiles.
+        g.sy = sy0; g.sx = sx0;
+        centered = allow_centered && bk.real_otf_supported(g, (int)sizeof(cplx<T>)) &&
+                   point_symmetric(psfs_host);
+        if (centered) {
+            if (!otf_real) otf_real = (T*)bk.alloc(sizeof(T) * otf_elems(g) * K);
+            OtfCenterArgs<T> oc;
+            oc.otf = otf; oc.otf_real = otf_real; oc.tw_y = tw_y; oc.tw_x = tw_x;
+            oc.nxb = g.nxb; oc.Ly = g.Ly; oc.Lx = g.Lx; oc.C = g.C;
+            oc.cy = (ny - 1) / 2; oc.cx = (nx - 1) / 2;
+            oc.n = otf_elems(g) * K;
+            bk.otf_center(oc);
+            g.sy = 0; g.sx = 0;
+        }
         bk.sync();
         bk.free(rows); bk.free(dT); bk.free(d64);
         have_norm = false;
+    }
+    // psf[c + a] == psf[c - a] for every PSF (odd sizes only), to 1e-12 of the peak
+    bool point_symmetric(const double* psfs_host) const {
+        if (ny % 2 == 0 || nx % 2 == 0) return false;
+        const size_t n = (size_t)ny * nx;
+        for (int k = 0; k < K; ++k) {
+            const double* p = psfs_host + n * k;
+            double peak = 0, worst = 0;
+            for (size_t i = 0; i < n; ++i) {
+                const double a = p[i] < 0 ? -p[i] : p[i];
+                const double d = p[i] - p[n - 1 - i];
+                if (a > peak) peak = a;
+                if ((d < 0 ? -d : d) > worst) worst = (d < 0 ? -d : d);
+            }
+            if (!(worst <= 1e-12 * peak)) return false;
+        }
+        return true;
     }
 
     // ---- operators on device arrays ------------------------------------
@@ -327,6 +366,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         ColArgs<T> a;
         memset(&a, 0, sizeof(a));
         a.g = gg; a.tw = tw_y; a.otf = otf; a.rows_in = gg.Ny; a.scale = (T)1;
+        a.otf_real = centered ? otf_real : 0;
         return a;
     }
     // specK holds K row-spectra -> out = sum_k conv_k (spec1 is clobbered)
@@ -345,6 +385,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
                 ColArgs<T> ct = col_args(g);
                 ct.src = specK + (same_input ? 0 : spec_elems(g, g.Ny) * k);
                 ct.otf = otf + otf_elems(g) * k;
+                if (centered) ct.otf_real = otf_real + otf_elems(g) * k;
                 ct.dst = spec1; ct.K = 1;
                 bk.template launch_col<COL_HT, T>(g.nxb, ct);
                 RowArgs<T> rb = row_args(g);

@@ -73,6 +73,7 @@ typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 
 // G: image geometry known at compile time (the 2048-wide / 107-wide-PSF headline case) or not
 typedef lsted::RowGeomFixed<2048, 53> RowGeom2048;
+typedef lsted::RowGeomFixed<2048, 0> RowGeom2048c;    // centred real OTFs: no crop offset
 template <int MODE, class P, class G = lsted::RowGeomRuntime>
 __global__ void __launch_bounds__(P::ROW_THREADS, sizeof(typename P::T) == 4 ? (LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
 row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
@@ -109,13 +110,14 @@ row_mid_dual_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
 }
 
 typedef lsted::ColGeomFixed<2048, 53> ColGeom2048;
-template <int MODE, class P, class G = lsted::ColGeomRuntime>
+typedef lsted::ColGeomFixed<2048, 0> ColGeom2048c;    // centred real OTFs: no crop offset
+template <int MODE, class P, class G = lsted::ColGeomRuntime, bool RO = false>
 __global__ void __launch_bounds__(P::COL_THREADS, 1)
 col_fast_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceCtx cx;
     lsted::ColRegs<P> r;
-    lsted::col_fast_body<MODE, P, DeviceCtx, G>(cx, blockIdx.x, a,
+    lsted::col_fast_body<MODE, P, DeviceCtx, G, RO>(cx, blockIdx.x, a,
                                   reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
 }
 
@@ -161,6 +163,13 @@ __global__ void __launch_bounds__(kEwThreads) win_kernel(const lsted::WinArgs<T>
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
         lsted::win_apply<OP, T>(a, e);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) otf_center_kernel(const lsted::OtfCenterArgs<T> a) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
+        lsted::otf_center_apply<T>(a, i);
 }
 
 // Fused cross-GPU H_t reduction (conv_fast.cuh): the kernels after it on this stream may read
@@ -275,6 +284,8 @@ class CudaBackend {
         if (dual) row_dual_ = atoi(dual) != 0;
         const char* plan2 = getenv("LSTED_ROW_PLAN2");  // A/B switch, same as option "row_plan2"
         if (plan2) row_plan2_ = atoi(plan2) != 0;
+        const char* ro = getenv("LSTED_REAL_OTF");      // A/B switch: centred real OTFs (read at set_psfs)
+        if (ro) real_otf_ = atoi(ro) != 0;
         const char* pf = getenv("LSTED_PREFETCH");      // A/B switch, same as option "prefetch"
         if (pf) prefetch_ = atoi(pf) != 0;
         const char* pq = getenv("LSTED_PREFETCH_CTAS_PER_SM");   // prefetch distance in CTAs per SM
@@ -373,6 +384,17 @@ class CudaBackend {
         after();
     }
     void zero_bytes(void* p, size_t n) { CUDA_CHECK(cudaMemsetAsync(p, 0, n, stream_)); }
+    // centred real OTFs are read by the compile-time column kernels only
+    bool real_otf_supported(const lsted::ConvGeom& g, int cplx_bytes) const {
+        return use_fast_ && real_otf_ &&
+               (cplx_bytes == 8 ? plan_fits_cols<Plan2160f>(g) : plan_fits_cols<Plan2160d>(g));
+    }
+    template <typename T> void otf_center(const lsted::OtfCenterArgs<T>& a) {
+        before(KK_EW);
+        otf_center_kernel<T><<<num_sms_ * 8, 256, 0, stream_>>>(a);
+        after();
+    }
+    void set_real_otf(bool on) { real_otf_ = on; }
     void fill_double(double* p, size_t n, double v) {
         if (v != 0.0) { lsted::ApiError e; e.code = LSTED_ERR_ARG; e.msg = "fill_double: zero only"; throw e; }
         CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(double), stream_));
@@ -448,13 +470,18 @@ class CudaBackend {
         // fp32 kernels that index pixels have an instance with the headline geometry folded in
         const bool fixed = sizeof(typename P::T) == 4 && MODE != lsted::ROW_FWD &&
                            a.g.Nx == (int)RowGeom2048::NX && a.g.sx == (int)RowGeom2048::SX;
+        const bool fixed_c = sizeof(typename P::T) == 4 && MODE != lsted::ROW_FWD &&
+                             a.g.Nx == (int)RowGeom2048c::NX && a.g.sx == 0;   // centred OTFs
         static bool configured = false;
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (sizeof(typename P::T) == 4)
+            if (sizeof(typename P::T) == 4) {
                 CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048c>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
             configured = true;
         }
         before(kind);
@@ -462,6 +489,7 @@ class CudaBackend {
         const int fast_grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
         (void)grid;
         if (fixed) row_fast_kernel<MODE, P, RowGeom2048><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
+        else if (fixed_c) row_fast_kernel<MODE, P, RowGeom2048c><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
         else row_fast_kernel<MODE, P><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
         after();
     }
@@ -489,6 +517,24 @@ class CudaBackend {
             const int ncta = grid < num_sms_ ? grid : num_sms_;
             before(kind);
             col_ht_p2p_kernel<P><<<ncta, P::COL_THREADS, smem, stream_>>>(a);
+            after();
+            return;
+        }
+        if (a.otf_real) {   // centred real OTFs
+            const bool fixed_c = sizeof(typename P::T) == 4 && a.g.Ny == (int)ColGeom2048c::NY &&
+                                 a.g.sy == 0 && a.rows_in == a.g.Ny;
+            static bool ro_configured = false;
+            if (!ro_configured) {
+                CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P, lsted::ColGeomRuntime, true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (sizeof(typename P::T) == 4)
+                    CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P, ColGeom2048c, true>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ro_configured = true;
+            }
+            before(kind);
+            if (fixed_c) col_fast_kernel<MODE, P, ColGeom2048c, true><<<grid, P::COL_THREADS, smem, stream_>>>(a);
+            else col_fast_kernel<MODE, P, lsted::ColGeomRuntime, true><<<grid, P::COL_THREADS, smem, stream_>>>(a);
             after();
             return;
         }
@@ -661,6 +707,7 @@ class CudaBackend {
     void* p2p_spec_[lsted::kMaxPeers]; unsigned* p2p_done_[lsted::kMaxPeers];
     std::vector<void*> p2p_opened_;
     int p2p_rank_ = 0, p2p_world_ = 1; unsigned p2p_epoch_ = 0;
+    bool real_otf_ = true;
     bool prefetch_ = true;
     int prefetch_quarters_ = 2;   // row-kernel L2 prefetch distance in CTAs per SM (half a wave of the
                                   // 4 resident CTAs; measured 1: 0.280, 2: 0.281, 4: 0.283, 8: 0.321,

@@ -53,12 +53,17 @@ extern "C" void emul_set_broadcast(broadcast_cb cb) { g_broadcast = cb; }
 
 static int g_dual_launches = 0;
 static int g_row2_launches = 0;
+static int g_real_otf_launches = 0;
+extern "C" int emul_real_otf_launches(void) { return g_real_otf_launches; }
 extern "C" int emul_row2_launches(void) { return g_row2_launches; }
 extern "C" int emul_dual_launches(void) { return g_dual_launches; }
 
 class HostBackend {
   public:
-    explicit HostBackend(int) : bytes_(0), use_fast_(true) {}
+    explicit HostBackend(int) : bytes_(0), use_fast_(true) {
+        const char* ro = getenv("LSTED_REAL_OTF");   // same A/B switch as the CUDA backend
+        if (ro) real_otf_ = atoi(ro) != 0;
+    }
     void set_fast_path(bool on) { use_fast_ = on; }
     void set_row_dual(bool on) { row_dual_ = on; }
     void set_row_plan2(bool on) { row_plan2_ = on; }
@@ -98,6 +103,14 @@ class HostBackend {
     void fill_double(double* p, size_t n, double v) { for (size_t i = 0; i < n; ++i) p[i] = v; }
     // peer-memory reduction: GPU only (the CPU replay reduces through the callback)
     void zero_bytes(void* p, size_t n) { memset(p, 0, n); }
+    bool real_otf_supported(const lsted::ConvGeom& g, int cplx_bytes) const {
+        return use_fast_ && real_otf_ && g.Ly == Plan2160f::L &&
+               g.C == (cplx_bytes == 8 ? (int)Plan2160f::C : (int)Plan2160d::C);
+    }
+    template <typename T> void otf_center(const lsted::OtfCenterArgs<T>& a) {
+        for (size_t i = 0; i < a.n; ++i) lsted::otf_center_apply<T>(a, i);
+    }
+    void set_real_otf(bool on) { real_otf_ = on; }
     void p2p_export(void*, void*, void*, char*) { throw std::string("peer memory needs GPUs"); }
     void p2p_attach(int, int, const char*, size_t) { throw std::string("peer memory needs GPUs"); }
     bool p2p_ready(const lsted::ConvGeom&, int) const { return false; }
@@ -195,10 +208,17 @@ class HostBackend {
                 std::vector<lsted::ColRegs<P> > regs(P::COL_THREADS);
                 HostCtx cx;
                 cx.nthreads = P::COL_THREADS;
-                const bool fixed = sizeof(T) == 4 && a.g.Ny == 2048 && a.g.sy == 53;
+                const bool fixed = sizeof(T) == 4 && a.g.Ny == 2048 && a.g.sy == 53 && !a.otf_real;
+                if (a.otf_real) {
+#pragma omp single
+                    ++g_real_otf_launches;
+                }
 #pragma omp for schedule(dynamic)
                 for (int b = 0; b < grid; ++b) {
-                    if (fixed)
+                    if (a.otf_real)
+                        lsted::col_fast_body<(MODE == lsted::COL_OTF ? lsted::COL_H : MODE), P, HostCtx,
+                                             lsted::ColGeomRuntime, true>(cx, b, a, smem.data(), regs.data());
+                    else if (fixed)
                         lsted::col_fast_body<(MODE == lsted::COL_OTF ? lsted::COL_H : MODE), P, HostCtx,
                                              lsted::ColGeomFixed<2048, 53> >(cx, b, a, smem.data(), regs.data());
                     else
@@ -254,6 +274,7 @@ class HostBackend {
     bool use_fast_;
     bool row_dual_ = false;
     bool row_plan2_ = false;
+    bool real_otf_ = true;
 };
 
 #define LSTED_BACKEND HostBackend

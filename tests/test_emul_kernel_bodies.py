@@ -297,3 +297,42 @@ def test_two_pass_row_kernels_match_three_pass_and_oracle(lib, shape):
     assert rel_l2(res[1]['H'], np.concatenate(o.H(obj))) < 1e-5
     assert rel_l2(res[1]['Ht'], o.H_t([v[None] for v in y])) < 1e-5
     assert rel_l2(res[1]['H'], res[0]['H']) < 2e-6
+
+
+@pytest.mark.parametrize('precision,tol', [(64, 1e-12), (32, 1e-5)])
+def test_centred_real_otfs_for_point_symmetric_psfs(lib, monkeypatch, precision, tol):
+    """Point-symmetric PSFs (all the reference's are) on a 2160-long column geometry: the
+    OTFs are stored centred and real, the crop offsets drop out of the geometry; against
+    the oracle and against the same handle with the option off (complex OTFs)."""
+    rng = np.random.default_rng(31)
+    shape = (2100, 8)
+    half = rng.random((3, 11, 3))
+    psfs = np.concatenate([half, rng.random((3, 1, 3)), half[:, ::-1, ::-1]], axis=1)   # 23 x 3
+    psfs[:, 11, :] = 0.5 * (psfs[:, 11, :] + psfs[:, 11, ::-1])
+    assert np.abs(psfs - psfs[:, ::-1, ::-1]).max() == 0
+    obj = rng.random((1,) + shape) + 0.05
+    y = rng.random((3,) + shape) + 0.1
+    o = orc.Deconvolver([p[None] for p in psfs])
+    res = {}
+    launches = {}
+    for real in (1, 0):
+        monkeypatch.setenv('LSTED_REAL_OTF', str(real))   # read when the handle is created
+        before = lib.cdll.emul_real_otf_launches()
+        h = _lib.DeconvHandle(lib, psfs, shape, precision=precision)
+        assert h.info().Ly == 2160
+        res[real] = dict(H=h.H(obj), Ht=h.Ht(y, True))
+        h.create_data(obj, 1e5 * obj.size, 9)
+        noisy = [h.get(_lib.NOISY, k) for k in range(3)]
+        h.iterate(2)
+        res[real]['est'] = h.get(_lib.ESTIMATE)
+        res[real]['noisy'] = noisy
+        launches[real] = lib.cdll.emul_real_otf_launches() - before
+        h.close()
+    assert launches[1] >= 6 and launches[0] == 0
+    assert rel_l2(res[1]['H'], np.concatenate(o.H(obj))) < tol
+    assert rel_l2(res[1]['Ht'], o.H_t([v[None] for v in y])) < tol
+    o.create_data_from_object(obj, total_brightness=1e5 * obj.size, random_seed=9)
+    o.noisy_measurement = res[1]['noisy']
+    o.iterate(); o.iterate()
+    assert rel_l2(res[1]['est'], o.estimate) < 10 * tol
+    assert rel_l2(res[1]['H'], res[0]['H']) < tol
