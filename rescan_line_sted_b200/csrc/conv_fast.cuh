@@ -373,7 +373,7 @@ LSTED_HD int p2p_block_at(int pos, int me, int world, int nxb) {
     return run * world + (off < me ? off : off + 1);
 }
 
-template <class P, class Ctx, class G = ColGeomRuntime>
+template <class P, class Ctx, class G = ColGeomRuntime, bool RO = false>
 LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename P::T>& a,
                               cplx<typename P::T>* smem, ColRegs<P>* regs, G = G()) {
     typedef typename P::T T;
@@ -390,7 +390,8 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
     cplx<T>* const buf1 = smem + (size_t)P::C * P::LSM_COL;
     cplx<T>* const otf_s = tw_s + P::COL_TW;
     mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
-    const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(cplx<T>));
+    typedef typename std::conditional<RO, T, cplx<T> >::type OtfT;   // real OTFs: see col_fast_body
+    const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(OtfT));
     const int K = a.K, world = a.p2p_world, me = a.p2p_rank;
     // one partial sum in the receive slab: pairs of register values, so that a thread moves
     // 16 bytes per store / load (512 contiguous bytes per warp on the NVLink side)
@@ -414,7 +415,7 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
         const int xb = p2p_block_at(pos, me, world, g.nxb);
         const int owner = xb % world;
         const cplx<T>* src0 = a.src + (size_t)xb * slab_ny;
-        const cplx<T>* otf0 = a.otf + (size_t)xb * slab_ly;
+        const OtfT* otf0 = (RO ? (const OtfT*)a.otf_real : (const OtfT*)a.otf) + (size_t)xb * slab_ly;
         for (int k = 0; k <= K; ++k) {
             cx.phase(regs, [&](int tid, ColRegs<P>& r) {
                 LSTED_COL_IDS
@@ -431,7 +432,8 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
                 if (k > 0) {
                     F::pass_c(r.v, t, s1, tw);
                     mbar_wait(mbar, (seq + (unsigned)(k - 1)) & 1u);
-                    col_otf_product<P, true>(r, t, c, otf_s, k == 1);
+                    if (RO) col_otf_product_real<P, true>(r, t, c, (const T*)otf_s);
+                    else col_otf_product<P, true>(r, t, c, otf_s, k == 1);
                 }
                 if (k < K) {
                     col_load_fwd_a<P>(r.v, t, c, src0 + (size_t)k * img_ny, Ny);

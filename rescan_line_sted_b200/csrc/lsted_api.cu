@@ -122,13 +122,13 @@ col_fast_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
 }
 
 // COL_HT with the cross-GPU sum fused in (persistent: one CTA per SM walks several blocks)
-template <class P, class G = lsted::ColGeomRuntime>
+template <class P, bool RO = false>
 __global__ void __launch_bounds__(P::COL_THREADS, 1)
 col_ht_p2p_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceCtx cx;
     lsted::ColRegs<P> r;
-    lsted::col_ht_p2p_body<P, DeviceCtx, G>(cx, blockIdx.x, gridDim.x, a,
+    lsted::col_ht_p2p_body<P, DeviceCtx, lsted::ColGeomRuntime, RO>(cx, blockIdx.x, gridDim.x, a,
                                   reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
 }
 
@@ -510,13 +510,16 @@ class CudaBackend {
         if (MODE == lsted::COL_HT && a.p2p_world > 1) {
             static bool p2p_configured = false;
             if (!p2p_configured) {
-                CUDA_CHECK(cudaFuncSetAttribute(col_ht_p2p_kernel<P>,
+                CUDA_CHECK(cudaFuncSetAttribute(col_ht_p2p_kernel<P, false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CUDA_CHECK(cudaFuncSetAttribute(col_ht_p2p_kernel<P, true>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 p2p_configured = true;
             }
             const int ncta = grid < num_sms_ ? grid : num_sms_;
             before(kind);
-            col_ht_p2p_kernel<P><<<ncta, P::COL_THREADS, smem, stream_>>>(a);
+            if (a.otf_real) col_ht_p2p_kernel<P, true><<<ncta, P::COL_THREADS, smem, stream_>>>(a);
+            else col_ht_p2p_kernel<P, false><<<ncta, P::COL_THREADS, smem, stream_>>>(a);
             after();
             return;
         }
