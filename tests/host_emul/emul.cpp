@@ -412,3 +412,8 @@ extern "C" int emul_fft2_2160(int dir, int precision, const double* in, double* 
     else { if (dir < 0) run_fft2<double, -1, 48, 45>(in, out); else run_fft2<double, +1, 45, 48>(in, out); }
     return 0;
 }
+
+// block order of the fused peer-memory reduction (conv_fast.cuh: p2p_block_at)
+extern "C" int emul_p2p_block_at(int pos, int me, int world, int nxb) {
+    return lsted::p2p_block_at(pos, me, world, nxb);
+}

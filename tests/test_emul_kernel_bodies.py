@@ -336,3 +336,19 @@ def test_centred_real_otfs_for_point_symmetric_psfs(lib, monkeypatch, precision,
     o.iterate(); o.iterate()
     assert rel_l2(res[1]['est'], o.estimate) < 10 * tol
     assert rel_l2(res[1]['H'], res[0]['H']) < tol
+
+
+def test_peer_reduction_block_order(lib):
+    """Every rank walks all column blocks exactly once, the ones it does not own first
+    (ascending), then its own (xb % world == rank): the order the fused H_t reduction relies
+    on to have the peers' partial sums in place when it reaches the blocks it finishes."""
+    for world in (2, 3, 4, 8):
+        for nxb in (271, 8, 9, 541):
+            if nxb < world:
+                continue
+            for me in range(world):
+                seq = [lib.cdll.emul_p2p_block_at(p, me, world, nxb) for p in range(nxb)]
+                assert sorted(seq) == list(range(nxb))
+                owned = [x for x in range(nxb) if x % world == me]
+                others = [x for x in range(nxb) if x % world != me]
+                assert seq == others + owned
