@@ -59,6 +59,8 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
     static_assert(RA * RC < 256 && RC * RA < 256 && NT_ <= 256 && NT_ * C_ >= 256 && RA * RB * RC >= 256,
                   "base twiddles of both transforms must sit in the first COL_TW table entries");
     static_assert((RC - QH) * PX <= LSM_ROW, "mirror exchange must fit one row buffer");
+    static_assert(2 * L * sizeof(T_) + sizeof(mbar_t) <= LSM_ROW * 2 * sizeof(T_),
+                  "two staged rows + their mbarrier must fit one row buffer");
 };
 
 template <class P> struct ColRegs {
@@ -72,6 +74,9 @@ template <class P> struct RowRegs {
     cplx<typename P::T> ramp0;           // crop-offset phase ramp at this thread's first bin
 };
 
+#ifndef LSTED_ROW_BULK_STAGE
+#define LSTED_ROW_BULK_STAGE 1   // measurement / normalisation / estimate rows by cp.async.bulk
+#endif
 #ifndef LSTED_COL_STAGE_OTF
 #define LSTED_COL_STAGE_OTF 1   // OTF slabs travel global -> shared by cp.async.bulk, one k ahead
 #endif
@@ -556,6 +561,9 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     // XB2: the pair (row y, row y+1) of column c sits at ((xb*Nye + y)*C + 2c) + {0, 1}
     const int NBUF = MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
     const bool stage_est = MODE == ROW_FINAL && P::ROW_FINAL_BUFS == 4;
+    const unsigned row_bytes = (unsigned)(Nx * sizeof(T));
+    const bool bulk_rows = LSTED_ROW_BULK_STAGE && row_bytes % 16 == 0 &&
+                           (((size_t)a.aux | (size_t)a.real_out) & 15) == 0;
 
 #define LSTED_ROW_IDS                                      \
     const int f = tid / P::NTG, t = tid - f * P::NTG;      \
@@ -627,12 +635,29 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 // measurement (MID) or normalisation + estimate (FINAL) rows y, y+1 -> shared
                 // memory, asynchronously (used after the inverse transform, two barriers from here)
                 const T* m0 = (MODE == ROW_MID ? a.aux + real_off : a.aux) + (size_t)y * Nx;
-                async_copy_row(stage, m0, Nx, t, P::NTG);
-                if (two) async_copy_row(stage + P::L, m0 + Nx, Nx, t, P::NTG);
-                if (stage_est) {
-                    const T* e0 = a.real_out + (size_t)y * Nx;
-                    async_copy_row(stage2, e0, Nx, t, P::NTG);
-                    if (two) async_copy_row(stage2 + P::L, e0 + Nx, Nx, t, P::NTG);
+                if (bulk_rows) {
+                    // whole rows by the bulk-copy engine: one thread, one instruction per row,
+                    // nothing through the LSU (the rows are 16-byte multiples, 16-byte aligned)
+                    if (t == 0) {
+                        mbar_t* const mb = (mbar_t*)(stage + 2 * P::L);
+                        const int nrow = two ? 2 : 1;
+                        mbar_init(mb);
+                        bulk_expect(mb, row_bytes * nrow * (stage_est ? 2 : 1));
+                        for (int rr = 0; rr < nrow; ++rr) bulk_copy(stage + rr * P::L, m0 + (size_t)rr * Nx, row_bytes, mb);
+                        if (stage_est) {
+                            const T* e0 = a.real_out + (size_t)y * Nx;
+                            for (int rr = 0; rr < nrow; ++rr)
+                                bulk_copy(stage2 + rr * P::L, e0 + (size_t)rr * Nx, row_bytes, mb);
+                        }
+                    }
+                } else {
+                    async_copy_row(stage, m0, Nx, t, P::NTG);
+                    if (two) async_copy_row(stage + P::L, m0 + Nx, Nx, t, P::NTG);
+                    if (stage_est) {
+                        const T* e0 = a.real_out + (size_t)y * Nx;
+                        async_copy_row(stage2, e0, Nx, t, P::NTG);
+                        if (two) async_copy_row(stage2 + P::L, e0 + Nx, Nx, t, P::NTG);
+                    }
                 }
             }
             if (!live) return;
@@ -669,7 +694,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 I::load_b(r.v, t, s0, r.twi);
                 I::pass_b(r.v, t, s1);
             }
-            if (MODE == ROW_MID || MODE == ROW_FINAL) async_copy_wait_all();   // visible after the barrier
+            if ((MODE == ROW_MID || MODE == ROW_FINAL) && !bulk_rows) async_copy_wait_all();   // visible after the barrier
         });
         // inverse pass C, the pointwise step on registers (logical position
         // idx = j + q*NC holds pixel idx - sx of rows y (re) and y+1 (im)) and the
@@ -682,6 +707,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             if (MODE == ROW_INV_SIM && t == 0) *(int*)stage = 0;   // noise queue (below)
             if (!live) return;
             I::pass_c(r.v, t, s1, r.twi);
+            if ((MODE == ROW_MID || MODE == ROW_FINAL) && bulk_rows)
+                mbar_wait((mbar_t*)(stage + 2 * P::L), 0u);    // the staged rows have landed
             LSTED_UNROLL
             for (int m = 0; m < I::MC; ++m) {
                 const int j = t + m * P::NT;

@@ -252,6 +252,29 @@ LSTED_HD void bulk_load(void* dst_smem, const void* src, unsigned bytes, mbar_t*
     for (unsigned i = 0; i < bytes; ++i) d[i] = s[i];
 #endif
 }
+// several bulk copies on one mbarrier phase: announce the total once, then issue the copies
+LSTED_HD void bulk_expect(mbar_t* bar, unsigned total_bytes) {
+#ifdef __CUDA_ARCH__
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(total_bytes) : "memory");
+#else
+    (void)bar; (void)total_bytes;
+#endif
+}
+LSTED_HD void bulk_copy(void* dst_smem, const void* src, unsigned bytes, mbar_t* bar) {
+#ifdef __CUDA_ARCH__
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+#else
+    (void)bar;
+    const char* s = (const char*)src;
+    char* d = (char*)dst_smem;
+    for (unsigned i = 0; i < bytes; ++i) d[i] = s[i];
+#endif
+}
 LSTED_HD void mbar_wait(mbar_t* bar, unsigned parity) {
 #ifdef __CUDA_ARCH__
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
