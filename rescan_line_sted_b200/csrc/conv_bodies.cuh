@@ -76,6 +76,8 @@ template <typename T> struct RowArgs {
     unsigned long long seed; // SIM
     unsigned int img0;       // SIM: global index of image 0 (RNG stream id)
     int prefetch_ahead;      // fast path: L2-prefetch the operands of CTA (blockIdx + this); 0 = off
+    const void* tmap_in;     // fast path, fp32: tensor maps (CUtensorMap in global memory) of spec_in /
+    const void* tmap_out;    // spec_out; when set the pair's spectrum chunks travel by TMA (fft_core.cuh)
 };
 
 template <typename T> LSTED_HD T clip0(T v) { return v < (T)0 ? (T)0 : v; }

@@ -40,7 +40,7 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
         COL_TW = 256,                               // + base twiddles
         // row CTA: PR groups of NTG threads (whole warps), one row pair each
         NTG = (NT_ + 31) / 32 * 32,
-        LSM_ROW = (SEQ + 15) / 16 * 16 + 8,
+        LSM_ROW = (SEQ + 15) / 16 * 16 + 16,    // multiple of 128 bytes: tensor-map copies land here
         ROW_THREADS = NTG * PR_,
         // two ping-pong buffers + staging per pair: 2 measurement rows of <= L pixels (ROW_MID),
         // 2 normalisation rows + 2 estimate rows (ROW_FINAL)
@@ -538,7 +538,9 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
 struct RowGeomRuntime { enum { NX = 0, SX = 0 }; };
 template <int NX_, int SX_> struct RowGeomFixed { enum { NX = NX_, SX = SX_ }; };
 
-template <int MODE, class P, class Ctx, class G = RowGeomRuntime>
+// TMA: the spectrum chunks of the pair come and go through tensor-map bulk copies staged in
+// the second exchange buffer (free while they are needed) instead of per-thread LDG / STG.
+template <int MODE, class P, class Ctx, class G = RowGeomRuntime, bool TMA = false>
 LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                             cplx<typename P::T>* smem, RowRegs<P>* regs, G = G()) {
     typedef typename P::T T;
@@ -561,6 +563,11 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     // XB2: the pair (row y, row y+1) of column c sits at ((xb*Nye + y)*C + 2c) + {0, 1}
     const int NBUF = MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
     const bool stage_est = MODE == ROW_FINAL && P::ROW_FINAL_BUFS == 4;
+    enum { CHUNK = 2 * P::PR * P::C,                                  // complex numbers per chunk
+           TMA_BYTES = 2 * kTmaBoxBlocks * CHUNK * (int)sizeof(cplx<T>) };  // two boxes cover nxb blocks
+    enum { TMA_MB_OFF = P::LSM_ROW * (int)sizeof(cplx<T>) - 16 };   // its mbarrier: the buffer's last 16 bytes
+    static_assert(!TMA || (P::PR == 1 && (P::L / 2 / P::C + 1) * CHUNK * (int)sizeof(cplx<T>) <= TMA_MB_OFF),
+                  "staged spectrum + its mbarrier must fit the second exchange buffer");
     const unsigned row_bytes = (unsigned)(Nx * sizeof(T));
     const bool bulk_rows = LSTED_ROW_BULK_STAGE && row_bytes % 16 == 0 &&
                            (((size_t)a.aux | (size_t)a.real_out) & 15) == 0;
@@ -591,8 +598,12 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             const T* ax = (MODE == ROW_MID ? a.aux + (size_t)img2 * Ny * Nx : a.aux) + (size_t)y2 * Nx;
             cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {   // prefetches only: no barrier
                 (void)r;
-                for (int xb = tid; xb < g.nxb; xb += P::ROW_THREADS)
-                    prefetch_chunk(sp + (size_t)xb * xb_stride, (unsigned)(2 * P::PR * C * sizeof(cplx<T>)));
+                if (TMA) {
+                    if (tid < 2) tma_prefetch_chunks(a.tmap_in, img2, y2, tid * (g.nxb - kTmaBoxBlocks), C);
+                } else {
+                    for (int xb = tid; xb < g.nxb; xb += P::ROW_THREADS)
+                        prefetch_chunk(sp + (size_t)xb * xb_stride, (unsigned)(2 * P::PR * C * sizeof(cplx<T>)));
+                }
                 prefetch_l2_range(ax, (size_t)rows2 * Nx * sizeof(T), tid, P::ROW_THREADS);
                 if (MODE == ROW_FINAL)
                     prefetch_l2_range(a.real_out + (size_t)y2 * Nx, (size_t)rows2 * Nx * sizeof(T), tid,
@@ -629,8 +640,29 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         // Z[i] = A[i] + i B[i] (i <= L/2), conj(A[L-i]) + i conj(B[L-i]) otherwise.
         // q < QH is always the lower half, q > QH always the upper half.
         const cplx<T>* src = a.spec_in + spec_off;
+        if (TMA) {
+            // request the pair's spectrum chunks; the barrier of this phase publishes the
+            // initialised mbarrier to the threads that wait on it in the next one
+            cx.phase(regs, [&](int tid, RowRegs<P>& r) {
+                LSTED_ROW_IDS
+                (void)r;
+                if (t == 0 && pair < Py) {
+                    mbar_t* const mb = (mbar_t*)((char*)s1 + TMA_MB_OFF);
+                    mbar_init(mb);
+                    bulk_expect(mb, (unsigned)TMA_BYTES);
+                    // two boxes of kTmaBoxBlocks column blocks; the second one ends at the last block
+                    // (it overlaps the first by a block or so: no out-of-bounds box rows)
+                    for (int h = 0; h < 2; ++h) {
+                        const int xb0 = h * (g.nxb - kTmaBoxBlocks);
+                        tma_load_chunks<T>((char*)s1 + (size_t)xb0 * CHUNK * sizeof(cplx<T>), a.tmap_in, src, img, y,
+                                           xb0, g.nxb, Nye, C, CHUNK, mb);
+                    }
+                }
+            });
+        }
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
+            mbar_t* const mb_spec = (mbar_t*)((char*)s1 + TMA_MB_OFF);
             if ((MODE == ROW_MID || MODE == ROW_FINAL) && pair < Py) {
                 // measurement (MID) or normalisation + estimate (FINAL) rows y, y+1 -> shared
                 // memory, asynchronously (used after the inverse transform, two barriers from here)
@@ -668,6 +700,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             }
             const cplx<T>* lo = src + ((size_t)(t / C) * Nye + y) * C + 2 * (t % C);
             const int tm = Lx - t;  // mirror of bin t; (tm - q*NC) is the mirror of bin t + q*NC
+            if (TMA) mbar_wait(mb_spec, 0u);   // staged chunks: bin k sits at s1[2k], s1[2k + 1]
             LSTED_UNROLL
             for (int q = 0; q < I::RA; ++q) {
                 const int i = t + q * P::NC;
@@ -675,10 +708,10 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 if (q == P::QH) upper = 2 * i > Lx;
                 const cplx<T>* p;
                 if (q < P::QH || (q == P::QH && !upper)) {
-                    p = lo + (size_t)(q * (P::NC / C)) * xb_stride;
+                    p = TMA ? s1 + 2 * i : lo + (size_t)(q * (P::NC / C)) * xb_stride;
                 } else {
                     const int k = tm - q * P::NC;
-                    p = src + ((size_t)(k / C) * Nye + y) * C + 2 * (k % C);
+                    p = TMA ? s1 + 2 * k : src + ((size_t)(k / C) * Nye + y) * C + 2 * (k % C);
                 }
                 cplx<T> A, B;
                 load_pair(p, A, B);   // one 16-byte (fp32) access; the slot of a missing last row is never used
@@ -820,12 +853,14 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     // Hermitian split of the lower half, crop-offset phase ramp, XB store:
     // bins k = t + q*NC with mirror L - k = (NC - t) + (RC - 1 - q)*NC.
     cplx<T>* dst = a.spec_out + spec_off;
-    cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {   // last phase: nothing to wait for
+    auto split_and_store = [&](int tid, RowRegs<P>& r) {
         LSTED_ROW_IDS
         if (!live) return;
         const int tp = t == 0 ? 0 : P::NC - t;         // mirror thread
         const int qoff = t == 0 ? 1 : 0;               // thread 0 mirrors onto itself, one q up
-        cplx<T>* pk = dst + ((size_t)(t / C) * Nye + y) * C + 2 * (t % C);
+        // TMA: the pair's chunks are assembled in s1 (bin k at s1[2k], s1[2k+1]) and leave in bulk
+        cplx<T>* pk = TMA ? s1 + 2 * t : dst + ((size_t)(t / C) * Nye + y) * C + 2 * (t % C);
+        const size_t xb_stride = TMA ? (size_t)2 * C : (size_t)Nye * C;   // elements per column block
         // phase ramp exp(+2 pi i k shift / L) at bins k = t + q*NC: ramp0 * d^q with the
         // thread-independent step d (powers by binary splitting, no table gathers)
         cplx<T> dq[P::QH + 2];
@@ -854,7 +889,24 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             // (a missing last row has its own never-read slot: the pair is always stored whole)
             store_pair(pk + (size_t)(q * (P::NC / C)) * xb_stride, oa, two ? ob : mk<T>(0, 0));
         }
-    });
+        if (TMA) fence_async_smem();
+    };
+    if (!TMA) {
+        cx.phase_nosync(regs, split_and_store);   // last phase: nothing to wait for
+    } else {
+        cx.phase(regs, split_and_store);
+        cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {
+            LSTED_ROW_IDS
+            (void)r;
+            if (t != 0 || pair >= Py) return;
+            for (int h = 0; h < 2; ++h) {
+                const int xb0 = h * (g.nxb - kTmaBoxBlocks);
+                tma_store_chunks<T>((const char*)s1 + (size_t)xb0 * CHUNK * sizeof(cplx<T>), a.tmap_out, dst, img, y,
+                                    xb0, g.nxb, Nye, C, CHUNK);
+            }
+            tma_store_finish();
+        });
+    }
 #undef LSTED_ROW_IDS
 }
 

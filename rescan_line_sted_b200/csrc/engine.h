@@ -66,7 +66,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         : allow_centered(force_L == 0), centered(false), otf_real(0),
           K(K_), ny(ny_), nx(nx_), iterations_done(0), have_norm(false), have_estimate(false),
           exact_clip(false), rank(0), world(1), k_offset(0), bk(backend), tmpK(0), p2p_recv(0),
-          p2p_flags(0), p2p_words(0) {
+          p2p_flags(0), p2p_words(0), tmaps_tried(false), tmap_specK(0), tmap_spec1(0) {
         const char* why = make_geom(Ny, Nx, ny, nx, (int)sizeof(cplx<T>), &g, &BK::fast_cols, force_L);
         if (why[0]) throw std::string(why);
         npix = (size_t)Ny * Nx;
@@ -94,7 +94,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     ~DeconvEngine() {
         void* all[] = {tw_x, tw_y, otf, spec1, specK, true_object, estimate, norm,
                        scratch, noiseless, noisy, stage64, object64, partial, tmpK, p2p_recv, p2p_flags,
-                       otf_real};
+                       otf_real, tmap_specK, tmap_spec1};
         for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) bk.free(all[i]);
     }
 
@@ -214,6 +214,16 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         simulate(total_brightness, rescale, seed);
     }
     void forget_normalization() { have_norm = false; }
+    // tensor maps of the two row-spectrum arrays (fp32 fast rows): see fft_core.cuh tma_load_chunks
+    void ensure_tmaps() {
+        if (tmaps_tried) return;
+        tmaps_tried = true;
+        if (!bk.row_tma_supported(g, (int)sizeof(cplx<T>))) return;
+        const int chunk_floats = 2 * 1 * g.C * 2;   // 2 rows x C columns x (re, im), one pair per CTA
+        tmap_specK = bk.make_spec_tmap(specK, even_rows(g.Ny), g.nxb, g.C, K, chunk_floats);
+        tmap_spec1 = bk.make_spec_tmap(spec1, even_rows(g.Ny), g.nxb, g.C, 1, chunk_floats);
+        if (!tmap_specK || !tmap_spec1) tmap_specK = tmap_spec1 = 0;
+    }
 
     // Orientation sharding: this handle owns `K` of the orientations
     // (global indices k_offset .. k_offset+K-1) plus replicas of the estimate and
@@ -257,8 +267,10 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
             ColArgs<T> ca = col_args(g);
             ca.src = spec1; ca.dst = specK; ca.K = K;
             bk.template launch_col<COL_H, T>(g.nxb, ca);
+            ensure_tmaps();
             RowArgs<T> rm = row_args(g);
             rm.nimg = K; rm.spec_in = specK; rm.spec_out = specK; rm.aux = noisy;
+            rm.tmap_in = rm.tmap_out = tmap_specK;
             bk.template launch_row<ROW_MID, T>(row_blocks(g) * K, rm);
             if (!exact_clip) {
                 ColArgs<T> ct = col_args(g);
@@ -275,6 +287,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
                 RowArgs<T> rf = row_args(g);
                 rf.nimg = 1; rf.spec_in = spec1; rf.spec_out = spec1;
                 rf.real_out = estimate; rf.aux = norm;
+                rf.tmap_in = rf.tmap_out = tmap_spec1;
                 bk.template launch_row<ROW_FINAL, T>(row_blocks(g), rf);
             } else {
                 ht_from_specK(scratch);
@@ -350,6 +363,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     double *stage64, *object64, *partial;
     T* tmpK;  // K images, allocated on first use by the host-array forms of H / H_t
     cplx<T>* p2p_recv; unsigned* p2p_flags; size_t p2p_words;
+    bool tmaps_tried; void* tmap_specK; void* tmap_spec1;
     T* tmp_images() {
         if (!tmpK) tmpK = (T*)bk.alloc(sizeof(T) * npix * K);
         return tmpK;

@@ -275,6 +275,75 @@ LSTED_HD void bulk_copy(void* dst_smem, const void* src, unsigned bytes, mbar_t*
     for (unsigned i = 0; i < bytes; ++i) d[i] = s[i];
 #endif
 }
+// Tensor-map (TMA) copies of one row pair's spectrum: the pair owns one 64-byte chunk
+// (2 rows x C columns) in every column block, 64 KB apart -- a 3-D tensor
+// [image][block][floats of a block slab] with a box of {floats of the chunk, kTmaBoxBlocks, 1}
+// moves the nxb chunks with two instructions, none of them through the LSU.  Device: the
+// descriptor `tmap` (CUtensorMap in global memory) does the addressing; host replay: the
+// same box is copied with plain loops from `base` (the image's spectrum, XB2 layout).
+enum { kTmaBoxBlocks = 137 };
+template <typename T>
+LSTED_HD void tma_load_chunks(void* dst_smem, const void* tmap, const cplx<T>* base, int img, int y, int xb0,
+                              int nxb, int rows_e, int C, int chunk_cplx, mbar_t* bar) {
+#ifdef __CUDA_ARCH__
+    (void)base; (void)nxb; (void)rows_e;
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int c0 = y * C * 2;   // floats from the start of the block slab (y even)
+    (void)chunk_cplx;
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(d), "l"(tmap), "r"(b), "r"(c0), "r"(xb0), "r"(img) : "memory");
+#else
+    (void)tmap; (void)bar; (void)img;
+    cplx<T>* d = (cplx<T>*)dst_smem;
+    for (int i = 0; i < kTmaBoxBlocks; ++i)
+        for (int e = 0; e < chunk_cplx; ++e) {
+            const int xb = xb0 + i;
+            d[(size_t)i * chunk_cplx + e] =
+                xb < nxb ? base[((size_t)xb * rows_e + y) * C + e] : mk<T>(0, 0);
+        }
+#endif
+}
+template <typename T>
+LSTED_HD void tma_store_chunks(const void* src_smem, const void* tmap, cplx<T>* base, int img, int y, int xb0,
+                               int nxb, int rows_e, int C, int chunk_cplx) {
+#ifdef __CUDA_ARCH__
+    (void)base; (void)nxb; (void)rows_e; (void)chunk_cplx;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(src_smem);
+    const int c0 = y * C * 2;
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tmap), "r"(d), "r"(c0), "r"(xb0), "r"(img) : "memory");
+#else
+    (void)tmap; (void)img;
+    const cplx<T>* s = (const cplx<T>*)src_smem;
+    for (int i = 0; i < kTmaBoxBlocks; ++i)
+        for (int e = 0; e < chunk_cplx; ++e) {
+            const int xb = xb0 + i;
+            if (xb < nxb) base[((size_t)xb * rows_e + y) * C + e] = s[(size_t)i * chunk_cplx + e];
+        }
+#endif
+}
+LSTED_HD void tma_store_finish() {   // by the issuing thread: the bulk stores have read shared memory
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+LSTED_HD void tma_prefetch_chunks(const void* tmap, int img, int y, int xb0, int C) {
+#ifdef __CUDA_ARCH__
+    const int c0 = y * C * 2;
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(tmap), "r"(c0), "r"(xb0), "r"(img) : "memory");
+#else
+    (void)tmap; (void)img; (void)y; (void)xb0; (void)C;
+#endif
+}
+LSTED_HD void fence_async_smem() {   // generic-proxy writes to shared memory -> visible to bulk copies
+#ifdef __CUDA_ARCH__
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 LSTED_HD void mbar_wait(mbar_t* bar, unsigned parity) {
 #ifdef __CUDA_ARCH__
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);

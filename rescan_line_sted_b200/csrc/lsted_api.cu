@@ -3,6 +3,7 @@
 // Build: see Makefile (nvcc -gencode arch=compute_100a,code=sm_100a).
 // The kernels are thin __global__ shells around the bodies in
 // conv_bodies.cuh / psf_kernels.cuh; orchestration lives in engine.h.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -13,6 +14,7 @@
 #include <string>
 #include <map>
 #include <vector>
+#include <type_traits>
 
 #include "../../include/lsted.h"
 #include "engine.h"
@@ -74,13 +76,13 @@ typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 // G: image geometry known at compile time (the 2048-wide / 107-wide-PSF headline case) or not
 typedef lsted::RowGeomFixed<2048, 53> RowGeom2048;
 typedef lsted::RowGeomFixed<2048, 0> RowGeom2048c;    // centred real OTFs: no crop offset
-template <int MODE, class P, class G = lsted::RowGeomRuntime>
+template <int MODE, class P, class G = lsted::RowGeomRuntime, bool TMA = false>
 __global__ void __launch_bounds__(P::ROW_THREADS, sizeof(typename P::T) == 4 ? (LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
 row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     DeviceCtx cx;
     lsted::RowRegs<P> r;
-    lsted::row_fast_body<MODE, P, DeviceCtx, G>(cx, blockIdx.x, a,
+    lsted::row_fast_body<MODE, P, DeviceCtx, G, TMA>(cx, blockIdx.x, a,
                                   reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
 }
 
@@ -284,6 +286,8 @@ class CudaBackend {
         if (dual) row_dual_ = atoi(dual) != 0;
         const char* plan2 = getenv("LSTED_ROW_PLAN2");  // A/B switch, same as option "row_plan2"
         if (plan2) row_plan2_ = atoi(plan2) != 0;
+        const char* rt = getenv("LSTED_ROW_TMA");       // A/B switch: spectrum chunks by tensor-map copies
+        if (rt) row_tma_ = atoi(rt) != 0;
         const char* ro = getenv("LSTED_REAL_OTF");      // A/B switch: centred real OTFs (read at set_psfs)
         if (ro) real_otf_ = atoi(ro) != 0;
         const char* pf = getenv("LSTED_PREFETCH");      // A/B switch, same as option "prefetch"
@@ -484,15 +488,82 @@ class CudaBackend {
             }
             configured = true;
         }
-        before(kind);
         // the plan's own pairs-per-CTA decides the grid (the generic geometry may differ)
         const int fast_grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
         (void)grid;
+        if (launch_row_fast_tma<MODE, P>(fast_grid, a, kind, smem, fixed, fixed_c)) return;
+        before(kind);
         if (fixed) row_fast_kernel<MODE, P, RowGeom2048><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
         else if (fixed_c) row_fast_kernel<MODE, P, RowGeom2048c><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
         else row_fast_kernel<MODE, P><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
         after();
     }
+    // spectrum chunks by tensor-map bulk copies (fp32, one pair per CTA, ROW_MID / ROW_FINAL)
+    template <int MODE, class P>
+    typename std::enable_if<(sizeof(typename P::T) == 4 && P::PR == 1 &&
+                             (MODE == lsted::ROW_MID || MODE == lsted::ROW_FINAL)), bool>::type
+    launch_row_fast_tma(int fast_grid, const lsted::RowArgs<typename P::T>& a, int kind, size_t smem,
+                        bool fixed, bool fixed_c) {
+        if (!a.tmap_in || !a.tmap_out || !row_tma_) return false;
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, lsted::RowGeomRuntime, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048c, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        before(kind);
+        if (fixed) row_fast_kernel<MODE, P, RowGeom2048, true><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
+        else if (fixed_c) row_fast_kernel<MODE, P, RowGeom2048c, true><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
+        else row_fast_kernel<MODE, P, lsted::RowGeomRuntime, true><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
+        after();
+        return true;
+    }
+    template <int MODE, class P>
+    typename std::enable_if<!(sizeof(typename P::T) == 4 && P::PR == 1 &&
+                              (MODE == lsted::ROW_MID || MODE == lsted::ROW_FINAL)), bool>::type
+    launch_row_fast_tma(int, const lsted::RowArgs<typename P::T>&, int, size_t, bool, bool) { return false; }
+
+    // CUtensorMap (in global memory) of a row-spectrum array: [nimg][nxb][rows_e * C * 2 floats],
+    // box = {floats of one pair chunk, kTmaBoxBlocks, 1}.  Returns 0 when tensor maps are unavailable.
+    void* make_spec_tmap(void* base, int rows_e, int nxb, int C, int nimg, int chunk_floats) {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+        static encode_fn encode = 0;
+        if (!encode) {
+            void* fn = 0;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+                qres != cudaDriverEntryPointSuccess || !fn)
+                return 0;
+            encode = (encode_fn)fn;
+        }
+        CUtensorMap map;
+        const cuuint64_t dims[3] = {(cuuint64_t)rows_e * C * 2, (cuuint64_t)nxb, (cuuint64_t)nimg};
+        const cuuint64_t strides[2] = {(cuuint64_t)rows_e * C * 2 * sizeof(float),
+                                       (cuuint64_t)nxb * rows_e * C * 2 * sizeof(float)};
+        const cuuint32_t box[3] = {(cuuint32_t)chunk_floats, (cuuint32_t)lsted::kTmaBoxBlocks, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 0;
+        void* d = alloc(sizeof(map));
+        CUDA_CHECK(cudaMemcpyAsync(d, &map, sizeof(map), cudaMemcpyHostToDevice, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        return d;
+    }
+    bool row_tma_supported(const lsted::ConvGeom& g, int cplx_bytes) const {
+        return use_fast_ && row_tma_ && cplx_bytes == 8 && plan_fits_rows<Plan2160f>(g) && Plan2160f::PR == 1 &&
+               g.nxb >= lsted::kTmaBoxBlocks && g.nxb <= 2 * lsted::kTmaBoxBlocks &&
+               (g.nxb - lsted::kTmaBoxBlocks) % 2 == 0;   // two boxes cover the blocks, 128-byte aligned in smem
+    }
+    void set_row_tma(bool on) { row_tma_ = on; }
     template <int MODE, class P> void launch_col_fast(int grid, const lsted::ColArgs<typename P::T>& a,
                                                       int kind) {
         const size_t smem = lsted::fast_col_smem_bytes<P>();
@@ -711,6 +782,7 @@ class CudaBackend {
     std::vector<void*> p2p_opened_;
     int p2p_rank_ = 0, p2p_world_ = 1; unsigned p2p_epoch_ = 0;
     bool real_otf_ = true;
+    bool row_tma_ = true;
     bool prefetch_ = true;
     int prefetch_quarters_ = 2;   // row-kernel L2 prefetch distance in CTAs per SM (half a wave of the
                                   // 4 resident CTAs; measured 1: 0.280, 2: 0.281, 4: 0.283, 8: 0.321,

@@ -12,6 +12,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <type_traits>
 #include "../../include/lsted.h"
 #include "../../rescan_line_sted_b200/csrc/engine.h"
 #include "../../rescan_line_sted_b200/csrc/tiled.h"
@@ -54,6 +55,8 @@ extern "C" void emul_set_broadcast(broadcast_cb cb) { g_broadcast = cb; }
 static int g_dual_launches = 0;
 static int g_row2_launches = 0;
 static int g_real_otf_launches = 0;
+static int g_row_tma_launches = 0;
+extern "C" int emul_row_tma_launches(void) { return g_row_tma_launches; }
 extern "C" int emul_real_otf_launches(void) { return g_real_otf_launches; }
 extern "C" int emul_row2_launches(void) { return g_row2_launches; }
 extern "C" int emul_dual_launches(void) { return g_dual_launches; }
@@ -111,6 +114,13 @@ class HostBackend {
         for (size_t i = 0; i < a.n; ++i) lsted::otf_center_apply<T>(a, i);
     }
     void set_real_otf(bool on) { real_otf_ = on; }
+    // tensor-map copies: the host replay runs the same staged code path with plain loops
+    // (fft_core.cuh); the "descriptor" is just a non-null token
+    void* make_spec_tmap(void*, int, int, int, int, int) { return alloc(8); }
+    bool row_tma_supported(const lsted::ConvGeom& g, int cplx_bytes) const {
+        return use_fast_ && row_tma_ && cplx_bytes == 8 && g.Lx == Plan2160f::L && g.C == (int)Plan2160f::C;
+    }
+    void set_row_tma(bool on) { row_tma_ = on; }
     void p2p_export(void*, void*, void*, char*) { throw std::string("peer memory needs GPUs"); }
     void p2p_attach(int, int, const char*, size_t) { throw std::string("peer memory needs GPUs"); }
     bool p2p_ready(const lsted::ConvGeom&, int) const { return false; }
@@ -142,6 +152,7 @@ class HostBackend {
                 const bool fixed = sizeof(T) == 4 && MODE != lsted::ROW_FWD && a.g.Nx == 2048 && a.g.sx == 53;
 #pragma omp for schedule(dynamic)
                 for (int b = 0; b < grid; ++b) {
+                    if (run_row_tma<MODE, P>(cx, b, a, smem.data(), regs.data())) continue;
                     if (fixed)
                         lsted::row_fast_body<MODE, P, HostCtx, lsted::RowGeomFixed<2048, 53> >(
                             cx, b, a, smem.data(), regs.data());
@@ -159,6 +170,24 @@ class HostBackend {
             for (int b = 0; b < grid; ++b) lsted::row_body<MODE, T>(cx, b, a, smem.data());
         }
     }
+    template <int MODE, class P>
+    typename std::enable_if<(sizeof(typename P::T) == 4 && P::PR == 1 &&
+                             (MODE == lsted::ROW_MID || MODE == lsted::ROW_FINAL)), bool>::type
+    run_row_tma(HostCtx& cx, int b, const lsted::RowArgs<typename P::T>& a, lsted::cplx<typename P::T>* smem,
+                lsted::RowRegs<P>* regs) {
+        if (!a.tmap_in || !a.tmap_out || !row_tma_) return false;
+        if (b == 0) {
+#pragma omp atomic
+            ++g_row_tma_launches;
+        }
+        lsted::row_fast_body<MODE, P, HostCtx, lsted::RowGeomRuntime, true>(cx, b, a, smem, regs);
+        return true;
+    }
+    template <int MODE, class P>
+    typename std::enable_if<!(sizeof(typename P::T) == 4 && P::PR == 1 &&
+                              (MODE == lsted::ROW_MID || MODE == lsted::ROW_FINAL)), bool>::type
+    run_row_tma(HostCtx&, int, const lsted::RowArgs<typename P::T>&, lsted::cplx<typename P::T>*,
+                lsted::RowRegs<P>*) { return false; }
     template <int MODE> bool launch_row2(const lsted::RowArgs<double>&) { return false; }
     template <int MODE> bool launch_row2(const lsted::RowArgs<float>& a) {
         typedef lsted::FastPlan2<float, 48, 45, 4, 2> P;
@@ -275,6 +304,7 @@ class HostBackend {
     bool row_dual_ = false;
     bool row_plan2_ = false;
     bool real_otf_ = true;
+    bool row_tma_ = true;
 };
 
 #define LSTED_BACKEND HostBackend
