@@ -48,3 +48,27 @@ def test_fast_path_matches_oracle_and_generic(precision, tol, shape):
         assert rel_l2(g.get(_lib.ESTIMATE), h.get(_lib.ESTIMATE)) < 10 * tol
         g.close()
     h.close()
+
+
+@pytest.mark.parametrize('shape,K', [((64, 2048), 2), ((1184, 2048), 2), ((801, 2048), 3), ((2048, 2048), 4)])
+def test_tensor_map_row_staging_is_bit_identical(shape, K):
+    """ROW_MID / ROW_FINAL move their spectrum chunks by tensor-map TMA (option `row_tma`,
+    default on); the arithmetic is the same, so the estimates must agree bit for bit with the
+    per-thread LDG/STG kernels.  Sizes on both sides of two full waves of row CTAs and of a
+    20 MB spectrum array, an odd row count, and the last orientation (whose chunks end the
+    allocation)."""
+    from rescan_line_sted_b200 import _lib
+    lib = _lib.get()
+    rng = np.random.default_rng(3)
+    psfs = rng.random((K, 3, 21))
+    x = rng.random((1,) + shape) + 0.1
+    est = {}
+    for tma in (0, 1):
+        h = _lib.DeconvHandle(lib, psfs, shape, precision=32)
+        h.set_option('row_tma', tma)
+        h.create_data(x, 1e6 * x.size, 1)
+        h.iterate(3)
+        est[tma] = h.get(_lib.ESTIMATE)
+        h.close()
+    assert np.isfinite(est[1]).all() and est[1].min() > 0
+    assert np.array_equal(est[0], est[1])
