@@ -89,8 +89,8 @@ template <class P> LSTED_HD size_t fast_col_smem_bytes() {
                                                   (LSTED_COL_STAGE_OTF ? P::COL_OTF_ELEMS : 0)) +
            (LSTED_COL_STAGE_OTF ? 16 : 0);
 }
-template <class P> LSTED_HD size_t fast_row_smem_bytes(int mode) {
-    const int bufs = mode == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
+template <class P> LSTED_HD size_t fast_row_smem_bytes(int mode, bool lean = false) {
+    const int bufs = lean ? 2 : mode == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
     return sizeof(cplx<typename P::T>) * (size_t)bufs * P::PR * P::LSM_ROW;
 }
 
@@ -540,7 +540,10 @@ template <int NX_, int SX_> struct RowGeomFixed { enum { NX = NX_, SX = SX_ }; }
 
 // TMA: the spectrum chunks of the pair come and go through tensor-map bulk copies staged in
 // the second exchange buffer (free while they are needed) instead of per-thread LDG / STG.
-template <int MODE, class P, class Ctx, class G = RowGeomRuntime, bool TMA = false>
+// TMA == 2 (ROW_MID only, "lean"): additionally no staging buffer for the measurement rows
+// (they are read in place, from L2 thanks to the prefetch of an earlier CTA): two buffers
+// instead of three, so five CTAs per SM instead of four.
+template <int MODE, class P, class Ctx, class G = RowGeomRuntime, int TMA = 0>
 LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                             cplx<typename P::T>* smem, RowRegs<P>* regs, G = G()) {
     typedef typename P::T T;
@@ -561,7 +564,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     const int shift = (MODE == ROW_FWD) ? 0 : (G::NX ? (int)G::SX : g.sx);
     const size_t xb_stride = (size_t)Nye * C;  // elements between consecutive column blocks
     // XB2: the pair (row y, row y+1) of column c sits at ((xb*Nye + y)*C + 2c) + {0, 1}
-    const int NBUF = MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
+    const bool LEAN = TMA == 2 && MODE == ROW_MID;
+    const int NBUF = LEAN ? 2 : MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
     const bool stage_est = MODE == ROW_FINAL && P::ROW_FINAL_BUFS == 4;
     enum { CHUNK = 2 * P::PR * P::C,                                  // complex numbers per chunk
            TMA_BYTES = 2 * kTmaBoxBlocks * CHUNK * (int)sizeof(cplx<T>) };  // two boxes cover nxb blocks
@@ -663,7 +667,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             mbar_t* const mb_spec = (mbar_t*)((char*)s1 + TMA_MB_OFF);
-            if ((MODE == ROW_MID || MODE == ROW_FINAL) && pair < Py) {
+            if ((MODE == ROW_MID || MODE == ROW_FINAL) && !LEAN && pair < Py) {
                 // measurement (MID) or normalisation + estimate (FINAL) rows y, y+1 -> shared
                 // memory, asynchronously (used after the inverse transform, two barriers from here)
                 const T* m0 = (MODE == ROW_MID ? a.aux + real_off : a.aux) + (size_t)y * Nx;
@@ -727,7 +731,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 I::load_b(r.v, t, s0, r.twi);
                 I::pass_b(r.v, t, s1);
             }
-            if ((MODE == ROW_MID || MODE == ROW_FINAL) && !bulk_rows) async_copy_wait_all();   // visible after the barrier
+            if ((MODE == ROW_MID || MODE == ROW_FINAL) && !LEAN && !bulk_rows) async_copy_wait_all();   // visible after the barrier
         });
         // inverse pass C, the pointwise step on registers (logical position
         // idx = j + q*NC holds pixel idx - sx of rows y (re) and y+1 (im)) and the
@@ -740,7 +744,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             if (MODE == ROW_INV_SIM && t == 0) *(int*)stage = 0;   // noise queue (below)
             if (!live) return;
             I::pass_c(r.v, t, s1, r.twi);
-            if ((MODE == ROW_MID || MODE == ROW_FINAL) && bulk_rows)
+            if ((MODE == ROW_MID || MODE == ROW_FINAL) && !LEAN && bulk_rows)
                 mbar_wait((mbar_t*)(stage + 2 * P::L), 0u);    // the staged rows have landed
             LSTED_UNROLL
             for (int m = 0; m < I::MC; ++m) {
@@ -761,8 +765,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                                 out[o] = clip0(z.x);       // noisy image: second loop below
                                 if (two) out[o + Nx] = clip0(z.y);
                             } else if (MODE == ROW_MID) {
-                                w.x = fast_div(stage[i], clip0(z.x));
-                                if (two) w.y = fast_div(stage[P::L + i], clip0(z.y));
+                                w.x = fast_div(LEAN ? aux[o] : stage[i], clip0(z.x));
+                                if (two) w.y = fast_div(LEAN ? aux[o + Nx] : stage[P::L + i], clip0(z.y));
                             } else {  // ROW_FINAL
                                 w.x = (stage_est ? stage2[i] : out[o]) * fast_div(clip0(z.x), stage[i]);
                                 out[o] = w.x;

@@ -61,6 +61,9 @@ struct DeviceCtx {
 };
 
 // Compile-time plans of the fast path (conv_fast.cuh): 2160 = 16 * 9 * 15.
+#ifndef LSTED_ROW_LEAN_CTAS
+#define LSTED_ROW_LEAN_CTAS 5   // "lean" ROW_MID (two shared-memory buffers): CTAs per SM the registers must allow
+#endif
 #ifndef LSTED_ROW_RESIDENT_THREADS
 #define LSTED_ROW_RESIDENT_THREADS 480  // 3 row CTAs per SM: no register spills
 #endif
@@ -76,8 +79,8 @@ typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 // G: image geometry known at compile time (the 2048-wide / 107-wide-PSF headline case) or not
 typedef lsted::RowGeomFixed<2048, 53> RowGeom2048;
 typedef lsted::RowGeomFixed<2048, 0> RowGeom2048c;    // centred real OTFs: no crop offset
-template <int MODE, class P, class G = lsted::RowGeomRuntime, bool TMA = false>
-__global__ void __launch_bounds__(P::ROW_THREADS, sizeof(typename P::T) == 4 ? (LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
+template <int MODE, class P, class G = lsted::RowGeomRuntime, int TMA = 0>
+__global__ void __launch_bounds__(P::ROW_THREADS, TMA == 2 ? LSTED_ROW_LEAN_CTAS : sizeof(typename P::T) == 4 ? (LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
 row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DeviceCtx cx;
@@ -287,7 +290,7 @@ class CudaBackend {
         const char* plan2 = getenv("LSTED_ROW_PLAN2");  // A/B switch, same as option "row_plan2"
         if (plan2) row_plan2_ = atoi(plan2) != 0;
         const char* rt = getenv("LSTED_ROW_TMA");       // A/B switch: spectrum chunks by tensor-map copies
-        if (rt) row_tma_ = atoi(rt) != 0;
+        if (rt) row_tma_ = atoi(rt);   // 0 off, 1 tensor-map copies, 2 + "lean" ROW_MID
         const char* ro = getenv("LSTED_REAL_OTF");      // A/B switch: centred real OTFs (read at set_psfs)
         if (ro) real_otf_ = atoi(ro) != 0;
         const char* pf = getenv("LSTED_PREFETCH");      // A/B switch, same as option "prefetch"
@@ -505,22 +508,33 @@ class CudaBackend {
     launch_row_fast_tma(int fast_grid, const lsted::RowArgs<typename P::T>& a, int kind, size_t smem,
                         bool fixed, bool fixed_c) {
         if (!a.tmap_in || !a.tmap_out || !row_tma_) return false;
+        // "lean" ROW_MID: measurement rows read in place, two buffers, one more CTA per SM
+        if (MODE == lsted::ROW_MID && row_tma_ == 2) {
+            const size_t lean = lsted::fast_row_smem_bytes<P>(MODE, true);
+            launch_row_tma_variant<MODE, P, 2>(fast_grid, a, kind, lean, fixed, fixed_c);
+        } else {
+            launch_row_tma_variant<MODE, P, 1>(fast_grid, a, kind, smem, fixed, fixed_c);
+        }
+        return true;
+    }
+    template <int MODE, class P, int TMA>
+    void launch_row_tma_variant(int fast_grid, const lsted::RowArgs<typename P::T>& a, int kind, size_t smem,
+                                bool fixed, bool fixed_c) {
         static bool configured = false;
         if (!configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, lsted::RowGeomRuntime, true>,
+            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, lsted::RowGeomRuntime, TMA>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048, true>,
+            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048, TMA>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048c, true>,
+            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048c, TMA>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
         }
         before(kind);
-        if (fixed) row_fast_kernel<MODE, P, RowGeom2048, true><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
-        else if (fixed_c) row_fast_kernel<MODE, P, RowGeom2048c, true><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
-        else row_fast_kernel<MODE, P, lsted::RowGeomRuntime, true><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
+        if (fixed) row_fast_kernel<MODE, P, RowGeom2048, TMA><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
+        else if (fixed_c) row_fast_kernel<MODE, P, RowGeom2048c, TMA><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
+        else row_fast_kernel<MODE, P, lsted::RowGeomRuntime, TMA><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
         after();
-        return true;
     }
     template <int MODE, class P>
     typename std::enable_if<!(sizeof(typename P::T) == 4 && P::PR == 1 &&
@@ -563,7 +577,7 @@ class CudaBackend {
                g.nxb >= lsted::kTmaBoxBlocks && g.nxb <= 2 * lsted::kTmaBoxBlocks &&
                (g.nxb - lsted::kTmaBoxBlocks) % 2 == 0;   // two boxes cover the blocks, 128-byte aligned in smem
     }
-    void set_row_tma(bool on) { row_tma_ = on; }
+    void set_row_tma(int v) { row_tma_ = v; }
     template <int MODE, class P> void launch_col_fast(int grid, const lsted::ColArgs<typename P::T>& a,
                                                       int kind) {
         const size_t smem = lsted::fast_col_smem_bytes<P>();
@@ -782,7 +796,7 @@ class CudaBackend {
     std::vector<void*> p2p_opened_;
     int p2p_rank_ = 0, p2p_world_ = 1; unsigned p2p_epoch_ = 0;
     bool real_otf_ = true;
-    bool row_tma_ = true;
+    int row_tma_ = 1;   // 0 off, 1 tensor-map spectrum copies, 2 also the two-buffer ROW_MID
     bool prefetch_ = true;
     int prefetch_quarters_ = 2;   // row-kernel L2 prefetch distance in CTAs per SM (half a wave of the
                                   // 4 resident CTAs; measured 1: 0.280, 2: 0.281, 4: 0.283, 8: 0.321,

@@ -120,7 +120,7 @@ class HostBackend {
     bool row_tma_supported(const lsted::ConvGeom& g, int cplx_bytes) const {
         return use_fast_ && row_tma_ && cplx_bytes == 8 && g.Lx == Plan2160f::L && g.C == (int)Plan2160f::C;
     }
-    void set_row_tma(bool on) { row_tma_ = on; }
+    void set_row_tma(int v) { row_tma_ = v; }
     void p2p_export(void*, void*, void*, char*) { throw std::string("peer memory needs GPUs"); }
     void p2p_attach(int, int, const char*, size_t) { throw std::string("peer memory needs GPUs"); }
     bool p2p_ready(const lsted::ConvGeom&, int) const { return false; }
@@ -180,7 +180,10 @@ class HostBackend {
 #pragma omp atomic
             ++g_row_tma_launches;
         }
-        lsted::row_fast_body<MODE, P, HostCtx, lsted::RowGeomRuntime, true>(cx, b, a, smem, regs);
+        if (MODE == lsted::ROW_MID && row_tma_ == 2)
+            lsted::row_fast_body<MODE, P, HostCtx, lsted::RowGeomRuntime, 2>(cx, b, a, smem, regs);
+        else
+            lsted::row_fast_body<MODE, P, HostCtx, lsted::RowGeomRuntime, 1>(cx, b, a, smem, regs);
         return true;
     }
     template <int MODE, class P>
@@ -304,7 +307,7 @@ class HostBackend {
     bool row_dual_ = false;
     bool row_plan2_ = false;
     bool real_otf_ = true;
-    bool row_tma_ = true;
+    int row_tma_ = 1;
 };
 
 #define LSTED_BACKEND HostBackend

@@ -365,7 +365,7 @@ def test_row_kernels_with_staged_spectrum_chunks(lib, shape):
     obj = rng.random((1,) + shape) + 0.05
     meas = [rng.poisson(80.0, (1,) + shape).astype(np.float64) + 1e-9 for _ in range(3)]
     est, launches = {}, {}
-    for tma in (1, 0):
+    for tma in (2, 1, 0):   # 2: also the two-buffer ROW_MID (measurement rows read in place)
         before = lib.cdll.emul_row_tma_launches()
         h = _lib.DeconvHandle(lib, psfs, shape, precision=32)
         h.set_option('row_tma', tma)
@@ -376,10 +376,11 @@ def test_row_kernels_with_staged_spectrum_chunks(lib, shape):
         est[tma] = h.get(_lib.ESTIMATE)
         launches[tma] = lib.cdll.emul_row_tma_launches() - before
         h.close()
-    assert launches == {1: 6, 0: 0}
+    assert launches == {2: 6, 1: 6, 0: 0}
     o = orc.Deconvolver([p[None] for p in psfs])
     o.noisy_measurement = meas
     for _ in range(3):
         o.iterate()
     assert np.array_equal(est[1], est[0])      # same arithmetic, only the data path differs
+    assert np.array_equal(est[2], est[0])
     assert rel_l2(est[1], o.estimate) < 1e-4

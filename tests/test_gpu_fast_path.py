@@ -63,7 +63,7 @@ def test_tensor_map_row_staging_is_bit_identical(shape, K):
     psfs = rng.random((K, 3, 21))
     x = rng.random((1,) + shape) + 0.1
     est = {}
-    for tma in (0, 1):
+    for tma in (0, 1, 2):   # 2: also the two-buffer ROW_MID (measurement rows read in place)
         h = _lib.DeconvHandle(lib, psfs, shape, precision=32)
         h.set_option('row_tma', tma)
         h.create_data(x, 1e6 * x.size, 1)
@@ -72,3 +72,4 @@ def test_tensor_map_row_staging_is_bit_identical(shape, K):
         h.close()
     assert np.isfinite(est[1]).all() and est[1].min() > 0
     assert np.array_equal(est[0], est[1])
+    assert np.array_equal(est[0], est[2])
