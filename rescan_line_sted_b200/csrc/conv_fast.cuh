@@ -19,6 +19,9 @@
 // Bodies are written as per-thread phases separated by CTA barriers
 // (`cx.phase(regs, f)`), so tests/host_emul can replay them thread by thread.
 #pragma once
+#ifndef LSTED_LEAN_PROBE
+#define LSTED_LEAN_PROBE 0   // timing probe only: 1 = the lean ROW_MID divides a constant (no measurement loads)
+#endif
 #include <type_traits>
 #include "conv_bodies.cuh"
 #include "fft_static.cuh"
@@ -765,8 +768,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                                 out[o] = clip0(z.x);       // noisy image: second loop below
                                 if (two) out[o + Nx] = clip0(z.y);
                             } else if (MODE == ROW_MID) {
-                                w.x = fast_div(LEAN ? aux[o] : stage[i], clip0(z.x));
-                                if (two) w.y = fast_div(LEAN ? aux[o + Nx] : stage[P::L + i], clip0(z.y));
+                                w.x = fast_div(LEAN ? (LSTED_LEAN_PROBE ? (T)1 : aux[o]) : stage[i], clip0(z.x));
+                                if (two) w.y = fast_div(LEAN ? (LSTED_LEAN_PROBE ? (T)1 : aux[o + Nx]) : stage[P::L + i], clip0(z.y));
                             } else {  // ROW_FINAL
                                 w.x = (stage_est ? stage2[i] : out[o]) * fast_div(clip0(z.x), stage[i]);
                                 out[o] = w.x;
