@@ -19,9 +19,6 @@
 // Bodies are written as per-thread phases separated by CTA barriers
 // (`cx.phase(regs, f)`), so tests/host_emul can replay them thread by thread.
 #pragma once
-#ifndef LSTED_LEAN_PROBE
-#define LSTED_LEAN_PROBE 0   // timing probe only: 1 = the lean ROW_MID divides a constant (no measurement loads)
-#endif
 #include <type_traits>
 #include "conv_bodies.cuh"
 #include "fft_static.cuh"
@@ -543,9 +540,9 @@ template <int NX_, int SX_> struct RowGeomFixed { enum { NX = NX_, SX = SX_ }; }
 
 // TMA: the spectrum chunks of the pair come and go through tensor-map bulk copies staged in
 // the second exchange buffer (free while they are needed) instead of per-thread LDG / STG.
-// TMA == 2 (ROW_MID only, "lean"): additionally no staging buffer for the measurement rows
-// (they are read in place, from L2 thanks to the prefetch of an earlier CTA): two buffers
-// instead of three, so five CTAs per SM instead of four.
+// TMA == 2 (ROW_MID only, "lean"): additionally no third buffer for the measurement rows (they
+// are staged in the first exchange buffer between the two transforms): two buffers instead of
+// three, so five CTAs per SM instead of four.  Needs 16-byte aligned rows (checked at launch).
 template <int MODE, class P, class Ctx, class G = RowGeomRuntime, int TMA = 0>
 LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                             cplx<typename P::T>* smem, RowRegs<P>* regs, G = G()) {
@@ -742,11 +739,33 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         T* out = (MODE == ROW_FINAL) ? a.real_out : a.real_out + real_off;
         T* out2 = (MODE == ROW_INV_SIM) ? a.real_out2 + real_off : 0;
         const T* aux = (MODE == ROW_MID) ? a.aux + real_off : a.aux;
+        if (LEAN) {
+            // two-buffer variant: the first exchange buffer is idle from here until the forward
+            // transform, so the measurement rows are staged in IT (bulk copy, own mbarrier in its
+            // last 16 bytes) while inverse pass C runs; the forward transform then starts in the
+            // second buffer (one more barrier, one shared-memory buffer less)
+            cx.phase(regs, [&](int tid, RowRegs<P>& r) {
+                LSTED_ROW_IDS
+                if (t == 0 && pair < Py) {
+                    mbar_t* const mb = (mbar_t*)((char*)s0 + TMA_MB_OFF);
+                    const T* m0 = a.aux + real_off + (size_t)y * Nx;
+                    const int nrow = two ? 2 : 1;
+                    mbar_init(mb);
+                    bulk_expect(mb, row_bytes * nrow);
+                    for (int rr = 0; rr < nrow; ++rr) bulk_copy((T*)s0 + rr * P::L, m0 + (size_t)rr * Nx, row_bytes, mb);
+                }
+                if (!live) return;
+                I::pass_c(r.v, t, s1, r.twi);
+            });
+        }
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             if (MODE == ROW_INV_SIM && t == 0) *(int*)stage = 0;   // noise queue (below)
             if (!live) return;
-            I::pass_c(r.v, t, s1, r.twi);
+            if (!LEAN) I::pass_c(r.v, t, s1, r.twi);
+            const T* const rows_s = LEAN ? (const T*)s0 : stage;   // staged measurement rows (ROW_MID)
+            (void)rows_s;
+            if (LEAN) mbar_wait((mbar_t*)((char*)s0 + TMA_MB_OFF), 0u);
             if ((MODE == ROW_MID || MODE == ROW_FINAL) && !LEAN && bulk_rows)
                 mbar_wait((mbar_t*)(stage + 2 * P::L), 0u);    // the staged rows have landed
             LSTED_UNROLL
@@ -768,8 +787,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                                 out[o] = clip0(z.x);       // noisy image: second loop below
                                 if (two) out[o + Nx] = clip0(z.y);
                             } else if (MODE == ROW_MID) {
-                                w.x = fast_div(LEAN ? (LSTED_LEAN_PROBE ? (T)1 : aux[o]) : stage[i], clip0(z.x));
-                                if (two) w.y = fast_div(LEAN ? (LSTED_LEAN_PROBE ? (T)1 : aux[o + Nx]) : stage[P::L + i], clip0(z.y));
+                                w.x = fast_div(rows_s[i], clip0(z.x));
+                                if (two) w.y = fast_div(rows_s[P::L + i], clip0(z.y));
                             } else {  // ROW_FINAL
                                 w.x = (stage_est ? stage2[i] : out[o]) * fast_div(clip0(z.x), stage[i]);
                                 out[o] = w.x;
@@ -784,7 +803,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                     }
                 }
             }
-            if (MODE == ROW_MID || MODE == ROW_FINAL) F::pass_a(r.v, t, s0);
+            if (MODE == ROW_MID || MODE == ROW_FINAL) F::pass_a(r.v, t, LEAN ? s1 : s0);
         });
         if (MODE == ROW_INV_SIM) {
             // Shot noise in two dense steps.  (1) every pixel this thread just wrote gets the
@@ -843,30 +862,35 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         }
         if (MODE == ROW_INV_STORE || MODE == ROW_INV_SIM) return;
     }
+    // (two-buffer ROW_MID: the forward transform runs with the two buffers swapped)
+#define LSTED_ROW_FWD_BUFS cplx<T>* const fa = LEAN ? s1 : s0; cplx<T>* const fb = LEAN ? s0 : s1; (void)fa; (void)fb;
     cx.phase(regs, [&](int tid, RowRegs<P>& r) {
         LSTED_ROW_IDS
+        LSTED_ROW_FWD_BUFS
         if (!live) return;
-        F::load_b(r.v, t, s0, r.twf);
-        F::pass_b(r.v, t, s1);
+        F::load_b(r.v, t, fa, r.twf);
+        F::pass_b(r.v, t, fb);
     });
     // Forward pass C; the upper half of the spectrum goes to the mirror thread.
     cx.phase(regs, [&](int tid, RowRegs<P>& r) {
         LSTED_ROW_IDS
+        LSTED_ROW_FWD_BUFS
         if (!live) return;
-        F::pass_c(r.v, t, s1, r.twf);
+        F::pass_c(r.v, t, fb, r.twf);
         LSTED_UNROLL
-        for (int q = P::QH; q < P::RCF; ++q) s0[(q - P::QH) * P::PX + t] = r.v[q];
+        for (int q = P::QH; q < P::RCF; ++q) fa[(q - P::QH) * P::PX + t] = r.v[q];
     });
     // Hermitian split of the lower half, crop-offset phase ramp, XB store:
     // bins k = t + q*NC with mirror L - k = (NC - t) + (RC - 1 - q)*NC.
     cplx<T>* dst = a.spec_out + spec_off;
     auto split_and_store = [&](int tid, RowRegs<P>& r) {
         LSTED_ROW_IDS
+        LSTED_ROW_FWD_BUFS
         if (!live) return;
         const int tp = t == 0 ? 0 : P::NC - t;         // mirror thread
         const int qoff = t == 0 ? 1 : 0;               // thread 0 mirrors onto itself, one q up
         // TMA: the pair's chunks are assembled in s1 (bin k at s1[2k], s1[2k+1]) and leave in bulk
-        cplx<T>* pk = TMA ? s1 + 2 * t : dst + ((size_t)(t / C) * Nye + y) * C + 2 * (t % C);
+        cplx<T>* pk = TMA ? fb + 2 * t : dst + ((size_t)(t / C) * Nye + y) * C + 2 * (t % C);
         const size_t xb_stride = TMA ? (size_t)2 * C : (size_t)Nye * C;   // elements per column block
         // phase ramp exp(+2 pi i k shift / L) at bins k = t + q*NC: ramp0 * d^q with the
         // thread-independent step d (powers by binary splitting, no table gathers)
@@ -885,7 +909,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             cplx<T> z2;
             const int qm = P::RCF - 1 - q + qoff;      // q of the mirror bin in thread tp
             if (t == 0 && q == 0) z2 = z1;
-            else z2 = s0[(qm - P::QH) * P::PX + tp];
+            else z2 = fa[(qm - P::QH) * P::PX + tp];
             cplx<T> oa = mk<T>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y - z2.y));  // (z1 + conj z2)/2
             cplx<T> ob = mk<T>((T)0.5 * (z1.y + z2.y), (T)0.5 * (z2.x - z1.x));  // (z1 - conj z2)/(2i)
             if (shift) {
@@ -904,17 +928,19 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         cx.phase(regs, split_and_store);
         cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
+            LSTED_ROW_FWD_BUFS
             (void)r;
             if (t != 0 || pair >= Py) return;
             for (int h = 0; h < 2; ++h) {
                 const int xb0 = h * (g.nxb - kTmaBoxBlocks);
-                tma_store_chunks<T>((const char*)s1 + (size_t)xb0 * CHUNK * sizeof(cplx<T>), a.tmap_out, dst, img, y,
+                tma_store_chunks<T>((const char*)fb + (size_t)xb0 * CHUNK * sizeof(cplx<T>), a.tmap_out, dst, img, y,
                                     xb0, g.nxb, Nye, C, CHUNK);
             }
             tma_store_finish();
         });
     }
 #undef LSTED_ROW_IDS
+#undef LSTED_ROW_FWD_BUFS
 }
 
 

@@ -62,7 +62,7 @@ struct DeviceCtx {
 
 // Compile-time plans of the fast path (conv_fast.cuh): 2160 = 16 * 9 * 15.
 #ifndef LSTED_ROW_LEAN_CTAS
-#define LSTED_ROW_LEAN_CTAS 5   // "lean" ROW_MID (two shared-memory buffers): CTAs per SM the registers must allow
+#define LSTED_ROW_LEAN_CTAS 6   // "lean" ROW_MID (two shared-memory buffers, 35 KB): CTAs per SM -> 64 registers, no spills
 #endif
 #ifndef LSTED_ROW_RESIDENT_THREADS
 #define LSTED_ROW_RESIDENT_THREADS 480  // 3 row CTAs per SM: no register spills
@@ -508,8 +508,10 @@ class CudaBackend {
     launch_row_fast_tma(int fast_grid, const lsted::RowArgs<typename P::T>& a, int kind, size_t smem,
                         bool fixed, bool fixed_c) {
         if (!a.tmap_in || !a.tmap_out || !row_tma_) return false;
-        // "lean" ROW_MID: measurement rows read in place, two buffers, one more CTA per SM
-        if (MODE == lsted::ROW_MID && row_tma_ == 2) {
+        // "lean" ROW_MID: measurement rows staged in the first exchange buffer, two buffers, one
+        // more CTA per SM (bulk copies: the rows must be 16-byte multiples, 16-byte aligned)
+        if (MODE == lsted::ROW_MID && row_tma_ == 2 && (a.g.Nx * sizeof(typename P::T)) % 16 == 0 &&
+            ((size_t)a.aux & 15) == 0) {
             const size_t lean = lsted::fast_row_smem_bytes<P>(MODE, true);
             launch_row_tma_variant<MODE, P, 2>(fast_grid, a, kind, lean, fixed, fixed_c);
         } else {
@@ -796,7 +798,7 @@ class CudaBackend {
     std::vector<void*> p2p_opened_;
     int p2p_rank_ = 0, p2p_world_ = 1; unsigned p2p_epoch_ = 0;
     bool real_otf_ = true;
-    int row_tma_ = 1;   // 0 off, 1 tensor-map spectrum copies, 2 also the two-buffer ROW_MID
+    int row_tma_ = 2;   // 0 off, 1 tensor-map spectrum copies, 2 also the two-buffer ROW_MID (6 CTAs/SM)
     bool prefetch_ = true;
     int prefetch_quarters_ = 2;   // row-kernel L2 prefetch distance in CTAs per SM (half a wave of the
                                   // 4 resident CTAs; measured 1: 0.280, 2: 0.281, 4: 0.283, 8: 0.321,
