@@ -106,8 +106,8 @@ int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info);
  *          "forget_normalization" (drop the cached H_t_normalization, :590),
  *          "fast_path" (0|1, default 1: use the compile-time-planned kernels when
  *          the transform length has one; 0 forces the generic mixed-radix kernels),
- *          A/B switches of kernel variants with identical results: "row_tma" (0|1|2, default 1:
- *          row spectra moved by tensor-map bulk copies), "real_otf", "row_dual", "row_plan2",
+ *          A/B switches of kernel variants with identical results: "row_tma" (0|1|2, default 2:
+ *          row spectra moved by tensor-map bulk copies; 2 = also the two-buffer ROW_MID), "real_otf", "row_dual", "row_plan2",
  *          "prefetch" */
 int lsted_deconv_set_option(lsted_deconv* h, const char* name, double value);
 /* create_data_from_object (:496-512).  rescale != 0 applies total_brightness.
