@@ -90,7 +90,7 @@ template <class P> LSTED_HD size_t fast_col_smem_bytes() {
            (LSTED_COL_STAGE_OTF ? 16 : 0);
 }
 template <class P> LSTED_HD size_t fast_row_smem_bytes(int mode, bool lean = false) {
-    const int bufs = lean ? 2 : mode == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
+    const int bufs = lean ? (mode == ROW_FINAL ? 3 : 2) : mode == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
     return sizeof(cplx<typename P::T>) * (size_t)bufs * P::PR * P::LSM_ROW;
 }
 
@@ -540,9 +540,10 @@ template <int NX_, int SX_> struct RowGeomFixed { enum { NX = NX_, SX = SX_ }; }
 
 // TMA: the spectrum chunks of the pair come and go through tensor-map bulk copies staged in
 // the second exchange buffer (free while they are needed) instead of per-thread LDG / STG.
-// TMA == 2 (ROW_MID only, "lean"): additionally no third buffer for the measurement rows (they
-// are staged in the first exchange buffer between the two transforms): two buffers instead of
-// three, so five CTAs per SM instead of four.  Needs 16-byte aligned rows (checked at launch).
+// TMA == 2 ("lean"): additionally no buffer of their own for the measurement (ROW_MID) /
+// normalisation (ROW_FINAL) rows: they are staged in the first exchange buffer between the two
+// transforms -- two buffers instead of three (ROW_MID, 6 CTAs/SM), three instead of four
+// (ROW_FINAL, 4 CTAs/SM).  Needs 16-byte aligned rows (checked at launch).
 template <int MODE, class P, class Ctx, class G = RowGeomRuntime, int TMA = 0>
 LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                             cplx<typename P::T>* smem, RowRegs<P>* regs, G = G()) {
@@ -564,9 +565,9 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     const int shift = (MODE == ROW_FWD) ? 0 : (G::NX ? (int)G::SX : g.sx);
     const size_t xb_stride = (size_t)Nye * C;  // elements between consecutive column blocks
     // XB2: the pair (row y, row y+1) of column c sits at ((xb*Nye + y)*C + 2c) + {0, 1}
-    const bool LEAN = TMA == 2 && MODE == ROW_MID;
-    const int NBUF = LEAN ? 2 : MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
-    const bool stage_est = MODE == ROW_FINAL && P::ROW_FINAL_BUFS == 4;
+    const bool LEAN = TMA == 2 && (MODE == ROW_MID || MODE == ROW_FINAL);
+    const int NBUF = LEAN ? (MODE == ROW_MID ? 2 : 3) : MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
+    const bool stage_est = MODE == ROW_FINAL && P::ROW_FINAL_BUFS == 4 && !LEAN;
     enum { CHUNK = 2 * P::PR * P::C,                                  // complex numbers per chunk
            TMA_BYTES = 2 * kTmaBoxBlocks * CHUNK * (int)sizeof(cplx<T>) };  // two boxes cover nxb blocks
     enum { TMA_MB_OFF = P::LSM_ROW * (int)sizeof(cplx<T>) - 16 };   // its mbarrier: the buffer's last 16 bytes
@@ -667,6 +668,18 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             mbar_t* const mb_spec = (mbar_t*)((char*)s1 + TMA_MB_OFF);
+            if (MODE == ROW_FINAL && LEAN && pair < Py) {
+                // lean ROW_FINAL: only the estimate rows go to the third buffer now; the
+                // normalisation rows follow into the first exchange buffer (below)
+                if (t == 0) {
+                    mbar_t* const mb = (mbar_t*)(stage + 2 * P::L);
+                    const T* e0 = a.real_out + (size_t)y * Nx;
+                    const int nrow = two ? 2 : 1;
+                    mbar_init(mb);
+                    bulk_expect(mb, row_bytes * nrow);
+                    for (int rr = 0; rr < nrow; ++rr) bulk_copy(stage + rr * P::L, e0 + (size_t)rr * Nx, row_bytes, mb);
+                }
+            }
             if ((MODE == ROW_MID || MODE == ROW_FINAL) && !LEAN && pair < Py) {
                 // measurement (MID) or normalisation + estimate (FINAL) rows y, y+1 -> shared
                 // memory, asynchronously (used after the inverse transform, two barriers from here)
@@ -748,7 +761,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 LSTED_ROW_IDS
                 if (t == 0 && pair < Py) {
                     mbar_t* const mb = (mbar_t*)((char*)s0 + TMA_MB_OFF);
-                    const T* m0 = a.aux + real_off + (size_t)y * Nx;
+                    const T* m0 = (MODE == ROW_MID ? a.aux + real_off : a.aux) + (size_t)y * Nx;
                     const int nrow = two ? 2 : 1;
                     mbar_init(mb);
                     bulk_expect(mb, row_bytes * nrow);
@@ -763,9 +776,10 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             if (MODE == ROW_INV_SIM && t == 0) *(int*)stage = 0;   // noise queue (below)
             if (!live) return;
             if (!LEAN) I::pass_c(r.v, t, s1, r.twi);
-            const T* const rows_s = LEAN ? (const T*)s0 : stage;   // staged measurement rows (ROW_MID)
+            const T* const rows_s = LEAN ? (const T*)s0 : stage;   // staged measurement / normalisation rows
             (void)rows_s;
             if (LEAN) mbar_wait((mbar_t*)((char*)s0 + TMA_MB_OFF), 0u);
+            if (LEAN && MODE == ROW_FINAL) mbar_wait((mbar_t*)(stage + 2 * P::L), 0u);   // estimate rows
             if ((MODE == ROW_MID || MODE == ROW_FINAL) && !LEAN && bulk_rows)
                 mbar_wait((mbar_t*)(stage + 2 * P::L), 0u);    // the staged rows have landed
             LSTED_UNROLL
@@ -790,11 +804,11 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                                 w.x = fast_div(rows_s[i], clip0(z.x));
                                 if (two) w.y = fast_div(rows_s[P::L + i], clip0(z.y));
                             } else {  // ROW_FINAL
-                                w.x = (stage_est ? stage2[i] : out[o]) * fast_div(clip0(z.x), stage[i]);
+                                w.x = (LEAN ? stage[i] : stage_est ? stage2[i] : out[o]) * fast_div(clip0(z.x), rows_s[i]);
                                 out[o] = w.x;
                                 if (two) {
-                                    w.y = (stage_est ? stage2[P::L + i] : out[o + Nx]) *
-                                          fast_div(clip0(z.y), stage[P::L + i]);
+                                    w.y = (LEAN ? stage[P::L + i] : stage_est ? stage2[P::L + i] : out[o + Nx]) *
+                                          fast_div(clip0(z.y), rows_s[P::L + i]);
                                     out[o + Nx] = w.y;
                                 }
                             }

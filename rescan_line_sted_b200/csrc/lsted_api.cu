@@ -80,7 +80,7 @@ typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 typedef lsted::RowGeomFixed<2048, 53> RowGeom2048;
 typedef lsted::RowGeomFixed<2048, 0> RowGeom2048c;    // centred real OTFs: no crop offset
 template <int MODE, class P, class G = lsted::RowGeomRuntime, int TMA = 0>
-__global__ void __launch_bounds__(P::ROW_THREADS, TMA == 2 ? LSTED_ROW_LEAN_CTAS : sizeof(typename P::T) == 4 ? (LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
+__global__ void __launch_bounds__(P::ROW_THREADS, TMA == 2 ? (MODE == lsted::ROW_MID ? LSTED_ROW_LEAN_CTAS : 4) : sizeof(typename P::T) == 4 ? (LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
 row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DeviceCtx cx;
@@ -510,8 +510,8 @@ class CudaBackend {
         if (!a.tmap_in || !a.tmap_out || !row_tma_) return false;
         // "lean" ROW_MID: measurement rows staged in the first exchange buffer, two buffers, one
         // more CTA per SM (bulk copies: the rows must be 16-byte multiples, 16-byte aligned)
-        if (MODE == lsted::ROW_MID && row_tma_ == 2 && (a.g.Nx * sizeof(typename P::T)) % 16 == 0 &&
-            ((size_t)a.aux & 15) == 0) {
+        if (row_tma_ == 2 && (a.g.Nx * sizeof(typename P::T)) % 16 == 0 && ((size_t)a.aux & 15) == 0 &&
+            (MODE == lsted::ROW_MID || ((size_t)a.real_out & 15) == 0)) {
             const size_t lean = lsted::fast_row_smem_bytes<P>(MODE, true);
             launch_row_tma_variant<MODE, P, 2>(fast_grid, a, kind, lean, fixed, fixed_c);
         } else {

@@ -180,8 +180,8 @@ class HostBackend {
 #pragma omp atomic
             ++g_row_tma_launches;
         }
-        if (MODE == lsted::ROW_MID && row_tma_ == 2 && (a.g.Nx * sizeof(typename P::T)) % 16 == 0 &&
-            ((size_t)a.aux & 15) == 0)
+        if (row_tma_ == 2 && (a.g.Nx * sizeof(typename P::T)) % 16 == 0 && ((size_t)a.aux & 15) == 0 &&
+            (MODE == lsted::ROW_MID || ((size_t)a.real_out & 15) == 0))
             lsted::row_fast_body<MODE, P, HostCtx, lsted::RowGeomRuntime, 2>(cx, b, a, smem, regs);
         else
             lsted::row_fast_body<MODE, P, HostCtx, lsted::RowGeomRuntime, 1>(cx, b, a, smem, regs);
