@@ -288,6 +288,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
                 rf.nimg = 1; rf.spec_in = spec1; rf.spec_out = spec1;
                 rf.real_out = estimate; rf.aux = norm;
                 rf.tmap_in = rf.tmap_out = tmap_spec1;
+                rf.prefetch_ahead = bk.row_final_prefetch_distance();
                 bk.template launch_row<ROW_FINAL, T>(row_blocks(g), rf);
             } else {
                 ht_from_specK(scratch);

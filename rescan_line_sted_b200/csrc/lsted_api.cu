@@ -296,7 +296,7 @@ class CudaBackend {
         const char* pf = getenv("LSTED_PREFETCH");      // A/B switch, same as option "prefetch"
         if (pf) prefetch_ = atoi(pf) != 0;
         const char* pq = getenv("LSTED_PREFETCH_CTAS_PER_SM");   // prefetch distance in CTAs per SM
-        if (pq && atoi(pq) > 0) prefetch_quarters_ = atoi(pq);
+        if (pq && atoi(pq) > 0) { prefetch_quarters_ = atoi(pq); prefetch_final_quarters_ = 0; }
     }
     ~CudaBackend() {
         cudaSetDevice(device_);
@@ -445,6 +445,11 @@ class CudaBackend {
     void set_row_plan2(bool on) { row_plan2_ = on; }
     // row CTAs resident at once (4 per SM): prefetch for the CTA one wave ahead
     int row_prefetch_distance() const { return prefetch_ ? (num_sms_ * prefetch_quarters_) : 0; }
+    // ROW_FINAL has few CTAs (one image): its prefetch must reach past everything resident
+    // (4 CTAs per SM) to be of any use -- measured best at 6 CTAs per SM ahead
+    int row_final_prefetch_distance() const {
+        return prefetch_ ? num_sms_ * (prefetch_final_quarters_ > 0 ? prefetch_final_quarters_ : prefetch_quarters_) : 0;
+    }
     void set_prefetch(bool on) { prefetch_ = on; }
     void profile_reset() {
         profile_drain();
@@ -800,9 +805,10 @@ class CudaBackend {
     bool real_otf_ = true;
     int row_tma_ = 2;   // 0 off, 1 tensor-map spectrum copies, 2 also the two-buffer ROW_MID (6 CTAs/SM)
     bool prefetch_ = true;
-    int prefetch_quarters_ = 2;   // row-kernel L2 prefetch distance in CTAs per SM (half a wave of the
-                                  // 4 resident CTAs; measured 1: 0.280, 2: 0.281, 4: 0.283, 8: 0.321,
-                                  // off: 0.330 ms for row_mid)
+    int prefetch_quarters_ = 1;   // row-kernel L2 prefetch distance in CTAs per SM.  With per-thread
+                                  // loads it was worth 14 % of row_mid; with the TMA-staged kernels
+                                  // it hardly matters for row_mid (1: 0.196, 2: 0.197, 4: 0.199, 8: 0.213 ms)
+    int prefetch_final_quarters_ = 6;   // ROW_FINAL (1024 CTAs, 592 resident): 2: 0.0271, 6: 0.0234 ms
     // two-pass 48 x 45 row kernels (fp32): 35 % fewer warp instructions and half the shared-memory
     // wavefronts, but 0.334 ms vs 0.283 ms for ROW_MID: 4792 straight-line instructions run by
     // 9 warps per SM stall on instruction fetch (ncu: no_inst 32 %).  Kept behind this switch.

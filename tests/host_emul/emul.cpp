@@ -71,6 +71,7 @@ class HostBackend {
     void set_row_dual(bool on) { row_dual_ = on; }
     void set_row_plan2(bool on) { row_plan2_ = on; }
     int row_prefetch_distance() const { return 3; }
+    int row_final_prefetch_distance() const { return 5; }
     void set_prefetch(bool) {}
     static int fast_cols(int L, int cplx_bytes) {
         if (L == Plan2160f::L) return cplx_bytes == 8 ? (int)Plan2160f::C : (int)Plan2160d::C;
