@@ -751,7 +751,6 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         // forward pass A of the result, all in one phase.
         T* out = (MODE == ROW_FINAL) ? a.real_out : a.real_out + real_off;
         T* out2 = (MODE == ROW_INV_SIM) ? a.real_out2 + real_off : 0;
-        const T* aux = (MODE == ROW_MID) ? a.aux + real_off : a.aux;
         if (LEAN) {
             // two-buffer variant: the first exchange buffer is idle from here until the forward
             // transform, so the measurement rows are staged in IT (bulk copy, own mbarrier in its
