@@ -13,7 +13,17 @@ orientations of the figure-2 '2p0x_lr' rescan PSF (107^2), fp32.
 With N > 1 (torchrun) every rank simulates and deconvolves its own frames
 (independent frames = the reference's own unit of parallel work: figure 2
 runs 24 deconvolvers x 4 images); no data-path collective, weak scaling.
+The same line then carries an `orientation_sharded` record: ONE frame with its
+K orientations split over the N GPUs (strong scaling, the per-iteration sum
+fused into the column kernel over NVLink peer memory), its speed-up over the
+rank-local unsharded frame and the rel-L2 between the two estimates.
 Prints ONE JSON line on rank 0.
+
+`e2e` goes through the reference-facing API: line_sted_tools.Deconvolver --
+create_data_from_object(host object) + 64 x iterate() + read of `.estimate`.
+The reference arm runs the UNMODIFIED reference module from baseline/_ref/
+(a git-ignored copy made by __graft_entry__.build(); `kind: "reference"`),
+or the oracle port when that copy is absent (`kind: "port"`).
 """
 import argparse
 import json
@@ -45,6 +55,7 @@ def parse_args():
     ap.add_argument('--iterations', type=int, default=64)
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp64'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-fp64', action='store_true', help='skip the fp64 companion figure')
     ap.add_argument('--shard', default='frames', choices=['frames', 'orientations'],
                     help='N>1: independent frames per GPU (weak scaling, no collective) or the '
                          'K orientations of every frame split over the GPUs (strong scaling, one '
@@ -155,74 +166,123 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# CPU reference arm / cpu_baseline (the only place bench.py runs oracle/)
+# CPU reference arm / cpu_baseline (the only place bench.py runs oracle/ or baseline/_ref)
 # ---------------------------------------------------------------------------
-def cpu_frame_seconds(obj, psfs, n_iter, workers, timed_iterations):
-    """Time the oracle port of the reference Deconvolver on a bounded sample:
-    one forward model (+Poisson), H_t_normalization, `timed_iterations` RL
-    iterations; frame(n_iter) = forward + normalisation + n_iter * mean."""
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def load_reference_module():
+    """The unmodified reference `line_sted_tools` from baseline/_ref (None when absent).
+    matplotlib is not installed in the image; the module imports it at the top and never
+    uses it, so an empty stand-in module goes into sys.modules (no source change)."""
+    path = os.path.join(REF_DIR, 'line_sted_tools.py')
+    if not os.path.isfile(path):
+        return None
+    import importlib.util
+    import types
+    import warnings
+    for name in ('matplotlib', 'matplotlib.pyplot'):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except ImportError:
+                sys.modules[name] = types.ModuleType(name)
+    sys.path.insert(0, REF_DIR)          # its own `import np_tif`
+    try:
+        spec = importlib.util.spec_from_file_location('reference_line_sted_tools', path)
+        mod = importlib.util.module_from_spec(spec)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(REF_DIR)
+    return mod
+
+
+def host_cores():
+    """All the cores of the box, also under torchrun (which may narrow the affinity)."""
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
+def reference_psfs(ref, K):
+    """The benchmark PSFs by the reference's own psf_report (+ the caller's rotate)."""
+    if ref is None:
+        from oracle import line_sted_oracle as orc
+        return orc.benchmark_psfs(K)
+    base = ref.psf_report('line', verbose=False, **FIG2_2P0X_LR)['psfs']['rescan_sted']
+    return orientation_psfs(base, K)
+
+
+def cpu_reference_frame(args, obj, psfs, ref, workers, warmup, steps):
+    """Times the reference Deconvolver exactly as figure 2 drives it
+    (line_sted_figure_2.py:40-56): create_data_from_object, then iterate() calls -- the first
+    one also builds the estimate and H_t_normalization (ref:521-522, :589-593) -- on the
+    full-size workload with scipy.fft workers = all cores (a context manager around the
+    unmodified code).  frame(n) = forward + first iterate() + (n-1) x mean later iterate()."""
+    import tempfile
+    import warnings
     import scipy.fft
-    from oracle import line_sted_oracle as orc
     N = obj.shape[-1]
-    with scipy.fft.set_workers(workers):
-        d = orc.Deconvolver(psfs, engine='scipy')
+    if ref is not None:
+        make = lambda: ref.Deconvolver(psfs, output_prefix=tempfile.mkdtemp() + os.sep, verbose=False)
+        kind = 'reference'
+    else:
+        from oracle import line_sted_oracle as orc
+        make = lambda: orc.Deconvolver(psfs, engine='scipy')
+        kind = 'port'
+    with scipy.fft.set_workers(workers), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        d = make()
         t0 = time.perf_counter()
         d.create_data_from_object(obj, total_brightness=total_brightness(N), random_seed=0)
         t_forward = time.perf_counter() - t0
         t0 = time.perf_counter()
-        d.H_t(d.noisy_measurement)          # builds H_t_normalization (ref:521-522)
-        t_norm = (time.perf_counter() - t0) / 2.0  # two H_t passes inside
-        d.estimate = np.ones_like(d.noisy_measurement[0])
-        d.num_iterations = 1
+        d.iterate()
+        t_first = time.perf_counter() - t0
+        for _ in range(warmup):
+            d.iterate()
         its = []
-        for _ in range(timed_iterations):
+        for _ in range(steps):
             t0 = time.perf_counter()
             d.iterate()
             its.append(time.perf_counter() - t0)
     t_iter = float(np.mean(its))
-    return {'forward_s': t_forward, 'normalization_s': t_norm, 'iteration_s': t_iter,
-            'frame_s': t_forward + t_norm + n_iter * t_iter}
+    n = args.iterations
+    frame_s = t_forward + t_first + max(0, n - 1) * t_iter
+    sample = ('%s Deconvolver at full size (%d^2, K=%d, float64), scipy.fft workers=%d: '
+              'create_data_from_object %.2f s, first iterate() (incl. H_t_normalization) %.2f s, '
+              '%d timed iterate() calls %.3f s each; frame(%d) = forward + first + %d x iterate '
+              '(EXTRAPOLATED from the timed calls, %.0f s)'
+              % ('unmodified reference' if ref is not None else 'oracle port of the reference',
+                 N, len(psfs), workers, t_forward, t_first, steps, t_iter, n, n - 1, frame_s))
+    return {'kind': kind, 'frame_s': frame_s, 'forward_s': t_forward, 'first_iterate_s': t_first,
+            'iteration_s': t_iter, 'sample': sample, 'cores': workers}
 
 
-def run_reference_arm(args, psfs, obj):
+def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
-        return
-    import scipy.fft  # noqa: F401
-    from oracle import line_sted_oracle as orc
-    import scipy.fft as sfft
-    workers = os.cpu_count() or 1
+        return                      # one CPU process: the other ranks exit without work
+    workers = host_cores()
+    ref = load_reference_module()
     N, K = args.size, args.orientations
-    with sfft.set_workers(workers):
-        d = orc.Deconvolver(psfs, engine='scipy')
-        t0 = time.perf_counter()
-        d.create_data_from_object(obj, total_brightness=total_brightness(N), random_seed=0)
-        t_forward = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        d.H_t_normalization = d.H_t([np.ones(obj.shape)] * K, normalize=False)
-        t_norm = time.perf_counter() - t0
-        d.estimate = np.ones(obj.shape)
-        d.num_iterations = 1
-        for _ in range(args.warmup):
-            d.iterate()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            d.iterate()
-        t_iter = (time.perf_counter() - t0) / max(1, args.steps)
-    frame_s = t_forward + t_norm + args.iterations * t_iter
-    value = 1.0 / frame_s
-    sample = ('each step = 1 RL iteration (2K fftconvolve) at full size; forward+Poisson '
-              '(%.2f s) and H_t_normalization (%.2f s) timed once; frame(%d) = forward + '
-              'norm + %d x mean iteration (%.3f s)'
-              % (t_forward, t_norm, args.iterations, args.iterations, t_iter))
+    psfs = reference_psfs(ref, K)
+    cpu = cpu_reference_frame(args, synthetic_object(N), psfs, ref, workers,
+                              max(0, args.warmup - 1), max(1, args.steps))
+    value = 1.0 / cpu['frame_s']
     print(json.dumps({
         'impl': 'reference', 'metric': 'frames_per_sec', 'value': value, 'unit': 'frames/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': frame_s * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': cpu['frame_s'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args),
-        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': workers, 'kind': 'port',
-                         'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cpu['cores'],
+                         'kind': cpu['kind'], 'sample': cpu['sample']},
+        'note': 'one CPU process on rank 0 whatever --gpus says: compare it with the N=1 line',
         'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0}}))
 
@@ -244,6 +304,39 @@ def workload_config(args):
 # ---------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------
+def measured_peak():
+    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(peaks_file):
+        with open(peaks_file) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_facts(precision, N, K):
+    """Per-launch DRAM bytes and pipe utilisation of the four iteration kernels from the
+    committed `ncu --set full` capture of this workload (profiles/, newest round first)."""
+    if precision != 'fp32' or N != 2048 or K != 16:
+        return None
+    for name in ('r02_dram_traffic.json', 'r01_dram_traffic.json'):
+        path = os.path.join(ROOT, 'profiles', name)
+        if os.path.isfile(path):
+            with open(path) as f:
+                t = json.load(f)
+            t['_file'] = 'profiles/' + name
+            return t
+    return None
+
+
+def time_frames(h, frame, seeds, barrier):
+    barrier()
+    h.timer_start()
+    for s in seeds:
+        frame(s)
+    ms = h.timer_stop()
+    barrier()
+    return ms
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -252,11 +345,7 @@ def main():
     N, K, n_iter = args.size, args.orientations, args.iterations
 
     if args.impl == 'reference':
-        if rank != 0:
-            return
-        from oracle import line_sted_oracle as orc
-        psfs = orc.benchmark_psfs(K)
-        run_reference_arm(args, psfs, synthetic_object(N))
+        run_reference_arm(args)
         return
 
     os.environ['LSTED_DEVICE'] = str(local_rank)
@@ -275,33 +364,30 @@ def main():
     psfs = orientations.line_orientation_psfs(base, K, EMISSION_2P0X_LR)
     obj_host = synthetic_object(N)
     brightness = total_brightness(N)
+    prec_bits = 32 if args.precision == 'fp32' else 64
 
     lib = _lib.get()
     by_orientation = args.shard == 'orientations' and world > 1
     if by_orientation:
         from rescan_line_sted_b200 import sharded
         sd = sharded.OrientationShardedDeconvolver(
-            st._stack_psfs(psfs), (N, N), precision=32 if args.precision == 'fp32' else 64,
-            device=local_rank)
+            st._stack_psfs(psfs), (N, N), precision=prec_bits, device=local_rank)
         h = sd.handle
     else:
-        h = _lib.DeconvHandle(lib, st._stack_psfs(psfs), (N, N),
-                              precision=32 if args.precision == 'fp32' else 64, device=local_rank)
+        h = _lib.DeconvHandle(lib, st._stack_psfs(psfs), (N, N), precision=prec_bits,
+                              device=local_rank)
     jobs = 1 if by_orientation else world   # frames in flight across the node
     info = h.info()
     pinned_in = _lib.pinned_empty((1, N, N))
     pinned_in[...] = obj_host
-    pinned_out = _lib.pinned_empty((1, N, N))
 
-    def frame_resident(seed):
-        h.set_option('forget_normalization', 1)
-        h.simulate(brightness, seed)
-        h.iterate(n_iter)
-
-    def frame_e2e(seed):
-        h.upload_object(pinned_in)                       # H2D, pinned
-        frame_resident(seed)
-        h.get_into(_lib.ESTIMATE, 0, pinned_out)         # D2H (syncs)
+    def frame_on(handle):
+        def frame(seed):
+            handle.set_option('forget_normalization', 1)
+            handle.simulate(brightness, seed)        # (restarts the estimate from ones)
+            handle.iterate(n_iter)
+        return frame
+    frame_resident = frame_on(h)
 
     def barrier():
         h.sync()
@@ -319,6 +405,7 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing (headline `value`) ----
+    seed0 = 0 if by_orientation else 7919 * rank
     h.upload_object(pinned_in)
     sampler = ClockSampler(local_rank)
     sampler.start()     # before the warm-up: nvidia-smi start-up stalls the driver briefly
@@ -326,19 +413,15 @@ def main():
         frame_resident(1000 + w)
     barrier()
     t_begin = time.perf_counter()
-    h.timer_start()
-    for s in range(args.steps):
-        frame_resident(s + 1 + (0 if by_orientation else 7919 * rank))
-    ms_total = h.timer_stop()
+    ms_total = time_frames(h, frame_resident, [s + 1 + seed0 for s in range(args.steps)], barrier)
     sampler.window(t_begin, time.perf_counter())
-    barrier()
     # Same K steps again with a CUDA-event pair around every launch (costs a few
     # microseconds of stream time per launch, so it is kept out of `value`): the
     # per-kernel durations behind `roofline` and `kernels`.
     h.set_option('profile', 1)
     h.profile(reset=True)
     for s in range(args.steps):
-        frame_resident(s + 1 + (0 if by_orientation else 7919 * rank))
+        frame_resident(s + 1 + seed0)
     prof = h.profile(reset=True)
     h.set_option('profile', 0)
     clocks = sampler.stop()
@@ -346,22 +429,91 @@ def main():
     ms_step = ms_total / args.steps
     value = jobs * 1000.0 / ms_step
 
-    # ---- end-to-end timing through host buffers ----
+    # ---- end-to-end through the reference-facing API (line_sted_figure_2.py:40-56) ----
+    # host object (pinned) -> Deconvolver.create_data_from_object -> n_iter x iterate() -> .estimate
+    h2d = int(pinned_in.nbytes)
+    if by_orientation:
+        pinned_out = _lib.pinned_empty((1, N, N))
+
+        def frame_e2e(seed):
+            h.upload_object(pinned_in)
+            frame_resident(seed)
+            h.get_into(_lib.ESTIMATE, 0, pinned_out)
+            return pinned_out
+        api = 'DeconvHandle of the orientation-sharded deconvolver (upload_object, simulate, iterate, get)'
+    else:
+        d = st.Deconvolver(psfs, output_prefix=os.path.join('/tmp', 'lsted_bench_%d_' % rank),
+                           verbose=False)
+        d._handle, d._shape = h, (1, N, N)          # share the bench handle (OTFs already built)
+        d._psf_key = tuple(id(p) for p in d.psfs)
+
+        def frame_e2e(seed):
+            d.num_iterations = 0
+            d.create_data_from_object(pinned_in, total_brightness=brightness, random_seed=seed)
+            for _ in range(n_iter):
+                d.iterate()
+            return d.estimate                        # D2H, fresh float64 array
+        api = ('line_sted_tools.Deconvolver: create_data_from_object(host float64 object, pinned) '
+               '+ %d x iterate() + read of .estimate' % n_iter)
     for w in range(min(2, args.warmup)):
-        frame_e2e(2000 + w)
+        est = frame_e2e(2000 + w)
     barrier()
     t0 = time.perf_counter()
     h.timer_start()
     for s in range(args.steps):
-        frame_e2e(s + 1)
+        est = frame_e2e(s + 1)
     h.sync()
     wall = (time.perf_counter() - t0) * 1e3
     ms_e2e = max(h.timer_stop(), wall)
     barrier()
     ms_e2e = max_over_ranks(ms_e2e) / args.steps
-    est = np.array(pinned_out)
+    est = np.array(est)
+    d2h = int(est.nbytes)
     if not np.isfinite(est).all() or est.min() < 0:
         raise RuntimeError('bench produced a non-finite estimate')
+
+    # ---- N > 1: the same frame with its orientations split over the GPUs ----
+    orientation_record = None
+    if world > 1 and not by_orientation and K >= world:
+        from rescan_line_sted_b200 import sharded
+        sd = sharded.OrientationShardedDeconvolver(
+            st._stack_psfs(psfs), (N, N), precision=prec_bits, device=local_rank)
+        hs = sd.handle
+        hs.upload_object(pinned_in)
+        frame_sharded = frame_on(hs)
+        for w in range(args.warmup):
+            frame_sharded(1000 + w)
+        ms_sh = max_over_ranks(time_frames(hs, frame_sharded,
+                                           [s + 1 for s in range(args.steps)], barrier)) / args.steps
+        # parity, witnessed in the driver's own run: same seed -> same Poisson field (keyed by
+        # global orientation and pixel); compare with the rank-local unsharded frame
+        frame_sharded(4242)
+        frame_resident(4242)
+        e_sh, e_1 = hs.get(_lib.ESTIMATE), h.get(_lib.ESTIMATE)
+        rel = float(np.linalg.norm(e_sh - e_1) / np.linalg.norm(e_1))
+        rel = max_over_ranks(rel)
+        orientation_record = {
+            'frames_per_sec': 1000.0 / ms_sh, 'ms_per_frame': ms_sh,
+            'speedup_vs_one_gpu': ms_step / ms_sh, 'efficiency': ms_step / ms_sh / world,
+            'rel_l2_vs_unsharded': rel, 'rel_l2_tolerance': 2e-4,
+            'reduction': 'fused into the column kernel over NVLink peer memory (P2P)' if sd.p2p
+                         else 'ncclAllReduce of the Fourier-domain partial sum',
+            'orientations_per_gpu': sd.k1 - sd.k0}
+        sd.close()
+
+    # ---- fp64-vs-fp64 companion figure (the tolerance-validation mode) ----
+    fp64_record = None
+    if args.precision == 'fp32' and not by_orientation and not args.no_fp64:
+        h64 = _lib.DeconvHandle(lib, st._stack_psfs(psfs), (N, N), precision=64, device=local_rank)
+        h64.upload_object(pinned_in)
+        f64 = frame_on(h64)
+        f64(1)
+        n64 = max(1, min(3, args.steps))
+        ms64 = max_over_ranks(time_frames(h64, f64, [s + 2 + seed0 for s in range(n64)], barrier)) / n64
+        fp64_record = {'value': jobs * 1000.0 / ms64, 'unit': 'frames/s', 'ms_per_step': ms64,
+                       'steps': n64, 'dtype': 'f64',
+                       'note': 'same frame(%d) with the engine in fp64 (the reference\'s dtype)' % n_iter}
+        h64.close()
 
     if rank != 0:
         if dist is not None:
@@ -369,28 +521,18 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (live CUDA-event timings) ----
-    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.isfile(peaks_file):
-        with open(peaks_file) as f:
-            peak, peak_src = float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    peak, peak_src = measured_peak()
     elem = 4 if args.precision == 'fp32' else 8
     A = elem * N * N
     K_total = K
     if by_orientation:
         K = sd.k1 - sd.k0       # per-GPU accounting: this rank's orientations
-    # algorithmic bytes charged to each launch (DESIGN.md "Roofline accounting")
-    alg = {'row_mid': K * A,        # streams the K measurements once
-           'row_final': 4 * A,      # norm + estimate read, estimate write (+ estimate for H)
-           'col_h': 0.0, 'col_ht': 0.0,   # spectra only: no algorithmic array touched
-           'row_inv_sim': 2 * K * A, 'row_fwd': A, 'row_inv_store': A}
     total_kernel_ms = sum(v[0] for v in prof.values())
     launches = int(sum(v[1] for v in prof.values()))
     dom = max(prof, key=lambda k: prof[k][0])
     dom_ms, dom_n = prof[dom]
     kernels = {k: {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[1] / args.steps,
-                   'share': v[0] / total_kernel_ms if total_kernel_ms else 0.0}
+                   'avg_ms': v[0] / v[1], 'share': v[0] / total_kernel_ms if total_kernel_ms else 0.0}
                for k, v in prof.items() if v[1]}
     # The iteration is one unit of (K+4)A bytes spread over its four launches:
     it_ms = sum(prof[k][0] for k in ('col_h', 'row_mid', 'col_ht', 'row_final')) / (
@@ -402,52 +544,64 @@ def main():
         'kernel_avg_ms': dom_ms / max(1, dom_n),
         'iteration_avg_ms': it_ms,
         'achieved': (K + 4) * A / (it_ms * 1e-3) / 1e9,
+        'algorithmic_bytes': (K + 4) * A,
         'traffic': None,
         'note': 'achieved = (K+4)*A algorithmic bytes of one RL iteration / the summed average '
-                'durations of its 4 launches (col_h,row_mid,col_ht,row_final); the path is '
-                'FFT (FP32/SMEM) bound, not HBM bound: see DESIGN.md',
+                'durations of its 4 launches (col_h,row_mid,col_ht,row_final).  The binding '
+                'resources are the FP32 and shared-memory pipes (FFT butterflies), not HBM: '
+                'fp32_pipe_frac / smem_pipe_frac / dram_frac below, DESIGN.md section 4',
     }
-    # DRAM traffic of the same four launches from the committed ncu --set full capture
-    traffic_file = os.path.join(ROOT, 'profiles', 'r01_dram_traffic.json')
-    if (os.path.isfile(traffic_file) and args.precision == 'fp32' and N == 2048 and K_total == 16
-            and not by_orientation):
-        with open(traffic_file) as f:
-            t = json.load(f)
-        roofline['traffic'] = sum(t[k]['dram_bytes_read'] + t[k]['dram_bytes_write']
-                                  for k in ('col_h', 'row_mid', 'col_ht', 'row_final'))
-        roofline['traffic_source'] = t['_source']
-        roofline['algorithmic_bytes'] = (K + 4) * A
+    facts = ncu_facts(args.precision, N, K_total) if not by_orientation else None
+    if facts:
+        names = ('col_h', 'row_mid', 'col_ht', 'row_final')
+        traffic = sum(facts[k]['dram_bytes_read'] + facts[k]['dram_bytes_write'] for k in names)
+        roofline['traffic'] = traffic
+        roofline['traffic_source'] = facts.get('_source', facts['_file'])
+        # real DRAM traffic of the iteration / its live duration / the measured copy peak
+        roofline['dram_frac'] = traffic / (it_ms * 1e-3) / 1e9 / peak
+        if all('fma_pipe_pct' in facts[k] for k in names):
+            # time-weighted ncu pipe utilisation of the four launches (captured durations)
+            tt = sum(facts[k]['duration_us'] for k in names)
+            roofline['fp32_pipe_frac'] = sum(facts[k]['fma_pipe_pct'] * facts[k]['duration_us']
+                                             for k in names) / tt / 100.0
+            roofline['smem_pipe_frac'] = sum(facts[k]['l1tex_pct'] * facts[k]['duration_us']
+                                             for k in names) / tt / 100.0
+            roofline['binding'] = 'fp32 + shared-memory pipes (see fp32_pipe_frac, smem_pipe_frac)'
     roofline['frac'] = roofline['achieved'] / peak
     roofline['step_achieved'] = step_bytes / (ms_step * 1e-3) / 1e9
     roofline['step_frac'] = roofline['step_achieved'] / peak
 
+    cfg = workload_config(args)
+    cfg['e2e_api'] = api
     line = {
         'metric': 'frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'strong' if by_orientation else 'weak',
         'vs_baseline': None,
         'dtype': 'f32' if args.precision == 'fp32' else 'f64', 'data': 'synthetic',
-        'config': workload_config(args),
+        'config': cfg,
         'e2e': {'value': jobs * 1000.0 / ms_e2e, 'unit': 'frames/s',
-                'h2d_bytes_per_step': int(pinned_in.nbytes),
-                'd2h_bytes_per_step': int(pinned_out.nbytes), 'ms_per_step': ms_e2e},
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'kernels': kernels,
         'rl_iterations_per_sec': jobs * n_iter * 1000.0 / ms_step,
         'geometry': {'Ly': info.Ly, 'Lx': info.Lx, 'cols_per_cta': info.cols_per_cta,
                      'row_pairs_per_cta': info.row_pairs_per_cta,
                      'device_bytes': int(info.device_bytes)},
     }
+    extra = {}
+    if fp64_record:
+        extra['fp64'] = fp64_record
+    if orientation_record:
+        line['orientation_sharded'] = orientation_record
+    if extra:
+        line['extra'] = extra
     if world == 1 and not args.no_cpu_baseline:
-        sample_iters = 2
-        cpu = cpu_frame_seconds(obj_host, psfs, n_iter, os.cpu_count() or 1, sample_iters)
-        line['cpu_baseline'] = {
-            'value': 1.0 / cpu['frame_s'], 'unit': 'frames/s', 'cores': os.cpu_count() or 1,
-            'kind': 'port',
-            'sample': '1 forward+Poisson (%.2f s) + H_t_normalization (%.2f s) + %d RL iterations '
-                      '(%.2f s each) of the same 2048^2/K=16 workload with scipy.fft workers = '
-                      'all cores; frame(%d) extrapolated as forward + norm + %d x iteration'
-                      % (cpu['forward_s'], cpu['normalization_s'], sample_iters,
-                         cpu['iteration_s'], n_iter, n_iter)}
+        ref = load_reference_module()
+        cpu = cpu_reference_frame(args, obj_host, reference_psfs(ref, K_total), ref,
+                                  host_cores(), 0, 1)
+        line['cpu_baseline'] = {'value': 1.0 / cpu['frame_s'], 'unit': 'frames/s',
+                                'cores': cpu['cores'], 'kind': cpu['kind'],
+                                'sample': cpu['sample']}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -104,6 +104,8 @@ int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info);
 /* options: "exact_clip" (0|1: clip every H_t term before the sum, like :587),
  *          "profile" (0|1: per-kernel CUDA-event timing),
  *          "forget_normalization" (drop the cached H_t_normalization, :590),
+ *          "reset_estimate" (the next iterate() starts from an all-ones estimate, :521-522;
+ *          new data alone do not reset it, as in the reference),
  *          "fast_path" (0|1, default 1: use the compile-time-planned kernels when
  *          the transform length has one; 0 forces the generic mixed-radix kernels),
  *          A/B switches of kernel variants with identical results: "row_tma" (0|1|2, default 2:

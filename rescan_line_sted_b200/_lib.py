@@ -192,10 +192,14 @@ class DeconvHandle:
         self.lib.call('lsted_deconv_set_option', self._h, name.encode(),
                       float(value))
 
-    def create_data(self, obj, total_brightness, seed):
+    def create_data(self, obj, total_brightness, seed, reset_estimate=True):
+        """Forward model + noise.  `reset_estimate` (default): the next iterate() starts
+        from ones; the library itself leaves the estimate alone, like ref:496-512."""
         obj, p = as_f64(obj)
         assert obj.size == self.Ny * self.Nx
         rescale = total_brightness is not None
+        if reset_estimate:
+            self.set_option('reset_estimate', 1)
         self.lib.call('lsted_deconv_create_data', self._h, p,
                       float(total_brightness or 0.0), int(rescale),
                       ctypes.c_uint64(seed))
@@ -207,8 +211,10 @@ class DeconvHandle:
         self.lib.call('lsted_deconv_upload_object', self._h,
                       obj.ctypes.data_as(c_double_p))
 
-    def simulate(self, total_brightness, seed):
+    def simulate(self, total_brightness, seed, reset_estimate=True):
         rescale = total_brightness is not None
+        if reset_estimate:
+            self.set_option('reset_estimate', 1)
         self.lib.call('lsted_deconv_simulate', self._h,
                       float(total_brightness or 0.0), int(rescale),
                       ctypes.c_uint64(seed))

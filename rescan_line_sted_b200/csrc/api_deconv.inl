@@ -15,7 +15,8 @@ struct lsted_deconv {
     }                                                                      \
     catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }  \
     catch (const std::string& s) { return set_error(LSTED_ERR_ARG, s); }   \
-    catch (const std::bad_alloc&) { return set_error(LSTED_ERR_ARG, "host allocation failed"); }
+    catch (const std::bad_alloc&) { return set_error(LSTED_ERR_ARG, "host allocation failed"); } \
+    catch (...) { return set_error(LSTED_ERR_ARG, "unexpected exception"); }
 #define LSTED_ENGINE(h, call)  \
     do {                       \
         (h)->bk->activate();   \
@@ -58,6 +59,8 @@ extern "C" int lsted_deconv_create_tiled(lsted_deconv** out, int device, const d
     }
     catch (const lsted::ApiError& e) { lsted_deconv_destroy(h); return set_error(e.code, e.msg); }
     catch (const std::string& s) { lsted_deconv_destroy(h); return set_error(LSTED_ERR_ARG, s); }
+    catch (const std::bad_alloc&) { lsted_deconv_destroy(h); return set_error(LSTED_ERR_ARG, "host allocation failed"); }
+    catch (...) { lsted_deconv_destroy(h); return set_error(LSTED_ERR_ARG, "unexpected exception in lsted_deconv_create"); }
 }
 
 extern "C" int lsted_deconv_create(lsted_deconv** out, int device, const double* psfs, int K, int ny,
@@ -79,6 +82,8 @@ extern "C" int lsted_deconv_destroy(lsted_deconv* h) {
 extern "C" int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info) {
     if (!h || !info) return set_error(LSTED_ERR_ARG, "null pointer");
     memset(info, 0, sizeof(*info));
+    LSTED_TRY
+    h->bk->activate();
     lsted::EngineInfo ei;
     h->e->info(&ei);
     const int cb = h->precision == 32 ? 8 : 16;
@@ -99,16 +104,23 @@ extern "C" int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info) {
     info->tile_out_y = ei.tile_out_y; info->tile_out_x = ei.tile_out_x;
     info->band_y0 = ei.band_y0; info->band_y1 = ei.band_y1;
     return LSTED_OK;
+    LSTED_CATCH
 }
 
 extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double value) {
     if (!h || !name) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    h->bk->activate();
     if (!strcmp(name, "exact_clip")) {
         h->e->set_exact_clip(value != 0);
         return LSTED_OK;
     }
     if (!strcmp(name, "forget_normalization")) {
         h->e->forget_normalization();
+        return LSTED_OK;
+    }
+    if (!strcmp(name, "reset_estimate")) {
+        h->e->reset_estimate();
         return LSTED_OK;
     }
     if (!strcmp(name, "prefetch")) { h->bk->set_prefetch(value != 0); return LSTED_OK; }
@@ -119,6 +131,7 @@ extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double
     if (!strcmp(name, "real_otf")) { h->bk->set_real_otf(value != 0); return LSTED_OK; }   // before set_psfs
     if (!strcmp(name, "profile")) { h->bk->set_profile(value != 0); return LSTED_OK; }
     return set_error(LSTED_ERR_ARG, std::string("unknown option ") + name);
+    LSTED_CATCH
 }
 
 extern "C" int lsted_deconv_create_data(lsted_deconv* h, const double* object, double total_brightness,
@@ -199,8 +212,8 @@ static int check_which(lsted_deconv* h, int which, int k) {
 
 extern "C" int lsted_deconv_get(lsted_deconv* h, int which, int k, double* out) {
     if (!h || !out) return set_error(LSTED_ERR_ARG, "null pointer");
-    if (check_which(h, which, k)) return set_error(LSTED_ERR_ARG, "bad array selector");
     LSTED_TRY
+    if (check_which(h, which, k)) return set_error(LSTED_ERR_ARG, "bad array selector");
     LSTED_ENGINE(h, get_array(which, k, out));
     return LSTED_OK;
     LSTED_CATCH
@@ -208,8 +221,8 @@ extern "C" int lsted_deconv_get(lsted_deconv* h, int which, int k, double* out) 
 
 extern "C" int lsted_deconv_set(lsted_deconv* h, int which, int k, const double* in) {
     if (!h || !in) return set_error(LSTED_ERR_ARG, "null pointer");
-    if (check_which(h, which, k)) return set_error(LSTED_ERR_ARG, "bad array selector");
     LSTED_TRY
+    if (check_which(h, which, k)) return set_error(LSTED_ERR_ARG, "bad array selector");
     LSTED_ENGINE(h, set_array(which, k, in));
     h->bk->sync();
     return LSTED_OK;

@@ -48,6 +48,11 @@ LSTED_HD size_t xb_index(int y, int x, int rows, int C) {   // OTF arrays: [xb][
 // apart) while a column CTA still streams a fully contiguous slab.  Images with an odd
 // number of rows are stored as if they had one more (never read).
 LSTED_HD int even_rows(int rows) { return (rows + 1) & ~1; }
+// Position of cropped output i inside a transform of length L.  Inside overlap-save tiles the
+// window is as long as the transform (N == L, crop offset s > 0): the last s outputs wrap
+// around -- they lie outside the alias-free interior and are discarded by the caller, but the
+// read must stay inside the sequence.
+LSTED_HD int crop_pos(int s, int i, int L) { const int p = s + i; return p >= L ? p - L : p; }
 LSTED_HD size_t slab2_index(int y, int c, int C) { return (size_t)(y & ~1) * C + 2 * c + (y & 1); }
 LSTED_HD size_t xb2_index(int xb, int y, int c, int rows, int C) {
     return (size_t)xb * even_rows(rows) * C + slab2_index(y, c, C);
@@ -80,10 +85,21 @@ template <typename T> struct RowArgs {
     const void* tmap_out;    // spec_out; when set the pair's spectrum chunks travel by TMA (fft_core.cuh)
 };
 
-template <typename T> LSTED_HD T clip0(T v) { return v < (T)0 ? (T)0 : v; }
+// clip(v, 0): NaN clips to 0 on the device (FMNMX) and in the CPU replay alike
+template <typename T> LSTED_HD T clip0(T v) { return v > (T)0 ? v : (T)0; }
 #ifdef __CUDA_ARCH__
 LSTED_HD float clip0(float v) { return fmaxf(v, 0.f); }   // one FMNMX instead of FSETP + FSEL
 #endif
+// RL ratio measurement / clip(expected) (line_sted_tools.py:527-528).  Deliberate deviation, pinned by
+// tests: where the expected image is not positive -- FFT round-off clipped to zero in dark regions,
+// which fp32 reaches on any zero-background object -- the reference divides by zero (inf, and NaN in
+// every pixel after the next transform); here such a pixel contributes a ratio of 0 and the
+// estimate stays finite.  `FAST`: MUFU.RCP based division (<= 2 ulp), fp32 fast path.
+template <bool FAST, typename T> LSTED_HD T rl_ratio(T meas, T expected) {
+    const T e = clip0(expected);
+    const T q = FAST ? fast_div(meas, e) : meas / e;
+    return e > (T)0 ? q : (T)0;
+}
 
 // Row-pair kernel body.  smem: 2 * PR * Lpx complex.
 template <int MODE, typename T, class Ctx>
@@ -144,7 +160,7 @@ LSTED_HD void row_body(Ctx& cx, int block, const RowArgs<T>& a, cplx<T>* smem) {
             T* out2 = (MODE == ROW_INV_SIM) ? a.real_out2 + real_off : 0;
             cx.parallel_for(nrow * Nx, [&](int w) {
                 const int r = w / Nx, i = w - r * Nx;
-                const cplx<T> v = z[(r >> 1) * Lp + pad<T>(g.sx + i)];
+                const cplx<T> v = z[(r >> 1) * Lp + pad<T>(crop_pos(g.sx, i, Lx))];
                 T val = (r & 1) ? v.y : v.x;
                 const size_t o = (size_t)(row0 + r) * Nx + i;
                 if (MODE == ROW_INV_SIM) {
@@ -166,11 +182,11 @@ LSTED_HD void row_body(Ctx& cx, int block, const RowArgs<T>& a, cplx<T>* smem) {
             const int f = w / Lx, i = w - f * Lx, y = row0 + 2 * f;
             T ra = 0, rb = 0;
             if (i < Nx) {
-                const cplx<T> v = z[f * Lp + pad<T>(g.sx + i)];
+                const cplx<T> v = z[f * Lp + pad<T>(crop_pos(g.sx, i, Lx))];
                 const size_t o = (size_t)y * Nx + i;
                 if (MODE == ROW_MID) {
-                    ra = aux[o] / clip0(v.x);
-                    if (y + 1 < Ny) rb = aux[o + Nx] / clip0(v.y);
+                    ra = rl_ratio<false>(aux[o], v.x);
+                    if (y + 1 < Ny) rb = rl_ratio<false>(aux[o + Nx], v.y);
                 } else {
                     ra = est[o] * (clip0(v.x) / aux[o]);
                     est[o] = ra;
@@ -288,7 +304,7 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
             cplx<T>* dst = a.dst + (size_t)k * img_ny + (size_t)xb * slab_ny;
             cx.parallel_for(C * Ny, [&](int w) {
                 const int y = w / C, c = w - y * C;
-                dst[slab2_index(y, c, C)] = z[c * Lp + pad<T>(g.sy + y)];
+                dst[slab2_index(y, c, C)] = z[c * Lp + pad<T>(crop_pos(g.sy, y, Ly))];
             });
         }
         return;
@@ -315,7 +331,7 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
     cplx<T>* dst = a.dst + (size_t)xb * slab_ny;
     cx.parallel_for(C * Ny, [&](int w) {
         const int y = w / C, c = w - y * C;
-        dst[slab2_index(y, c, C)] = z[c * Lp + pad<T>(g.sy + y)];
+        dst[slab2_index(y, c, C)] = z[c * Lp + pad<T>(crop_pos(g.sy, y, Ly))];
     });
 }
 

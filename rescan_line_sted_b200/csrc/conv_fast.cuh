@@ -800,8 +800,8 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                                 out[o] = clip0(z.x);       // noisy image: second loop below
                                 if (two) out[o + Nx] = clip0(z.y);
                             } else if (MODE == ROW_MID) {
-                                w.x = fast_div(rows_s[i], clip0(z.x));
-                                if (two) w.y = fast_div(rows_s[P::L + i], clip0(z.y));
+                                w.x = rl_ratio<true>(rows_s[i], z.x);
+                                if (two) w.y = rl_ratio<true>(rows_s[P::L + i], z.y);
                             } else {  // ROW_FINAL
                                 w.x = (LEAN ? stage[i] : stage_est ? stage2[i] : out[o]) * fast_div(clip0(z.x), rows_s[i]);
                                 out[o] = w.x;
@@ -1084,10 +1084,10 @@ LSTED_HD void row_mid_dual_body(Ctx& cx, int block, const RowArgs<typename P::T>
                     const c2 z = r.v[m * I::RC + q];
                     c2 w = mk2(mk<T>(0, 0), mk<T>(0, 0));
                     if (i >= 0 && i < Nx) {
-                        w.a.x = fast_div(stage[i], clip0(z.a.x));
-                        w.a.y = fast_div(stage[P::L + i], clip0(z.a.y));
-                        w.b.x = fast_div(stage[2 * P::L + i], clip0(z.b.x));
-                        w.b.y = fast_div(stage[3 * P::L + i], clip0(z.b.y));
+                        w.a.x = rl_ratio<true>(stage[i], z.a.x);
+                        w.a.y = rl_ratio<true>(stage[P::L + i], z.a.y);
+                        w.b.x = rl_ratio<true>(stage[2 * P::L + i], z.b.x);
+                        w.b.y = rl_ratio<true>(stage[3 * P::L + i], z.b.y);
                     }
                     r.v[m * I::RC + q] = w;
                 }
@@ -1335,8 +1335,8 @@ LSTED_HD void row2_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a
                             out[o] = clip0(z.x);
                             if (two) out[o + Nx] = clip0(z.y);
                         } else if (MODE == ROW_MID) {
-                            w.x = fast_div(stage[i], clip0(z.x));
-                            if (two) w.y = fast_div(stage[P::L + i], clip0(z.y));
+                            w.x = rl_ratio<true>(stage[i], z.x);
+                            if (two) w.y = rl_ratio<true>(stage[P::L + i], z.y);
                         } else {  // ROW_FINAL
                             w.x = stage2[i] * fast_div(clip0(z.x), stage[i]);
                             out[o] = w.x;

@@ -44,6 +44,7 @@ class EngineBase {
     virtual void H_host(const double* x, double* out) = 0;
     virtual void Ht_host(const double* y, double* out, bool normalize) = 0;
     virtual void forget_normalization() = 0;
+    virtual void reset_estimate() = 0;     // the next iterate() starts from ones (ref:521-522)
     virtual void set_sharding(int rank, int world, int k_offset) = 0;
     virtual void set_exact_clip(bool on) = 0;
     virtual void p2p_export(char* handles_out) = 0;                       // kIpcBytes
@@ -205,8 +206,9 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         if (rescale) s = total_brightness / bk.sum(object64, npix, partial);
         bk.cast_in(true_object, object64, npix, s);
         op_H(true_object, noiseless, noisy, seed);
-        iterations_done = 0;
-        have_estimate = false;
+        // like the reference (ref:496-512) new data leave the estimate alone: the caller
+        // decides whether the next iterate() restarts from ones (reset_estimate)
+        invalidate_estimate_spectrum();   // op_H went through spec1
     }
     void create_data(const double* obj_host, double total_brightness, bool rescale,
                      unsigned long long seed) {
@@ -214,6 +216,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         simulate(total_brightness, rescale, seed);
     }
     void forget_normalization() { have_norm = false; }
+    void reset_estimate() { have_estimate = false; iterations_done = 0; }
     // tensor maps of the two row-spectrum arrays (fp32 fast rows): see fft_core.cuh tma_load_chunks
     void ensure_tmaps() {
         if (tmaps_tried) return;

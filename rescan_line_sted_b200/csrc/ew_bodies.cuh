@@ -78,7 +78,7 @@ template <int OP, typename T> LSTED_HD void win_apply(const WinArgs<T>& a, size_
         a.big[gi] = v;
         const unsigned long long pix = (unsigned long long)gy * a.Nx + gx;
         a.big2[gi] = (T)(poisson_sample((double)v, a.seed, pix, a.img0 + img) + 1e-9);
-    } else if (OP == WIN_RATIO) a.big[gi] = a.big2[gi] / v;
+    } else if (OP == WIN_RATIO) a.big[gi] = v > (T)0 ? a.big2[gi] / v : (T)0;   // see rl_ratio (conv_bodies.cuh)
     else if (OP == WIN_UPDATE) a.big[gi] = a.big[gi] * (v / a.big2[gi]);
 }
 

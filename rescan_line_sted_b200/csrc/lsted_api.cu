@@ -465,6 +465,14 @@ class CudaBackend {
     }
 
     // ---- launches ----
+    // MaxDynamicSharedMemorySize is a per-device function attribute: remembered per backend
+    // (one backend = one device), not in process-wide statics.
+    template <class F> void ensure_smem(F* fn, size_t smem) {
+        size_t& have = smem_cfg_[(const void*)fn];
+        if (smem <= have) return;
+        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
     // ---- fast path (compile-time plans) ----
     static int fast_cols(int L, int cplx_bytes) {
         if (L == Plan2160f::L) return cplx_bytes == 8 ? (int)Plan2160f::C : (int)Plan2160d::C;
@@ -484,17 +492,10 @@ class CudaBackend {
                            a.g.Nx == (int)RowGeom2048::NX && a.g.sx == (int)RowGeom2048::SX;
         const bool fixed_c = sizeof(typename P::T) == 4 && MODE != lsted::ROW_FWD &&
                              a.g.Nx == (int)RowGeom2048c::NX && a.g.sx == 0;   // centred OTFs
-        static bool configured = false;
-        if (!configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (sizeof(typename P::T) == 4) {
-                CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048c>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            }
-            configured = true;
+        ensure_smem(row_fast_kernel<MODE, P>, smem);
+        if (sizeof(typename P::T) == 4) {
+            ensure_smem(row_fast_kernel<MODE, P, RowGeom2048>, smem);
+            ensure_smem(row_fast_kernel<MODE, P, RowGeom2048c>, smem);
         }
         // the plan's own pairs-per-CTA decides the grid (the generic geometry may differ)
         const int fast_grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
@@ -527,16 +528,9 @@ class CudaBackend {
     template <int MODE, class P, int TMA>
     void launch_row_tma_variant(int fast_grid, const lsted::RowArgs<typename P::T>& a, int kind, size_t smem,
                                 bool fixed, bool fixed_c) {
-        static bool configured = false;
-        if (!configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, lsted::RowGeomRuntime, TMA>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048, TMA>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUDA_CHECK(cudaFuncSetAttribute(row_fast_kernel<MODE, P, RowGeom2048c, TMA>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        ensure_smem(row_fast_kernel<MODE, P, lsted::RowGeomRuntime, TMA>, smem);
+        ensure_smem(row_fast_kernel<MODE, P, RowGeom2048, TMA>, smem);
+        ensure_smem(row_fast_kernel<MODE, P, RowGeom2048c, TMA>, smem);
         before(kind);
         if (fixed) row_fast_kernel<MODE, P, RowGeom2048, TMA><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
         else if (fixed_c) row_fast_kernel<MODE, P, RowGeom2048c, TMA><<<fast_grid, P::ROW_THREADS, smem, stream_>>>(a);
@@ -590,24 +584,11 @@ class CudaBackend {
         const size_t smem = lsted::fast_col_smem_bytes<P>();
         const bool fixed = sizeof(typename P::T) == 4 && a.g.Ny == (int)ColGeom2048::NY &&
                            a.g.sy == (int)ColGeom2048::SY && a.rows_in == a.g.Ny;
-        static bool configured = false;
-        if (!configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (sizeof(typename P::T) == 4)
-                CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P, ColGeom2048>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        ensure_smem(col_fast_kernel<MODE, P>, smem);
+        if (sizeof(typename P::T) == 4) ensure_smem(col_fast_kernel<MODE, P, ColGeom2048>, smem);
         if (MODE == lsted::COL_HT && a.p2p_world > 1) {
-            static bool p2p_configured = false;
-            if (!p2p_configured) {
-                CUDA_CHECK(cudaFuncSetAttribute(col_ht_p2p_kernel<P, false>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                CUDA_CHECK(cudaFuncSetAttribute(col_ht_p2p_kernel<P, true>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                p2p_configured = true;
-            }
+            ensure_smem(col_ht_p2p_kernel<P, false>, smem);
+            ensure_smem(col_ht_p2p_kernel<P, true>, smem);
             const int ncta = grid < num_sms_ ? grid : num_sms_;
             before(kind);
             if (a.otf_real) col_ht_p2p_kernel<P, true><<<ncta, P::COL_THREADS, smem, stream_>>>(a);
@@ -618,15 +599,8 @@ class CudaBackend {
         if (a.otf_real) {   // centred real OTFs
             const bool fixed_c = sizeof(typename P::T) == 4 && a.g.Ny == (int)ColGeom2048c::NY &&
                                  a.g.sy == 0 && a.rows_in == a.g.Ny;
-            static bool ro_configured = false;
-            if (!ro_configured) {
-                CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P, lsted::ColGeomRuntime, true>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                if (sizeof(typename P::T) == 4)
-                    CUDA_CHECK(cudaFuncSetAttribute(col_fast_kernel<MODE, P, ColGeom2048c, true>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ro_configured = true;
-            }
+            ensure_smem(col_fast_kernel<MODE, P, lsted::ColGeomRuntime, true>, smem);
+            if (sizeof(typename P::T) == 4) ensure_smem(col_fast_kernel<MODE, P, ColGeom2048c, true>, smem);
             before(kind);
             if (fixed_c) col_fast_kernel<MODE, P, ColGeom2048c, true><<<grid, P::COL_THREADS, smem, stream_>>>(a);
             else col_fast_kernel<MODE, P, lsted::ColGeomRuntime, true><<<grid, P::COL_THREADS, smem, stream_>>>(a);
@@ -641,12 +615,7 @@ class CudaBackend {
     template <int MODE> void launch_row2(const lsted::RowArgs<float>& a, int kind) {
         typedef Plan2160f2 P;
         const size_t smem = lsted::fast_row2_smem_bytes<P>(MODE);
-        static bool configured = false;
-        if (!configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(row2_fast_kernel<MODE, P>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        ensure_smem(row2_fast_kernel<MODE, P>, smem);
         lsted::RowArgs<float> b = a;
         if (b.prefetch_ahead > 0) b.prefetch_ahead = num_sms_ * LSTED_ROW2_CTAS;
         const int fast_grid = a.nimg * ((((a.g.Ny + 1) / 2) + P::PR - 1) / P::PR);
@@ -660,12 +629,7 @@ class CudaBackend {
         if (MODE == lsted::ROW_MID && row_dual_ && a.g.Ny % 4 == 0) {
             typedef lsted::RowDual<Plan2160f> D;
             const size_t smem = D::smem_bytes();
-            static bool configured = false;
-            if (!configured) {
-                CUDA_CHECK(cudaFuncSetAttribute(row_mid_dual_kernel<Plan2160f>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = true;
-            }
+            ensure_smem(row_mid_dual_kernel<Plan2160f>, smem);
             lsted::RowArgs<float> b = a;
             if (b.prefetch_ahead > 0) b.prefetch_ahead = num_sms_ * 2;   // two CTAs per SM
             before(kind);
@@ -702,12 +666,7 @@ class CudaBackend {
             if (use_fast_ && try_fast_row<MODE>(grid, a, kind0)) return;
         }
         const size_t smem = lsted::row_smem_bytes(a.g, (int)sizeof(lsted::cplx<T>));
-        static size_t configured = 0;  // per instantiation
-        if (smem > configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(row_kernel<MODE, T>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        ensure_smem(row_kernel<MODE, T>, smem);
         const int kind = MODE == lsted::ROW_FWD ? KK_ROW_FWD
                        : MODE == lsted::ROW_INV_STORE ? KK_ROW_INV_STORE
                        : MODE == lsted::ROW_INV_SIM ? KK_ROW_INV_SIM
@@ -729,12 +688,7 @@ class CudaBackend {
             e.msg = "generic column kernel does not fit in shared memory for this geometry";
             throw e;
         }
-        static size_t configured = 0;
-        if (smem > configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(col_kernel<MODE, T>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        ensure_smem(col_kernel<MODE, T>, smem);
         const int kind = MODE == lsted::COL_OTF ? KK_COL_OTF : MODE == lsted::COL_H ? KK_COL_H : KK_COL_HT;
         const int threads = sizeof(T) == 4 ? kColThreads32 : kColThreads64;
         before(kind);
@@ -797,6 +751,7 @@ class CudaBackend {
     size_t bytes_;
     bool profile_, use_fast_;
     std::map<void*, size_t> sizes_;   // live allocations (for lsted_deconv_info)
+    std::map<const void*, size_t> smem_cfg_;   // kernels whose dynamic shared-memory limit is raised
     void* p2p_local_[3] = {0, 0, 0};
     void* p2p_recv_[lsted::kMaxPeers]; unsigned* p2p_flags_[lsted::kMaxPeers];
     void* p2p_spec_[lsted::kMaxPeers]; unsigned* p2p_done_[lsted::kMaxPeers];

@@ -56,6 +56,7 @@ template <typename T, class BK> class TiledEngine : public EngineBase {
     void p2p_export(char*) { throw std::string("the peer-memory reduction applies to orientation sharding, not to tiles"); }
     void p2p_attach(const char*) { throw std::string("the peer-memory reduction applies to orientation sharding, not to tiles"); }
     void forget_normalization() { have_norm = false; }
+    void reset_estimate() { have_estimate = false; iterations_done = 0; }
     // Sharding of a tiled object = horizontal bands ("object tiles with
     // halo"): rank r owns image rows [o0, o1) and keeps measurements / ratios on that
     // band extended by the PSF halo, where it recomputes the ratio redundantly (the
@@ -104,8 +105,6 @@ template <typename T, class BK> class TiledEngine : public EngineBase {
                 a.seed = seed; a.img0 = 0;
                 bk.template launch_win<WIN_SIMULATE, T>(a);
             }
-        iterations_done = 0;
-        have_estimate = false;
     }
     void create_data(const double* obj_host, double total_brightness, bool rescale,
                      unsigned long long seed) {

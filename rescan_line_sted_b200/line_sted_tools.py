@@ -404,6 +404,7 @@ class Deconvolver:
         self.estimate_history = []
         self._handle = None
         self._shape = None
+        self._psf_key = None
         self._have = set()  # which device arrays hold data
         self._data_version = 0  # bumped whenever true_object changes
 
@@ -414,8 +415,23 @@ class Deconvolver:
         if len(shape) != 3 or shape[0] != 1:
             raise ValueError('images must have shape (1, Ny, Nx); got %r'
                              % (shape,))
-        if self._handle is None or self._shape != shape:
+        # The reference reads self.psfs on every H / H_t call (ref:573, :585): a replaced
+        # list or replaced arrays rebuild the OTFs (in-place edits of an array's contents
+        # are not seen -- assign a new array instead).
+        psf_key = tuple(id(p) for p in self.psfs)
+        if (self._handle is None or self._shape != shape
+                or self._psf_key != psf_key):
+            keep = {}
             if self._handle is not None:
+                if self._shape == shape:   # same images, new PSFs: the state carries over
+                    K_new = len(self.psfs)
+                    # (H_t_normalization included: the reference caches it once, ref:590-592)
+                    for which in sorted(self._have):
+                        per_psf = which in (_lib.NOISELESS, _lib.NOISY)
+                        if per_psf and K_new != self._handle.K:
+                            continue
+                        keep[which] = [self._handle.get(which, k) for k in
+                                       range(self._handle.K if per_psf else 1)]
                 self._handle.close()
             self._handle = _lib.DeconvHandle(
                 _lib.get(), _stack_psfs(self.psfs), shape[1:],
@@ -424,14 +440,19 @@ class Deconvolver:
             if os.environ.get('LSTED_EXACT_CLIP', '0') not in ('', '0'):
                 self._handle.set_option('exact_clip', 1)
             self._shape = shape
+            self._psf_key = psf_key
             self._have = set()
+            for which, arrays in keep.items():
+                for k, a in enumerate(arrays):
+                    self._handle.set(which, k, a)
+                self._have.add(which)
         return self._handle
 
     def _need(self, what, name):
         if self._handle is None or what not in self._have:
             raise AttributeError("'Deconvolver' object has no attribute '%s'"
                                  % name)
-        return self._handle
+        return self._engine(self._shape)   # (notices replaced PSFs)
 
     @property
     def true_object(self):
@@ -491,10 +512,11 @@ class Deconvolver:
         if random_seed is None:
             random_seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2 ** 31 + \
                 int(np.random.randint(0, 2 ** 31 - 1))
-        h.create_data(obj, total_brightness, int(random_seed) % 2 ** 64)
+        # like the reference, new data leave `estimate` and `num_iterations` alone
+        h.create_data(obj, total_brightness, int(random_seed) % 2 ** 64,
+                      reset_estimate=False)
         self._data_version += 1
         self._have |= {_lib.TRUE_OBJECT, _lib.NOISELESS, _lib.NOISY}
-        self._have.discard(_lib.ESTIMATE)
         return None
 
     def load_data_from_tif(self, filename):
@@ -509,6 +531,8 @@ class Deconvolver:
     def iterate(self):
         """One multi-view Richardson-Lucy update on the GPU (ref:520-531)."""
         h = self._need(_lib.NOISY, 'noisy_measurement')
+        if self.num_iterations == 0:   # ref:521-522: the first call always starts from ones
+            h.set_option('reset_estimate', 1)
         h.iterate(1)
         self.num_iterations += 1
         self._have |= {_lib.ESTIMATE, _lib.NORMALIZATION}
@@ -517,6 +541,8 @@ class Deconvolver:
     def iterate_many(self, n):
         """Extension: n RL updates without returning to Python in between."""
         h = self._need(_lib.NOISY, 'noisy_measurement')
+        if self.num_iterations == 0 and int(n) > 0:
+            h.set_option('reset_estimate', 1)
         h.iterate(int(n))
         self.num_iterations += int(n)
         self._have |= {_lib.ESTIMATE, _lib.NORMALIZATION}

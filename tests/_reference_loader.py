@@ -1,5 +1,6 @@
 """Import the UNMODIFIED reference module from /root/reference (build
-container only; absent on the GPU box).  Used by the golden-vector generator
+container) or from its git-ignored copy baseline/_ref/ that __graft_entry__.build()
+makes and gpurun ships to the GPU box.  Used by the golden-vector generator
 and by the CPU tests that pin the oracle.  matplotlib is not installed in the
 image and the reference imports (but never uses) it, so a stub is injected."""
 import importlib.util
@@ -8,8 +9,12 @@ import sys
 import types
 import warnings
 
-REFERENCE_DIR = os.environ.get('LSTED_REFERENCE_DIR',
-                               '/root/reference/figure_generation')
+_CANDIDATES = ('/root/reference/figure_generation',
+               os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                            'baseline', '_ref'))
+REFERENCE_DIR = os.environ.get('LSTED_REFERENCE_DIR') or next(
+    (d for d in _CANDIDATES if os.path.isfile(os.path.join(d, 'line_sted_tools.py'))),
+    _CANDIDATES[0])
 
 
 def reference_available():

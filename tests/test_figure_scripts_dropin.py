@@ -1,7 +1,9 @@
-"""The reference's UNMODIFIED figure scripts run on the drop-in module (build
-container only: needs /root/reference; kernels replayed on the CPU, plotting
-absorbed by a mock matplotlib).  Numbers printed / returned are compared with
-the same scripts running on the reference's own line_sted_tools."""
+"""The reference's UNMODIFIED figure scripts run on the drop-in module (needs the
+reference sources: /root/reference here, the git-ignored baseline/_ref copy on the
+GPU box; plotting absorbed by a mock matplotlib).  Numbers printed / returned are
+compared with the same scripts running on the reference's own line_sted_tools.
+Every test runs twice: kernels replayed on the CPU (`emul`) and, marked `gpu`,
+through liblsted.so on the B200 (`cuda`, fp64 and fp32)."""
 import contextlib
 import io
 import os
@@ -20,6 +22,23 @@ from rescan_line_sted_b200 import _lib
 pytestmark = pytest.mark.skipif(not reference_available(),
                                 reason='reference sources not present')
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+DEVICE = {'kind': 'emul', 'precision': 'fp64'}
+
+
+@pytest.fixture(params=['emul', pytest.param('cuda-fp64', marks=pytest.mark.gpu),
+                        pytest.param('cuda-fp32', marks=pytest.mark.gpu)], autouse=True)
+def device(request):
+    kind, _, precision = request.param.partition('-')
+    DEVICE['kind'], DEVICE['precision'] = kind, precision or 'fp64'
+    yield request.param
+    DEVICE['kind'], DEVICE['precision'] = 'emul', 'fp64'
+
+
+def loose():
+    """fp32 Deconvolver: image-level tolerances of the fp32 mode (1e-5 per pass)."""
+    return DEVICE['precision'] == 'fp32'
 
 
 @contextlib.contextmanager
@@ -44,8 +63,12 @@ def script_environment(tmp_path, backend):
         sys.path[:0] = [REFERENCE_DIR]
     os.chdir(str(work))
     saved_lib = _lib._library
-    _lib._library = emul_support.emulator_library()
-    os.environ['LSTED_PRECISION'] = 'fp64'
+    if DEVICE['kind'] == 'emul':
+        _lib._library = emul_support.emulator_library()
+    else:
+        _lib._library = None
+        _lib.get()                                # the real liblsted.so (raises without it)
+    os.environ['LSTED_PRECISION'] = DEVICE['precision']
     try:
         yield
     finally:
