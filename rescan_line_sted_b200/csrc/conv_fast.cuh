@@ -25,7 +25,10 @@
 
 namespace lsted {
 
-template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct FastPlan {
+// CS_: columns per column CTA when the OTFs are real ("sub-block": C_/CS_ CTAs share one
+// C_-column block of the HBM layout; fp32: 2 of 4, two CTAs per SM) -- also the layout of the
+// real OTF array, [k][xb][sub][y][CS] (each sub-block slab contiguous for its bulk copy).
+template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_, int CS_ = C_> struct FastPlan {
     typedef T_ T;
     typedef Fft3<T, -1, RA, RB, RC, NT_> Fwd;
     typedef Fft3<T, +1, RC, RB, RA, NT_> Inv;
@@ -38,6 +41,10 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
         COL_SMEM_ELEMS = 2 * C_ * LSM_COL,          // two ping-pong buffers
         COL_OTF_ELEMS = C_ * RA * RB * RC,          // + one staged OTF slab [L][C] (bulk copy)
         COL_TW = 256,                               // + base twiddles
+        CS = CS_, NSUB = C_ / CS_,
+        LSM_SUB = (SEQ + 15) / 16 * 16 + 16 / CS_,
+        SUB_THREADS = NT_ * CS_,
+        SUB_SMEM_ELEMS = 2 * CS_ * LSM_SUB,
         // row CTA: PR groups of NTG threads (whole warps), one row pair each
         NTG = (NT_ + 31) / 32 * 32,
         LSM_ROW = (SEQ + 15) / 16 * 16 + 16,    // multiple of 128 bytes: tensor-map copies land here
@@ -56,7 +63,8 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_> struct 
     static_assert(Fwd::MC == 1 && Fwd::NC == NT_, "row split assumes one pass-C butterfly per thread");
     static_assert(Inv::MA == 1 && Inv::NA == NT_, "row unpack assumes one pass-A butterfly per thread");
     static_assert(RC % 2 == 1, "row split assumes an odd last radix");
-    static_assert(RA * RC < 256 && RC * RA < 256 && NT_ <= 256 && NT_ * C_ >= 256 && RA * RB * RC >= 256,
+    static_assert(C_ % CS_ == 0, "sub-blocks must tile a column block");
+    static_assert(RA * RC < 256 && RC * RA < 256 && NT_ <= 256 && NT_ * CS_ >= 256 && RA * RB * RC >= 256,
                   "base twiddles of both transforms must sit in the first COL_TW table entries");
     static_assert((RC - QH) * PX <= LSM_ROW, "mirror exchange must fit one row buffer");
     static_assert(2 * L * sizeof(T_) + sizeof(mbar_t) <= LSM_ROW * 2 * sizeof(T_),
@@ -88,6 +96,12 @@ template <class P> LSTED_HD size_t fast_col_smem_bytes() {
     return sizeof(cplx<typename P::T>) * (size_t)(P::COL_SMEM_ELEMS + P::COL_TW +
                                                   (LSTED_COL_STAGE_OTF ? P::COL_OTF_ELEMS : 0)) +
            (LSTED_COL_STAGE_OTF ? 16 : 0);
+}
+// column CTA on a sub-block of CS columns with real OTFs: exchange buffers + twiddles + one
+// real OTF slab [L][CS] + its mbarrier
+template <class P> LSTED_HD size_t fast_col_sub_smem_bytes() {
+    return sizeof(cplx<typename P::T>) * (size_t)(P::SUB_SMEM_ELEMS + P::COL_TW) +
+           sizeof(typename P::T) * (size_t)P::CS * P::L + 16;
 }
 template <class P> LSTED_HD size_t fast_row_smem_bytes(int mode, bool lean = false) {
     const int bufs = lean ? (mode == ROW_FINAL ? 3 : 2) : mode == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
@@ -154,6 +168,7 @@ LSTED_HD void col_store_inv_c(const cplx<typename P::T>* v, int t, int c, cplx<t
 // v = keep (.) otf on the pass-C / pass-A operand set (rows j + q*NC of the OTF slab)
 template <class P, bool ACCUMULATE>
 LSTED_HD void col_otf_product(ColRegs<P>& r, int t, int c, const cplx<typename P::T>* otf, bool first) {
+    // (complex OTFs: always whole C-column blocks, [y][C])
     typedef typename P::Fwd F;
     typedef typename P::T T;
     LSTED_UNROLL
@@ -174,9 +189,11 @@ LSTED_HD void col_otf_product(ColRegs<P>& r, int t, int c, const cplx<typename P
     }
 }
 
-// the same with a REAL (centred, point-symmetric PSF) OTF: a real scaling / real FMA per element
+// the same with a REAL (centred, point-symmetric PSF) OTF: a real scaling / real FMA per element.
+// Real OTF slabs are laid out in sub-blocks of CS columns, [sub][y][CS]; `otf` points at the
+// thread's sub-block and column: &slab[(c / CS) * CS * L + c % CS] (sub-block CTAs: &slab[c]).
 template <class P, bool ACCUMULATE>
-LSTED_HD void col_otf_product_real(ColRegs<P>& r, int t, int c, const typename P::T* otf) {
+LSTED_HD void col_otf_product_real(ColRegs<P>& r, int t, const typename P::T* otf) {
     typedef typename P::Fwd F;
     typedef typename P::T T;
     LSTED_UNROLL
@@ -185,7 +202,7 @@ LSTED_HD void col_otf_product_real(ColRegs<P>& r, int t, int c, const typename P
         if (j < F::NC) {
             LSTED_UNROLL
             for (int q = 0; q < F::RC; ++q) {
-                const T o = otf[(size_t)(j + q * F::NC) * P::C + c];
+                const T o = otf[(size_t)(j + q * F::NC) * P::CS];
                 if (ACCUMULATE) r.keep[m * F::RC + q] = fma_real(r.v[m * F::RC + q], o, r.keep[m * F::RC + q]);
                 else r.v[m * F::RC + q] = scale(r.keep[m * F::RC + q], o);
             }

@@ -42,9 +42,9 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
         MA = ceil_div(NA, NT), MB = ceil_div(NB, NT), MC = ceil_div(NC, NT),
         // exchange pitches (brute-forced over the access patterns of load_b / pass_c,
         // scripts/smem_bank_conflicts.py): RA = 16 is conflict-free with PA odd, PB = 0 (mod 16);
-        // RA = 15 wants PB = 15 (mod 16) (and PA = 3 (mod 16) for 8-byte elements: also conflict-free
-        // for the 4 interleaved sequences of a column CTA)
-        PA = (RA % 16 == 15 && NA % 16 == 0 && sizeof(V) == 8) ? NA + 3 : ((NA % 2) ? NA : NA + 1),
+        // RA = 15 wants PB = 15 (mod 16) (and PA = 7 (mod 16) for 8-byte elements: also conflict-free
+        // for the 4 or 2 interleaved sequences of a column CTA; 3 (mod 16) conflicts with 2)
+        PA = (RA % 16 == 15 && NA % 16 == 0 && sizeof(V) == 8) ? NA + 7 : ((NA % 2) ? NA : NA + 1),
         PB = (RA % 16 == 0) ? pitch_congruent(NB, 0)
            : (RA % 16 == 15) ? pitch_congruent(NB, 15) : ((NB % 2) ? NB : NB + 1),
         SEQ = imax(imax(RA * PA, RB * PB), L),      // shared elements per sequence

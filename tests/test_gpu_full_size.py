@@ -128,7 +128,7 @@ def test_poisson_moments_at_full_size(setup):
 # update adds its own fp32 round-off, so the budget grows with the iteration count
 # (hard part 8).  Measured values are printed and written to
 # gpurun_out/parity_r02.json by these tests.
-TOL_ITER = {1: 1e-5, 2: 2e-5, 8: 5e-5, 64: 2e-4}
+TOL_ITER = {1: 1e-5, 2: 1e-5, 8: 1e-5, 64: 2e-5}   # measured on B200: 2e-7, 3e-7, 9e-7, 7e-6 (profiles/r02_parity_measured.json)
 _measured = {}
 
 
@@ -203,7 +203,7 @@ def test_objects_O2_O3_create_inject_iterate_both_clip_orders(setup, name):
             assert np.isfinite(got).all()
             err = rel_l2(got, est[n_it])
             _record('estimate_%s_iter%d_exact_clip%d_fp32' % (name, n_it, exact), err)
-            assert err < TOL_ITER[n_it] * (1 if n_it == 1 else 1), (name, exact, n_it, err)
+            assert err < TOL_ITER[n_it], (name, exact, n_it, err)
     h.set_option('exact_clip', 0)
     h.set_option('forget_normalization', 1)
 
