@@ -192,6 +192,9 @@ LSTED_HD void col_otf_product(ColRegs<P>& r, int t, int c, const cplx<typename P
 // the same with a REAL (centred, point-symmetric PSF) OTF: a real scaling / real FMA per element.
 // Real OTF slabs are laid out in sub-blocks of CS columns, [sub][y][CS]; `otf` points at the
 // thread's sub-block and column: &slab[(c / CS) * CS * L + c % CS] (sub-block CTAs: &slab[c]).
+template <class P> LSTED_HD const typename P::T* real_otf_at(const typename P::T* slab, int c) {
+    return slab + (size_t)(c / P::CS) * P::CS * P::L + c % P::CS;
+}
 template <class P, bool ACCUMULATE>
 LSTED_HD void col_otf_product_real(ColRegs<P>& r, int t, const typename P::T* otf) {
     typedef typename P::Fwd F;
@@ -215,8 +218,13 @@ LSTED_HD void col_otf_product_real(ColRegs<P>& r, int t, const typename P::T* ot
 struct ColGeomRuntime { enum { NY = 0, SY = 0 }; };
 template <int NY_, int SY_> struct ColGeomFixed { enum { NY = NY_, SY = SY_ }; };
 
-// RO: the OTFs are real (a.otf_real, see OtfCenterArgs) -- half the bytes to stage and stream
-template <int MODE, class P, class Ctx, class G = ColGeomRuntime, bool RO = false>
+// RO: the OTFs are real (a.otf_real, see OtfCenterArgs) -- half the bytes to stage and stream.
+// SUB (needs RO): the CTA works on a sub-block of CS of the C columns of a block
+// (`block` = xb * NSUB + sub): NT*CS threads and about 40 % of the shared memory, so TWO CTAs
+// share an SM and one runs butterflies while the other waits at its barrier; the HBM layout
+// (C-column blocks, 64-byte row-pair chunks) does not change: a sub-block reads / writes
+// whole 32-byte sectors of them.
+template <int MODE, class P, class Ctx, class G = ColGeomRuntime, bool RO = false, bool SUB = false>
 LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                             cplx<typename P::T>* smem, ColRegs<P>* regs, G = G()) {
     typedef typename P::T T;
@@ -225,33 +233,44 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     const ConvGeom& g = a.g;
     const int Ny = G::NY ? (int)G::NY : g.Ny, Ly = P::L;  // == g.Ly (checked at launch)
     const int sy = G::NY ? (int)G::SY : g.sy;
-    const int xb = block;
+    static_assert(!SUB || RO, "sub-block column CTAs read the real OTF layout");
+    enum { CC = SUB ? (int)P::CS : (int)P::C,                 // columns of this CTA
+           LSM = SUB ? (int)P::LSM_SUB : (int)P::LSM_COL,     // shared elements per sequence
+           NTHR = P::NT * CC, XELEMS = 2 * CC * LSM };
+    const int xb = SUB ? block / (int)P::NSUB : block;
+    const int sub = SUB ? block - xb * (int)P::NSUB : 0;
     const size_t slab_ly = (size_t)P::C * Ly, img_ly = (size_t)g.nxb * slab_ly;
     const size_t slab_ny = (size_t)P::C * even_rows(Ny), img_ny = (size_t)g.nxb * slab_ny;   // XB2
-    cplx<T>* const tw_s = smem + (size_t)P::COL_SMEM_ELEMS;   // base twiddles (filled below)
+    cplx<T>* const tw_s = smem + (size_t)XELEMS;   // base twiddles (filled below)
     const cplx<T>* tw = tw_s;
     cplx<T>* const buf0 = smem;
-    cplx<T>* const buf1 = smem + (size_t)P::C * P::LSM_COL;
+    cplx<T>* const buf1 = smem + (size_t)CC * LSM;
     const int K = a.K;
 
 #define LSTED_COL_IDS                                          \
-    const int t = tid / P::C, c = tid - t * P::C;              \
-    cplx<T>* const s0 = buf0 + c * P::LSM_COL;                 \
-    cplx<T>* const s1 = buf1 + c * P::LSM_COL;
+    const int t = tid / CC, cl = tid - t * CC, c = sub * CC + cl;  \
+    cplx<T>* const s0 = buf0 + cl * LSM;                       \
+    cplx<T>* const s1 = buf1 + cl * LSM;                       \
+    (void)cl;
 
     // OTF slabs are staged in shared memory by the bulk-copy engine: the slab of
     // orientation k+1 is requested as soon as every thread is done with slab k and
     // lands while the transform of k runs (no registers, no per-thread copy work).
     const bool stage = LSTED_COL_STAGE_OTF != 0;
     cplx<T>* const otf_s = tw_s + P::COL_TW;
-    mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
-    // one OTF slab: complex, or real when RO (`otf0` then counts T elements)
+    mbar_t* const mbar = SUB ? (mbar_t*)((T*)otf_s + (size_t)P::CS * Ly)
+                             : (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
+    // one OTF slab: complex, or real when RO (`otf0` then counts T elements; a sub-block's
+    // slab is the contiguous [Ly][CS] piece of the block's [NSUB][Ly][CS])
     typedef typename std::conditional<RO, T, cplx<T> >::type OtfT;
-    const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(OtfT));
-    const OtfT* otf0 = (RO ? (const OtfT*)a.otf_real : (const OtfT*)a.otf) + (size_t)xb * slab_ly;
+    const unsigned slab_bytes = (unsigned)((SUB ? (size_t)P::CS * Ly : slab_ly) * sizeof(OtfT));
+    const OtfT* otf0 = (RO ? (const OtfT*)a.otf_real : (const OtfT*)a.otf) + (size_t)xb * slab_ly +
+                       (SUB ? (size_t)sub * P::CS * Ly : 0);
+    // this thread's column inside a staged / streamed real slab
+#define LSTED_OTF_AT(base) (SUB ? (const T*)(base) + cl : real_otf_at<P>((const T*)(base), c))
     cx.phase(regs, [&](int tid, ColRegs<P>& r) {
         // (hoisting base twiddles into registers costs spills at 96 registers / 576 threads)
-        if (tid < P::COL_TW) tw_s[tid] = a.tw[tid];
+        if (tid < P::COL_TW) tw_s[tid] = a.tw[tid];   // (NTHR >= COL_TW)
         if (MODE == COL_HT) {
             LSTED_UNROLL
             for (int i = 0; i < P::NKEEP; ++i) r.keep[i] = mk<T>(0, 0);
@@ -279,7 +298,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                 // HBM -> L2 ahead of the bulk copy (staged) or of the loads (direct)
                 const int ahead = stage ? 2 : 1;
                 if (k + ahead < K)
-                    prefetch_l2_range(otf0 + (size_t)(k + ahead) * img_ly, slab_bytes, tid, P::COL_THREADS);
+                    prefetch_l2_range(otf0 + (size_t)(k + ahead) * img_ly, slab_bytes, tid, NTHR);
                 if (k == 0) {
                     F::pass_c(r.v, t, s1, tw);
                     LSTED_UNROLL
@@ -291,10 +310,10 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                 if (k < K) {
                     if (stage) {
                         mbar_wait(mbar, (unsigned)(k & 1));
-                        if (RO) col_otf_product_real<P, false>(r, t, c, (const T*)otf_s);
+                        if (RO) col_otf_product_real<P, false>(r, t, LSTED_OTF_AT(otf_s));
                         else col_otf_product<P, false>(r, t, c, otf_s, false);
                     } else {
-                        if (RO) col_otf_product_real<P, false>(r, t, c, (const T*)(otf0 + (size_t)k * img_ly));
+                        if (RO) col_otf_product_real<P, false>(r, t, LSTED_OTF_AT(otf0 + (size_t)k * img_ly));
                         else col_otf_product<P, false>(r, t, c, (const cplx<T>*)(otf0 + (size_t)k * img_ly), false);
                     }
                     I::pass_a(r.v, t, s0);
@@ -318,22 +337,22 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
             LSTED_COL_IDS
             if (k + 1 < K && !a.src_same)
                 prefetch_l2_range(src0 + (size_t)(k + 1) * img_ny, slab_ny * sizeof(cplx<T>), tid,
-                                  P::COL_THREADS);
+                                  NTHR);
             if (stage) {
                 // slab m is consumed in iteration m+1; slab k is requested once slab k-1 is done with
-                if (k + 1 < K) prefetch_l2_range(otf0 + (size_t)(k + 1) * img_ly, slab_bytes, tid, P::COL_THREADS);
+                if (k + 1 < K) prefetch_l2_range(otf0 + (size_t)(k + 1) * img_ly, slab_bytes, tid, NTHR);
                 if (tid == 0 && k == 0) bulk_load(otf_s, otf0, slab_bytes, mbar);
             } else if (k < K) {   // product k happens at the start of the next phase
-                prefetch_l2_range(otf0 + (size_t)k * img_ly, slab_bytes, tid, P::COL_THREADS);
+                prefetch_l2_range(otf0 + (size_t)k * img_ly, slab_bytes, tid, NTHR);
             }
             if (k > 0) {
                 F::pass_c(r.v, t, s1, tw);
                 if (stage) {
                     mbar_wait(mbar, (unsigned)((k - 1) & 1));
-                    if (RO) col_otf_product_real<P, true>(r, t, c, (const T*)otf_s);
+                    if (RO) col_otf_product_real<P, true>(r, t, LSTED_OTF_AT(otf_s));
                     else col_otf_product<P, true>(r, t, c, otf_s, k == 1);
                 } else {
-                    if (RO) col_otf_product_real<P, true>(r, t, c, (const T*)(otf0 + (size_t)(k - 1) * img_ly));
+                    if (RO) col_otf_product_real<P, true>(r, t, LSTED_OTF_AT(otf0 + (size_t)(k - 1) * img_ly));
                     else col_otf_product<P, true>(r, t, c, (const cplx<T>*)(otf0 + (size_t)(k - 1) * img_ly), k == 1);
                 }
             }
@@ -367,6 +386,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
         col_store_inv_c<P>(r.v, t, c, dst, sy, Ny);
     });
 #undef LSTED_COL_IDS
+#undef LSTED_OTF_AT
 }
 
 // ---------------------------------------------------------------------------
@@ -454,7 +474,7 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
                 if (k > 0) {
                     F::pass_c(r.v, t, s1, tw);
                     mbar_wait(mbar, (seq + (unsigned)(k - 1)) & 1u);
-                    if (RO) col_otf_product_real<P, true>(r, t, c, (const T*)otf_s);
+                    if (RO) col_otf_product_real<P, true>(r, t, real_otf_at<P>((const T*)otf_s, c));
                     else col_otf_product<P, true>(r, t, c, otf_s, k == 1);
                 }
                 if (k < K) {
