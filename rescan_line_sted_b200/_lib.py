@@ -241,7 +241,9 @@ class DeconvHandle:
         self.lib.call('lsted_deconv_iterate', self._h, int(n))
 
     def get(self, which, k=0):
-        out = np.empty((1, self.Ny, self.Nx), dtype=np.float64)
+        # large results land in recycled page-locked buffers (DMA at PCIe speed straight into
+        # the array the caller gets; a fresh pageable array costs page faults + a staged copy)
+        out = pooled_pinned_empty((1, self.Ny, self.Nx), lib=self.lib)
         self.lib.call('lsted_deconv_get', self._h, which, k,
                       out.ctypes.data_as(c_double_p))
         return out
@@ -300,6 +302,61 @@ def pinned_empty(shape, dtype=np.float64):
     arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
     _pinned_keepalive[arr.ctypes.data] = ptr
     return arr
+
+
+class _PinnedBlock:
+    """Owner of one page-locked buffer handed out as a numpy array (through the array
+    interface, so every view keeps it alive); when the last view dies the buffer goes back
+    to the pool instead of to cudaFreeHost."""
+
+    def __init__(self, lib, ptr, nbytes, shape, dtype):
+        self._lib, self._ptr, self._nbytes = lib, ptr, nbytes
+        self.__array_interface__ = {'shape': tuple(shape), 'typestr': np.dtype(dtype).str,
+                                    'data': (ptr.value, False), 'version': 3}
+
+    def __del__(self):
+        try:
+            _pinned_pool_release(self._lib, self._ptr, self._nbytes)
+        except Exception:   # interpreter shutdown
+            pass
+
+
+_pinned_pool = {}                 # nbytes -> [free c_void_p, ...]
+_pinned_pool_stats = {'outstanding': 0, 'pooled': 0}
+PINNED_POOL_MIN_BYTES = 1 << 20   # smaller results: plain numpy arrays
+PINNED_POOL_MAX_BYTES = 2 << 30   # page-locked bytes handed out + kept; beyond: plain arrays
+
+
+def _pinned_pool_release(lib, ptr, nbytes):
+    _pinned_pool_stats['outstanding'] -= nbytes
+    if _pinned_pool_stats['pooled'] + nbytes <= PINNED_POOL_MAX_BYTES // 2:
+        _pinned_pool.setdefault((id(lib), nbytes), []).append(ptr)
+        _pinned_pool_stats['pooled'] += nbytes
+    else:
+        lib.cdll.lsted_host_free(ptr)
+
+
+def pooled_pinned_empty(shape, dtype=np.float64, lib=None):
+    """Fresh numpy array for a result read back from the GPU.  At least 1 MB: page-locked
+    memory from a recycling pool (returned to it when the array is garbage-collected)."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    st = _pinned_pool_stats
+    lib = lib or get()
+    if (nbytes < PINNED_POOL_MIN_BYTES or st['outstanding'] + nbytes > PINNED_POOL_MAX_BYTES
+            or not hasattr(lib.cdll, 'lsted_host_alloc')):   # (the CPU replay has none)
+        return np.empty(shape, dtype=dtype)
+    free = _pinned_pool.get((id(lib), nbytes))
+    if free:
+        ptr = free.pop()
+        st['pooled'] -= nbytes
+    else:
+        ptr = ctypes.c_void_p()
+        try:
+            lib.call('lsted_host_alloc', ctypes.byref(ptr), nbytes)
+        except RuntimeError:
+            return np.empty(shape, dtype=dtype)
+    st['outstanding'] += nbytes
+    return np.asarray(_PinnedBlock(lib, ptr, nbytes, shape, dtype))
 
 
 def pinned_free(arr):

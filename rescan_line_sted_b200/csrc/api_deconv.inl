@@ -128,6 +128,7 @@ extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double
     if (!strcmp(name, "row_dual")) { h->bk->set_row_dual(value != 0); return LSTED_OK; }
     if (!strcmp(name, "row_plan2")) { h->bk->set_row_plan2(value != 0); return LSTED_OK; }
     if (!strcmp(name, "row_tma")) { h->bk->set_row_tma((int)value); return LSTED_OK; }
+    if (!strcmp(name, "col_sub")) { h->bk->set_col_sub(value != 0); return LSTED_OK; }
     if (!strcmp(name, "real_otf")) { h->bk->set_real_otf(value != 0); return LSTED_OK; }   // before set_psfs
     if (!strcmp(name, "profile")) { h->bk->set_profile(value != 0); return LSTED_OK; }
     return set_error(LSTED_ERR_ARG, std::string("unknown option ") + name);

@@ -342,10 +342,11 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
 // part has to be stored and streamed (half the OTF bytes of the column kernels).
 template <typename T> struct OtfCenterArgs {
     cplx<T>* otf;         // in/out: [K][nxb][Ly][C]
-    T* otf_real;          // out: real part, same indexing
+    T* otf_real;          // out: real part, [K][nxb][C/CS][Ly][CS] (CS = C: same indexing)
     const cplx<T>* tw_y;  // exp(-2 pi i m / Ly)
     const cplx<T>* tw_x;  // exp(-2 pi i m / Lx)
     int nxb, Ly, Lx, C, cy, cx;
+    int CS;               // columns per sub-block of the real array (set by the backend)
     size_t n;             // K * nxb * Ly * C
 };
 template <typename T> LSTED_HD void otf_center_apply(const OtfCenterArgs<T>& a, size_t i) {
@@ -357,7 +358,9 @@ template <typename T> LSTED_HD void otf_center_apply(const OtfCenterArgs<T>& a, 
     const cplx<T> ph = conj(a.tw_y[((size_t)y * a.cy) % a.Ly] * a.tw_x[((size_t)x * a.cx) % a.Lx]);
     const cplx<T> v = a.otf[i] * ph;
     a.otf[i] = v;
-    a.otf_real[i] = v.x;
+    // real array: each sub-block of CS columns contiguous (one bulk copy per sub-block CTA)
+    const size_t blk = i / ((size_t)a.Ly * a.C);
+    a.otf_real[((blk * (a.C / a.CS) + c / a.CS) * a.Ly + y) * a.CS + c % a.CS] = v.x;
 }
 
 }  // namespace lsted

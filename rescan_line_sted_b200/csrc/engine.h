@@ -138,7 +138,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
             if (!otf_real) otf_real = (T*)bk.alloc(sizeof(T) * otf_elems(g) * K);
             OtfCenterArgs<T> oc;
             oc.otf = otf; oc.otf_real = otf_real; oc.tw_y = tw_y; oc.tw_x = tw_x;
-            oc.nxb = g.nxb; oc.Ly = g.Ly; oc.Lx = g.Lx; oc.C = g.C;
+            oc.nxb = g.nxb; oc.Ly = g.Ly; oc.Lx = g.Lx; oc.C = g.C; oc.CS = g.C;
             oc.cy = (ny - 1) / 2; oc.cx = (nx - 1) / 2;
             oc.n = otf_elems(g) * K;
             bk.otf_center(oc);

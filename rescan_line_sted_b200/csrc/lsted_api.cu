@@ -70,10 +70,13 @@ struct DeviceCtx {
 #ifndef LSTED_FAST_C32
 #define LSTED_FAST_C32 4
 #endif
+#ifndef LSTED_FAST_CS32
+#define LSTED_FAST_CS32 2   // columns per sub-block column CTA (real OTFs): 2 CTAs per SM
+#endif
 #ifndef LSTED_FAST_PR
 #define LSTED_FAST_PR 1
 #endif
-typedef lsted::FastPlan<float, 16, 9, 15, 144, LSTED_FAST_C32, LSTED_FAST_PR> Plan2160f;
+typedef lsted::FastPlan<float, 16, 9, 15, 144, LSTED_FAST_C32, LSTED_FAST_PR, LSTED_FAST_CS32> Plan2160f;
 typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 
 // G: image geometry known at compile time (the 2048-wide / 107-wide-PSF headline case) or not
@@ -116,6 +119,16 @@ row_mid_dual_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
 
 typedef lsted::ColGeomFixed<2048, 53> ColGeom2048;
 typedef lsted::ColGeomFixed<2048, 0> ColGeom2048c;    // centred real OTFs: no crop offset
+// sub-block column CTAs (real OTFs): CS of the C columns of a block, two CTAs per SM
+template <int MODE, class P, class G = lsted::ColGeomRuntime>
+__global__ void __launch_bounds__(P::SUB_THREADS, 2)
+col_sub_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DeviceCtx cx;
+    lsted::ColRegs<P> r;
+    lsted::col_fast_body<MODE, P, DeviceCtx, G, true, true>(cx, blockIdx.x, a,
+                                  reinterpret_cast<lsted::cplx<typename P::T>*>(smem_raw), &r);
+}
 template <int MODE, class P, class G = lsted::ColGeomRuntime, bool RO = false>
 __global__ void __launch_bounds__(P::COL_THREADS, 1)
 col_fast_kernel(const __grid_constant__ lsted::ColArgs<typename P::T> a) {
@@ -291,6 +304,8 @@ class CudaBackend {
         if (plan2) row_plan2_ = atoi(plan2) != 0;
         const char* rt = getenv("LSTED_ROW_TMA");       // A/B switch: spectrum chunks by tensor-map copies
         if (rt) row_tma_ = atoi(rt);   // 0 off, 1 tensor-map copies, 2 + "lean" ROW_MID
+        const char* cs = getenv("LSTED_COL_SUB");       // A/B switch, same as option "col_sub"
+        if (cs) col_sub_ = atoi(cs) != 0;
         const char* ro = getenv("LSTED_REAL_OTF");      // A/B switch: centred real OTFs (read at set_psfs)
         if (ro) real_otf_ = atoi(ro) != 0;
         const char* pf = getenv("LSTED_PREFETCH");      // A/B switch, same as option "prefetch"
@@ -396,7 +411,9 @@ class CudaBackend {
         return use_fast_ && real_otf_ &&
                (cplx_bytes == 8 ? plan_fits_cols<Plan2160f>(g) : plan_fits_cols<Plan2160d>(g));
     }
-    template <typename T> void otf_center(const lsted::OtfCenterArgs<T>& a) {
+    template <typename T> void otf_center(const lsted::OtfCenterArgs<T>& a0) {
+        lsted::OtfCenterArgs<T> a = a0;   // the real array is read by the compile-time plans only
+        a.CS = sizeof(T) == 4 ? (int)Plan2160f::CS : (int)Plan2160d::CS;
         before(KK_EW);
         otf_center_kernel<T><<<num_sms_ * 8, 256, 0, stream_>>>(a);
         after();
@@ -599,6 +616,7 @@ class CudaBackend {
         if (a.otf_real) {   // centred real OTFs
             const bool fixed_c = sizeof(typename P::T) == 4 && a.g.Ny == (int)ColGeom2048c::NY &&
                                  a.g.sy == 0 && a.rows_in == a.g.Ny;
+            if (launch_col_sub<MODE, P>(grid, a, kind, fixed_c)) return;
             ensure_smem(col_fast_kernel<MODE, P, lsted::ColGeomRuntime, true>, smem);
             if (sizeof(typename P::T) == 4) ensure_smem(col_fast_kernel<MODE, P, ColGeom2048c, true>, smem);
             before(kind);
@@ -612,6 +630,24 @@ class CudaBackend {
         else col_fast_kernel<MODE, P><<<grid, P::COL_THREADS, smem, stream_>>>(a);
         after();
     }
+    // plans with sub-blocks (CS < C): NSUB CTAs per column block, two resident per SM
+    template <int MODE, class P>
+    typename std::enable_if<(P::CS < P::C), bool>::type
+    launch_col_sub(int grid, const lsted::ColArgs<typename P::T>& a, int kind, bool fixed_c) {
+        if (!col_sub_) return false;
+        const size_t smem = lsted::fast_col_sub_smem_bytes<P>();
+        ensure_smem(col_sub_kernel<MODE, P>, smem);
+        ensure_smem(col_sub_kernel<MODE, P, ColGeom2048c>, smem);
+        before(kind);
+        if (fixed_c) col_sub_kernel<MODE, P, ColGeom2048c><<<grid * P::NSUB, P::SUB_THREADS, smem, stream_>>>(a);
+        else col_sub_kernel<MODE, P><<<grid * P::NSUB, P::SUB_THREADS, smem, stream_>>>(a);
+        after();
+        return true;
+    }
+    template <int MODE, class P>
+    typename std::enable_if<!(P::CS < P::C), bool>::type
+    launch_col_sub(int, const lsted::ColArgs<typename P::T>&, int, bool) { return false; }
+    void set_col_sub(bool on) { col_sub_ = on; }
     template <int MODE> void launch_row2(const lsted::RowArgs<float>& a, int kind) {
         typedef Plan2160f2 P;
         const size_t smem = lsted::fast_row2_smem_bytes<P>(MODE);
@@ -758,6 +794,7 @@ class CudaBackend {
     std::vector<void*> p2p_opened_;
     int p2p_rank_ = 0, p2p_world_ = 1; unsigned p2p_epoch_ = 0;
     bool real_otf_ = true;
+    bool col_sub_ = true;     // sub-block column CTAs (2 per SM) where the plan has them
     int row_tma_ = 2;   // 0 off, 1 tensor-map spectrum copies, 2 also the two-buffer ROW_MID (6 CTAs/SM)
     bool prefetch_ = true;
     int prefetch_quarters_ = 1;   // row-kernel L2 prefetch distance in CTAs per SM.  With per-thread

@@ -10,7 +10,7 @@ $B > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
     --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/ncu_list_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k 'regex:(row_(fast_)?kernel<\(int\)3|col_(fast_)?kernel<\(int\)1|col_(fast_)?kernel<\(int\)2|row_(fast_)?kernel<\(int\)4)' \
+    -k 'regex:(row_(fast_)?kernel<\(int\)3|col_(fast_|sub_)?kernel<\(int\)1|col_(fast_|sub_)?kernel<\(int\)2|row_(fast_)?kernel<\(int\)4)' \
     -s 3 -c 5 -o gpurun_out/prof_$TAG $B > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_full_$TAG.log
 ls -la gpurun_out | tail -8

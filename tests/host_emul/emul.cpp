@@ -39,7 +39,7 @@ struct HostCtx {
     template <class R, class F> void phase_nosync(R* regs, F f) { phase(regs, f); }
 };
 
-typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 1> Plan2160f;
+typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 1, 2> Plan2160f;
 typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
 template <typename T> struct PlanFor;
 template <> struct PlanFor<float> { typedef Plan2160f type; };
@@ -56,6 +56,8 @@ static int g_dual_launches = 0;
 static int g_row2_launches = 0;
 static int g_real_otf_launches = 0;
 static int g_row_tma_launches = 0;
+static int g_col_sub_launches = 0;
+extern "C" int emul_col_sub_launches(void) { return g_col_sub_launches; }
 extern "C" int emul_row_tma_launches(void) { return g_row_tma_launches; }
 extern "C" int emul_real_otf_launches(void) { return g_real_otf_launches; }
 extern "C" int emul_row2_launches(void) { return g_row2_launches; }
@@ -111,7 +113,9 @@ class HostBackend {
         return use_fast_ && real_otf_ && g.Ly == Plan2160f::L &&
                g.C == (cplx_bytes == 8 ? (int)Plan2160f::C : (int)Plan2160d::C);
     }
-    template <typename T> void otf_center(const lsted::OtfCenterArgs<T>& a) {
+    template <typename T> void otf_center(const lsted::OtfCenterArgs<T>& a0) {
+        lsted::OtfCenterArgs<T> a = a0;
+        a.CS = (int)PlanFor<T>::type::CS;
         for (size_t i = 0; i < a.n; ++i) lsted::otf_center_apply<T>(a, i);
     }
     void set_real_otf(bool on) { real_otf_ = on; }
@@ -122,6 +126,7 @@ class HostBackend {
         return use_fast_ && row_tma_ && cplx_bytes == 8 && g.Lx == Plan2160f::L && g.C == (int)Plan2160f::C;
     }
     void set_row_tma(int v) { row_tma_ = v; }
+    void set_col_sub(bool on) { col_sub_ = on; }
     void p2p_export(void*, void*, void*, char*) { throw std::string("peer memory needs GPUs"); }
     void p2p_attach(int, int, const char*, size_t) { throw std::string("peer memory needs GPUs"); }
     bool p2p_ready(const lsted::ConvGeom&, int) const { return false; }
@@ -235,6 +240,24 @@ class HostBackend {
     }
     template <int MODE, typename T> void launch_col(int grid, const lsted::ColArgs<T>& a) {
         typedef typename PlanFor<T>::type P;
+        if (use_fast_ && MODE != lsted::COL_OTF && a.g.Ly == P::L && a.g.C == P::C && a.otf_real &&
+            (int)P::CS < (int)P::C && col_sub_) {
+            // sub-block column CTAs (two per SM on the GPU)
+            ++g_col_sub_launches;
+            ++g_real_otf_launches;
+#pragma omp parallel
+            {
+                std::vector<lsted::cplx<T> > smem(lsted::fast_col_sub_smem_bytes<P>() / sizeof(lsted::cplx<T>) + 1);
+                std::vector<lsted::ColRegs<P> > regs(P::SUB_THREADS);
+                HostCtx cx;
+                cx.nthreads = P::SUB_THREADS;
+#pragma omp for schedule(dynamic)
+                for (int b = 0; b < grid * (int)P::NSUB; ++b)
+                    lsted::col_fast_body<(MODE == lsted::COL_OTF ? lsted::COL_H : MODE), P, HostCtx,
+                                         lsted::ColGeomRuntime, true, true>(cx, b, a, smem.data(), regs.data());
+            }
+            return;
+        }
         if (use_fast_ && MODE != lsted::COL_OTF && a.g.Ly == P::L && a.g.C == P::C) {
 #pragma omp parallel
             {
@@ -310,6 +333,7 @@ class HostBackend {
     bool row_plan2_ = false;
     bool real_otf_ = true;
     int row_tma_ = 2;
+    bool col_sub_ = true;
 };
 
 #define LSTED_BACKEND HostBackend

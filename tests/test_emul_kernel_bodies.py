@@ -338,6 +338,37 @@ def test_centred_real_otfs_for_point_symmetric_psfs(lib, monkeypatch, precision,
     assert rel_l2(res[1]['H'], res[0]['H']) < tol
 
 
+def test_sub_block_column_ctas_are_bit_identical(lib):
+    """fp32 column kernels on real OTFs run as sub-block CTAs (2 of the 4 columns of a block,
+    two CTAs per SM on the GPU; option `col_sub`): same butterflies on the same numbers, so
+    the results agree bit for bit with the whole-block CTAs, and with the oracle."""
+    rng = np.random.default_rng(5)
+    shape = (2090, 10)
+    half = rng.random((2, 4, 5))
+    psfs = np.concatenate([half, rng.random((2, 1, 5)), half[:, ::-1, ::-1]], axis=1)   # 9 x 5
+    psfs[:, 4, :] = 0.5 * (psfs[:, 4, :] + psfs[:, 4, ::-1])
+    obj = rng.random((1,) + shape) + 0.05
+    y = rng.random((2,) + shape) + 0.1
+    res, launches = {}, {}
+    for sub in (1, 0):
+        before = lib.cdll.emul_col_sub_launches()
+        h = _lib.DeconvHandle(lib, psfs, shape, precision=32)
+        h.set_option('col_sub', sub)
+        assert h.info().Ly == 2160
+        res[sub] = dict(H=h.H(obj), Ht=h.Ht(y, True))
+        h.create_data(obj, 1e5 * obj.size, 9)
+        h.iterate(2)
+        res[sub]['est'] = h.get(_lib.ESTIMATE)
+        launches[sub] = lib.cdll.emul_col_sub_launches() - before
+        h.close()
+    assert launches[1] >= 6 and launches[0] == 0
+    for key in ('H', 'Ht', 'est'):
+        assert np.array_equal(res[1][key], res[0][key]), key
+    o = orc.Deconvolver([p[None] for p in psfs])
+    assert rel_l2(res[1]['H'], np.concatenate(o.H(obj))) < 1e-5
+    assert rel_l2(res[1]['Ht'], o.H_t([v[None] for v in y])) < 1e-5
+
+
 def test_peer_reduction_block_order(lib):
     """Every rank walks all column blocks exactly once, the ones it does not own first
     (ascending), then its own (xb % world == rank): the order the fused H_t reduction relies

@@ -166,3 +166,34 @@ def test_attribute_protocol(st, tmp_path):
     d.record_iteration()
     assert os.path.exists(str(tmp_path) + '/a_estimate_history.tif')
     assert os.path.exists(str(tmp_path) + '/a_noisy_measurement.tif')
+
+
+def test_large_results_come_back_in_recycled_pinned_buffers():
+    """Arrays of >= 1 MB read back from the handle live in page-locked memory from a pool:
+    they behave like any numpy array, stay valid while referenced, and their buffer is
+    reused once they are garbage-collected."""
+    import gc
+    from rescan_line_sted_b200 import _lib
+    lib = _lib.get()
+    rng = np.random.default_rng(0)
+    psfs = rng.random((1, 5, 5))
+    x = rng.random((1, 512, 512)) + 0.1          # 2 MB results
+    h = _lib.DeconvHandle(lib, psfs, x.shape[1:], precision=64)
+    h.create_data(x, None, 3)
+    a = h.get(_lib.TRUE_OBJECT)
+    assert a.dtype == np.float64 and a.shape == x.shape and a.flags.c_contiguous and a.flags.writeable
+    assert np.allclose(a, x, rtol=1e-14)
+    addr = a.ctypes.data
+    b = h.get(_lib.NOISELESS, 0)
+    assert b.ctypes.data != addr                  # `a` is alive: not handed out twice
+    keep = a[:, 10:20]                            # a view keeps the buffer alive
+    del a
+    gc.collect()
+    c = h.get(_lib.NOISELESS, 0)
+    assert c.ctypes.data != addr and np.allclose(keep, x[:, 10:20], rtol=1e-14)
+    del keep
+    gc.collect()
+    d = h.get(_lib.NOISELESS, 0)
+    assert d.ctypes.data == addr                  # recycled
+    assert np.array_equal(d, b)
+    h.close()

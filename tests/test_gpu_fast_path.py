@@ -73,3 +73,27 @@ def test_tensor_map_row_staging_is_bit_identical(shape, K):
     assert np.isfinite(est[1]).all() and est[1].min() > 0
     assert np.array_equal(est[0], est[1])
     assert np.array_equal(est[0], est[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape,K', [((2048, 64), 2), ((2048, 2048), 3), ((2001, 1030), 2)])
+def test_sub_block_column_ctas_are_bit_identical(shape, K):
+    """Column kernels on centred real OTFs as sub-block CTAs (2 of 4 columns, two CTAs per
+    SM; option `col_sub`, default on) against the whole-block CTAs: bit-identical estimates."""
+    from rescan_line_sted_b200 import _lib
+    lib = _lib.get()
+    rng = np.random.default_rng(8)
+    half = rng.random((K, 10, 21))
+    psfs = np.concatenate([half, rng.random((K, 1, 21)), half[:, ::-1, ::-1]], axis=1)
+    psfs[:, 10, :] = 0.5 * (psfs[:, 10, :] + psfs[:, 10, ::-1])
+    x = rng.random((1,) + shape) + 0.1
+    est = {}
+    for sub in (0, 1):
+        h = _lib.DeconvHandle(lib, psfs, shape, precision=32)
+        h.set_option('col_sub', sub)
+        h.create_data(x, 1e6 * x.size, 1)
+        h.iterate(3)
+        est[sub] = h.get(_lib.ESTIMATE)
+        h.close()
+    assert np.isfinite(est[1]).all() and est[1].min() > 0
+    assert np.array_equal(est[0], est[1])
