@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp64'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fp64', action='store_true', help='skip the fp64 companion figure')
+    ap.add_argument('--no-sweep', action='store_true', help='skip the config-3 PSF sweep record')
     ap.add_argument('--shard', default='frames', choices=['frames', 'orientations'],
                     help='N>1: independent frames per GPU (weak scaling, no collective) or the '
                          'K orientations of every frame split over the GPUs (strong scaling, one '
@@ -515,6 +516,16 @@ def main():
                        'note': 'same frame(%d) with the engine in fp64 (the reference\'s dtype)' % n_iter}
         h64.close()
 
+    # ---- config 3: the 64-point PSF sweep, points dealt over the GPUs ----
+    sweep_record = None
+    if not args.no_sweep and not by_orientation:
+        sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+        import sweep_times
+        sweep_record = sweep_times.sweep_benchmark(rank, world, dist, repeats=3, big=16)
+        sweep_record['note'] = ('psf_report_batch (one fused launch per rank: illumination, in-kernel '
+                                'lmdif width fits, rescan PSF, doses), points dealt round-robin over '
+                                'the GPUs, reports gathered once; wall clock, max over ranks')
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -591,6 +602,8 @@ def main():
     extra = {}
     if fp64_record:
         extra['fp64'] = fp64_record
+    if sweep_record:
+        extra['config3_sweep'] = sweep_record
     if orientation_record:
         line['orientation_sharded'] = orientation_record
     if extra:

@@ -61,6 +61,28 @@ int lsted_psf_rescan(int device, int batch, int n, const double* taps, int radiu
                      const double* sted_rows, const int* ratios, double* emission,
                      double* rescan, double* descan, double* wide);
 
+/* psf_report (:75-166) for a batch of operating points without returning to the host in
+ * between: illumination, the Gaussian width fits (get_width :653-668, a Levenberg-Marquardt
+ * fit from the reference's start (1, n/2, 1), run on the device to the fp64 floor), the
+ * integer rescan ratio the fit decides (:252-256), rescan / descan PSFs and the dose sums
+ * (:134-144, per pulse).  One CTA per point; every point has its own grid size n[b] and FIR
+ * taps (taps[b][0 .. 2*radius[b]], rows `tap_stride` apart).
+ * scalars [batch][16]: 0 excitation sigma, 1 STED sigma, 2 rescan sigma (line), 3 real and
+ * 4 rounded rescan ratio (line), 5 excitation dose, 6 depletion dose, 7 emission (all per
+ * pulse), 8 function evaluations of the fits, 9 fit status (0 = every fit ended with MINPACK
+ * info 1..4, which is what scipy accepts), 10-12 centre-row-maximum checks
+ * (:105-106, :120).  psfs: NULL, or [batch][7][nmax*nmax] (nmax = max n[b]; plane i of point
+ * b holds n[b]*n[b] packed values): excitation, depletion, excitation_fraction,
+ * depletion_fraction, sted, rescan_sted, descan_sted (the last two for lines only).       */
+int lsted_psf_report_batch(int device, int psf_type, int batch, const int* n, const int* radius,
+                           const double* taps, int tap_stride, const double* blur_sigma,
+                           const double* excitation_brightness, const double* depletion_brightness,
+                           double* scalars, double* psfs);
+
+/* get_width (:653-668) for a batch of profiles rows[batch][n]: the same in-kernel lmdif.
+ * out [batch][5]: A, mu, sigma, function evaluations, MINPACK info (scipy accepts 1..4). */
+int lsted_gauss_fit(int device, int batch, int n, const double* rows, double* out);
+
 /* Orientation step of Deconvolver's caller (line_sted_figure_2.py:264-272, used at
  * :244-247): rotate one plane [n0][n1] to `batch` orientations like
  * scipy.ndimage.rotate(order=3, mode='constant', cval=0, reshape=False) and clip to

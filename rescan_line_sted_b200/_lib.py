@@ -92,6 +92,11 @@ _CORE_SIGNATURES = {
     'lsted_psf_rescan': [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
                          ctypes.c_int, c_double_p, c_int_p, c_double_p,
                          c_double_p, c_double_p, c_double_p],
+    'lsted_psf_report_batch': [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
+                               c_int_p, c_double_p, ctypes.c_int, c_double_p,
+                               c_double_p, c_double_p, c_double_p, c_double_p],
+    'lsted_gauss_fit': [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
+                        c_double_p],
     'lsted_psf_rotate': [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                          c_double_p, c_double_p, ctypes.c_double, c_double_p],
 }

@@ -938,6 +938,11 @@ PsfWorkspace& psf_workspace(int device) {
     return w;
 }
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+// dynamic shared memory above 48 KB needs the opt-in attribute (per device; cheap to repeat)
+template <class F> void psf_raise_smem(F* kernel, size_t smem) {
+    if (smem > 48 * 1024)
+        CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
 }  // namespace
 
 extern "C" int lsted_psf_illumination(int device, int psf_type, int batch, int n, const double* taps,
@@ -981,6 +986,89 @@ extern "C" int lsted_psf_illumination(int device, int psf_type, int batch, int n
         for (int b = 0; b < batch; ++b)
             for (int i = 0; i < 5; ++i)
                 memcpy(outs[i] + img * b, h_out + img * (5 * (size_t)b + i), sizeof(double) * img);
+        return LSTED_OK;
+    } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
+}
+
+extern "C" int lsted_psf_report_batch(int device, int psf_type, int batch, const int* n, const int* radius,
+                                      const double* taps, int tap_stride, const double* blur_sigma,
+                                      const double* excitation_brightness,
+                                      const double* depletion_brightness, double* scalars, double* psfs) {
+    if (!n || !radius || !taps || !blur_sigma || !excitation_brightness || !depletion_brightness || !scalars)
+        return set_error(LSTED_ERR_ARG, "null pointer");
+    if (batch < 1 || tap_stride < 1 || (psf_type != 0 && psf_type != 1))
+        return set_error(LSTED_ERR_ARG, "bad PSF arguments");
+    int nmax = 0;
+    for (int b = 0; b < batch; ++b) {
+        if (n[b] < 1 || radius[b] < 0 || 2 * radius[b] + 1 > tap_stride)
+            return set_error(LSTED_ERR_ARG, "bad PSF arguments");
+        if (n[b] > lsted::kPsfMaxN || 2 * radius[b] + 1 > lsted::kPsfMaxTaps)
+            return set_error(LSTED_ERR_ARG, "PSF grid too large for the on-chip kernel");
+        nmax = n[b] > nmax ? n[b] : nmax;
+    }
+    try {
+        select_device(device);
+        PsfWorkspace& w = psf_workspace(device);
+        // input block: taps[batch][tap_stride] | sigma | exc | dep | n | radius
+        const size_t in_doubles = (size_t)batch * tap_stride + 3 * (size_t)batch;
+        const size_t in_bytes = align256(sizeof(double) * in_doubles + 2 * sizeof(int) * batch);
+        const size_t sc_bytes = align256(sizeof(double) * lsted::kPsfReportScalars * batch);
+        const size_t plane = (size_t)nmax * nmax;
+        const size_t psf_bytes = psfs ? sizeof(double) * plane * 7 * batch : 0;
+        w.reserve(in_bytes + sc_bytes + psf_bytes);
+        double* h_in = (double*)w.host;
+        memcpy(h_in, taps, sizeof(double) * batch * tap_stride);
+        double* h_par = h_in + (size_t)batch * tap_stride;
+        memcpy(h_par, blur_sigma, sizeof(double) * batch);
+        memcpy(h_par + batch, excitation_brightness, sizeof(double) * batch);
+        memcpy(h_par + 2 * batch, depletion_brightness, sizeof(double) * batch);
+        int* h_int = (int*)(h_in + in_doubles);
+        memcpy(h_int, n, sizeof(int) * batch);
+        memcpy(h_int + batch, radius, sizeof(int) * batch);
+        double* d_in = (double*)w.dev;
+        CUDA_CHECK(cudaMemcpyAsync(d_in, h_in, sizeof(double) * in_doubles + 2 * sizeof(int) * batch,
+                                   cudaMemcpyHostToDevice, w.stream));
+        lsted::PsfReportArgs a;
+        a.psf_type = psf_type; a.nmax = nmax; a.tap_stride = tap_stride;
+        a.taps = d_in;
+        a.blur_sigma = d_in + (size_t)batch * tap_stride;
+        a.exc_brightness = a.blur_sigma + batch; a.dep_brightness = a.blur_sigma + 2 * batch;
+        a.n = (const int*)(d_in + in_doubles); a.radius = a.n + batch;
+        a.scalars = (double*)((char*)w.dev + in_bytes);
+        a.psfs = psfs ? (double*)((char*)w.dev + in_bytes + sc_bytes) : 0;
+        const size_t smem = sizeof(double) * lsted::PsfReportSmem::doubles(nmax);
+        psf_raise_smem(lsted::psf_report_kernel, smem);
+        lsted::psf_report_kernel<<<batch, lsted::kPsfThreads, smem, w.stream>>>(a);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync((char*)w.host + in_bytes, (char*)w.dev + in_bytes, sc_bytes + psf_bytes,
+                                   cudaMemcpyDeviceToHost, w.stream));
+        CUDA_CHECK(cudaStreamSynchronize(w.stream));
+        memcpy(scalars, (char*)w.host + in_bytes, sizeof(double) * lsted::kPsfReportScalars * batch);
+        if (psfs) memcpy(psfs, (char*)w.host + in_bytes + sc_bytes, psf_bytes);
+        return LSTED_OK;
+    } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
+}
+
+extern "C" int lsted_gauss_fit(int device, int batch, int n, const double* rows, double* out) {
+    if (!rows || !out) return set_error(LSTED_ERR_ARG, "null pointer");
+    if (batch < 1 || n < 3 || n > lsted::kPsfMaxN) return set_error(LSTED_ERR_ARG, "bad fit arguments");
+    try {
+        select_device(device);
+        PsfWorkspace& w = psf_workspace(device);
+        const size_t in_bytes = align256(sizeof(double) * (size_t)n * batch);
+        const size_t out_bytes = sizeof(double) * 5 * batch;
+        w.reserve(in_bytes + out_bytes);
+        memcpy(w.host, rows, sizeof(double) * (size_t)n * batch);
+        CUDA_CHECK(cudaMemcpyAsync(w.dev, w.host, sizeof(double) * (size_t)n * batch, cudaMemcpyHostToDevice, w.stream));
+        lsted::GaussFitArgs a;
+        a.n = n; a.rows = (const double*)w.dev; a.out = (double*)((char*)w.dev + in_bytes);
+        const size_t smem = sizeof(double) * lsted::PsfReportSmem::doubles(n);
+        psf_raise_smem(lsted::gauss_fit_kernel, smem);
+        lsted::gauss_fit_kernel<<<batch, lsted::kPsfThreads, smem, w.stream>>>(a);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync((char*)w.host + in_bytes, a.out, out_bytes, cudaMemcpyDeviceToHost, w.stream));
+        CUDA_CHECK(cudaStreamSynchronize(w.stream));
+        memcpy(out, (char*)w.host + in_bytes, out_bytes);
         return LSTED_OK;
     } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
 }

@@ -25,6 +25,7 @@ def build_emulator():
 
 def emulator_library():
     sigs = dict(_lib._DECONV_SIGNATURES)
-    for name in ('lsted_psf_illumination', 'lsted_psf_rescan', 'lsted_psf_rotate'):
+    for name in ('lsted_psf_illumination', 'lsted_psf_rescan', 'lsted_psf_rotate',
+                 'lsted_psf_report_batch', 'lsted_gauss_fit'):
         sigs[name] = _lib._CORE_SIGNATURES[name]
     return _lib.Library(build_emulator(), sigs)

@@ -429,6 +429,35 @@ extern "C" int lsted_psf_rescan(int, int batch, int n, const double* taps, int r
     return 0;
 }
 
+extern "C" int lsted_psf_report_batch(int, int psf_type, int batch, const int* n, const int* radius,
+                                      const double* taps, int tap_stride, const double* blur_sigma,
+                                      const double* eb, const double* db, double* scalars, double* psfs) {
+    int nmax = 0;
+    for (int b = 0; b < batch; ++b) nmax = n[b] > nmax ? n[b] : nmax;
+    if (nmax > lsted::kPsfMaxN) return set_error(LSTED_ERR_ARG, "PSF grid too large for the on-chip kernel");
+    lsted::PsfReportArgs a;
+    a.psf_type = psf_type; a.nmax = nmax; a.tap_stride = tap_stride; a.n = n; a.radius = radius;
+    a.taps = taps; a.blur_sigma = blur_sigma; a.exc_brightness = eb; a.dep_brightness = db;
+    a.scalars = scalars; a.psfs = psfs;
+    std::vector<double> scratch(lsted::PsfReportSmem::doubles(nmax));
+    lsted::PsfReportSmem sm;
+    sm.carve(scratch.data(), nmax);
+    HostCtx cx;
+    for (int b = 0; b < batch; ++b) lsted::psf_report_body(cx, b, a, &sm);
+    return 0;
+}
+
+extern "C" int lsted_gauss_fit(int, int batch, int n, const double* rows, double* out) {
+    lsted::GaussFitArgs a;
+    a.n = n; a.rows = rows; a.out = out;
+    std::vector<double> scratch(lsted::PsfReportSmem::doubles(n));
+    lsted::PsfReportSmem sm;
+    sm.carve(scratch.data(), n);
+    HostCtx cx;
+    for (int b = 0; b < batch; ++b) lsted::gauss_fit_rows_body(cx, b, a, &sm);
+    return 0;
+}
+
 extern "C" int lsted_psf_rotate(int, int batch, int n0, int n1, const double* plane,
                                const double* xform, double clip_hi, double* out) {
     const size_t img = (size_t)n0 * n1;

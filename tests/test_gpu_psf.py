@@ -75,6 +75,31 @@ def test_sweep_batch_equals_single_calls(st):
         assert one['expected_emission'] == reps[i]['expected_emission']
 
 
+@pytest.mark.parametrize('psf_type,steps', [('line', 8), ('point', 8), ('line', 25), ('point', 25)])
+def test_device_fit_restates_scipy(st, monkeypatch, psf_type, steps):
+    """Single-launch psf_report (in-kernel restatement of MINPACK lmdif = scipy curve_fit)
+    against the host-fit path on the config-3 sweep grid: rescan ratios / array shapes exact,
+    resolution factors within 1e-6 (on the GPU only exp() can differ in the last
+    place from scipy's run), doses and arrays to 1e-12."""
+    import _psf_fit_cases as cases
+    fallbacks, exact = cases.check_fused_reports_against_host_fit(
+        st, monkeypatch, psf_type, steps, tol_R=1e-6, min_exact=0)
+    print('fallbacks %d, bit-identical resolution factors %d' % (fallbacks, exact))
+    assert fallbacks <= 16
+
+
+def test_tune_psf_batch_equals_sequential(st):
+    import _psf_fit_cases as cases
+    cases.check_tune_psf_batch(st, [
+        dict(psf_type='point', scan_type='descanned', desired_resolution_improvement=2.0,
+             desired_emissions_per_molecule=4.0),
+        dict(psf_type='line', scan_type='rescanned', desired_resolution_improvement=2.2,
+             desired_emissions_per_molecule=3.0),
+        dict(psf_type='line', scan_type='descanned', desired_resolution_improvement=1.7,
+             desired_emissions_per_molecule=3.0),
+    ])
+
+
 def test_tune_psf_golden(st, golden_dir):
     with open(os.path.join(golden_dir, 'scalars.json')) as f:
         scalars = json.load(f)

@@ -85,6 +85,74 @@ def test_tune_psf_golden(st, golden_dir):
         st.tune_psf('point', 'rescanned', 2., 4.)
 
 
+@pytest.mark.parametrize('psf_type,steps', [('line', 8), ('point', 8), ('line', 12)])
+def test_device_fit_restates_scipy(st, monkeypatch, psf_type, steps):
+    """The fused single-launch psf_report: its widths come from a step-for-step restatement
+    of MINPACK's lmdif (what scipy's curve_fit runs) inside the kernel: same iterates, same
+    stopping point.  Given the same row it reproduces scipy bit for bit (test below); through
+    the whole report (rows that differ in the last place between the two kernels) no
+    resolution factor of the sweep grid is off by more than 1e-9; sub-pixel profiles go to
+    the host fit."""
+    import _psf_fit_cases as cases
+    fallbacks, exact = cases.check_fused_reports_against_host_fit(
+        st, monkeypatch, psf_type, steps, tol_R=1e-9, min_exact=0)
+    print('fallbacks %d, bit-identical resolution factors %d' % (fallbacks, exact))
+    # (steps = 8: the two strongest depletions of the grid give sub-0.35-pixel profiles)
+    assert fallbacks <= 16
+
+
+def test_device_lmdif_follows_scipy(st):
+    """The in-kernel fit against scipy.optimize.curve_fit on the same rows: same iterates and
+    stopping point, so the coefficients agree to ~1e-10 (a Python transcription of the same
+    restatement that calls numpy's exp is bit-identical to scipy; libm's and CUDA's exp differ
+    from numpy's in the last place, which the forward-difference Jacobian amplifies by
+    1/sqrt(eps)) -- against up to 7e-6 between scipy's stopping point and the true minimum.
+    Gaussian, saturated, doughnut-suppressed, noisy and off-centre profiles, several lengths."""
+    from scipy.optimize import curve_fit
+    rng = np.random.default_rng(12)
+    for n in (17, 35, 107, 135):
+        x = np.arange(n)
+        rows = [np.exp(-(x - n // 2) ** 2 / (2 * 2.5 ** 2)),
+                0.3 * np.exp(-(x - n / 2 - 1.3) ** 2 / (2 * 4.0 ** 2)),
+                (1 - 2 ** -(8 * np.exp(-(x - n // 2) ** 2 / 18.))) *
+                2 ** -(9 * (1 - np.exp(-(x - n // 2) ** 2 / 30.))),
+                np.exp(-(x - n // 2) ** 2 / (2 * 1.1 ** 2)) + 0.01 * rng.random(n),
+                2 * np.exp(-np.abs(x - n // 2) / 3.0)]
+        widths, coeff = st.get_width_batch(np.array(rows))
+        for r, w, c in zip(rows, widths, coeff):
+            ref, _ = curve_fit(lambda t, A, mu, s: A * np.exp(-(t - mu) ** 2 / (2. * s ** 2)),
+                               range(n), r, p0=[1., n / 2., 1.])
+            assert np.allclose(c, ref, rtol=2e-9, atol=0) and w == c[2], (n, c, ref)
+
+
+def test_tune_psf_batch_equals_sequential(st):
+    import _psf_fit_cases as cases
+    cases.check_tune_psf_batch(st, [
+        dict(psf_type='point', scan_type='descanned', desired_resolution_improvement=2.0,
+             desired_emissions_per_molecule=4.0),
+        dict(psf_type='point', scan_type='descanned', desired_resolution_improvement=1.5,
+             desired_emissions_per_molecule=4.0),
+        dict(psf_type='line', scan_type='descanned', desired_resolution_improvement=1.7,
+             desired_emissions_per_molecule=3.0, steps_per_improved_psf_width=2.0),
+    ])
+
+
+def test_psf_report_batch_mixed_samplings(st):
+    """One launch, every point its own grid size."""
+    reps = st.psf_report_batch('line', [1, 0.5, 2], [9, 3, 27], [8, 12, 6], [1, 2, 3])
+    for rep, args in zip(reps, [(1, 9, 8, 1), (0.5, 3, 12, 2), (2, 27, 6, 3)]):
+        one = st.psf_report('line', *args, verbose=False)
+        assert rep['pulses_per_position'] == args[3]
+        for k in one:
+            if k == 'psfs':
+                for kk in one[k]:
+                    assert np.array_equal(rep[k][kk], one[k][kk])
+            else:
+                assert rep[k] == one[k], k
+    scal = st.psf_report_batch('point', [1, 2], 9, 8, 1, psfs=False)
+    assert 'psfs' not in scal[0] and scal[1]['expected_emission'] > 0
+
+
 def test_deconvolver_mirror(st, golden_dir, tmp_path):
     g = np.load(os.path.join(golden_dir, 'fig2_2p0x_lr.npz'))
     d = st.Deconvolver([p[None] for p in g['psfs']],
