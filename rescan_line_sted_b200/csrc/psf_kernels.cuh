@@ -208,7 +208,7 @@ LSTED_HD void psf_rescan_body(Ctx& cx, int b, const PsfRescanArgs& a, PsfSmem* s
 // two-call path above fit on the host: ~1.5 ms of scipy per fit around ~35 us
 // of kernels).
 // ---------------------------------------------------------------------------
-enum { kFitLanes = 64, kFitSums = 5, kPsfReportScalars = 16 };
+enum { kFitLanes = 64, kFitSums = 5, kPsfReportScalars = 16 };   // (kFitSums * kFitLanes >= 2 * 5 * kMpLanes)
 // scalar slots of one report
 enum { PR_EX_SIGMA = 0, PR_STED_SIGMA, PR_RESCAN_SIGMA, PR_RATIO_REAL, PR_RATIO, PR_EXC_DOSE,
        PR_DEP_DOSE, PR_EMISSION, PR_FIT_ITERS, PR_FIT_STATUS, PR_EX_MAX_OK, PR_STED_MAX_OK,
@@ -236,14 +236,13 @@ struct PsfReportSmem {
     double* red;      // [kFitSums][kFitLanes] partial sums of the reductions
     double* sc;       // [8] report scalars
     double* fit;      // [8] result of the last fit
-    double* sc_fit;   // [64] MpState of the running fit
     int nmax;
-    LSTED_HD static size_t doubles(int nmax) { return 10 * (size_t)nmax + kFitSums * kFitLanes + 80; }
+    LSTED_HD static size_t doubles(int nmax) { return 10 * (size_t)nmax + kFitSums * kFitLanes + 16; }
     LSTED_HD void carve(double* base, int nmax_) {
         nmax = nmax_;
         k1 = base; g2 = k1 + nmax; q = g2 + nmax; row_ex = q + nmax; row_sted = row_ex + nmax;
         fvec = row_sted + nmax; wa4 = fvec + nmax; jac = wa4 + nmax;
-        red = jac + 3 * (size_t)nmax; sc = red + kFitSums * kFitLanes; fit = sc + 8; sc_fit = fit + 8;
+        red = jac + 3 * (size_t)nmax; sc = red + kFitSums * kFitLanes; fit = sc + 8;
     }
 };
 
@@ -259,8 +258,6 @@ struct PsfReportSmem {
 // routines lmdif, lmpar, qrfac, qrsolv, fdjac2, enorm).  Given the same profile the CPU replay
 // reproduces scipy bit for bit (tests/test_host_mirror.py); on the GPU only exp() can differ
 // in the last place.
-// Work split: the m residuals are evaluated by all threads (one exp each); the O(m) serial
-// sums of the algorithm run on thread 0 between CTA barriers.
 // ---------------------------------------------------------------------------
 #ifdef __CUDA_ARCH__
 LSTED_HD double nofma_mul(double a, double b) { return __dmul_rn(a, b); }
@@ -307,67 +304,83 @@ LSTED_HD double mp_enorm(const double* x, int n) {
     }
     return nofma_mul(x3max, sqrt(s3));
 }
-// dot product in index order, products and sums rounded separately
-LSTED_HD double mp_dot(const double* a, const double* b, int from, int to) {
-    double s = 0;
-    for (int i = from; i < to; ++i) s = nofma_add(s, nofma_mul(a[i], b[i]));
-    return s;
-}
+enum { MP_N = 3, kMpLanes = 32 };
 
-enum { MP_N = 3 };
-// state of one fit, in shared memory (doubles; small integers stored as doubles)
-struct MpState {
-    double x[MP_N], diag[MP_N], qtf[MP_N], wa1[MP_N], wa2[MP_N], rdiag[MP_N], acnorm[MP_N], trial[MP_N];
-    double ipvt[MP_N];
-    double par, delta, xnorm, fnorm, fnorm1, gnorm, pnorm, iter, nfev, info, stage;
-};
-
-// QR factorisation with column pivoting of the m x 3 matrix in columns a[0..2] (qrfac)
-LSTED_HD void mp_qrfac(double* const* a, int m, MpState* st) {
-    const double epsmch = 2.220446049250313e-16;
-    double wa[MP_N];
-    int ipvt[MP_N];
-    for (int j = 0; j < MP_N; ++j) {
-        st->acnorm[j] = mp_enorm(a[j], m);
-        st->rdiag[j] = st->acnorm[j];
-        wa[j] = st->rdiag[j];
-        ipvt[j] = j;
+// The O(m) loops of the algorithm, spread over the CTA: element-wise steps by all threads,
+// sums as kMpLanes strided partial sums that every thread then combines in lane order (so all
+// threads hold the same scalar and the control flow stays uniform; the summation order differs
+// from MINPACK's serial loops by rounding only -- 1e-16, against the 1e-8 that exp()'s last
+// place puts into the forward-difference Jacobian).  Partial sums ping-pong between two
+// buffers: a thread can run at most one barrier ahead of the slowest.
+template <class Ctx> struct MpVec {
+    Ctx& cx;
+    double* red;    // [2][5][kMpLanes]
+    int flip;
+    LSTED_HD MpVec(Ctx& c, double* r) : cx(c), red(r), flip(0) {}
+    LSTED_HD void sync() { cx.parallel_for(0, [](int) {}); }
+    LSTED_HD double dot(const double* a, const double* b, int from, int to) {
+        double* buf = red + (flip ^= 1) * 5 * kMpLanes;
+        cx.parallel_for(kMpLanes, [&](int lane) {
+            double s = 0;
+            for (int i = from + lane; i < to; i += kMpLanes) s = nofma_add(s, nofma_mul(a[i], b[i]));
+            buf[lane] = s;
+        });
+        double s = 0;
+        for (int l = 0; l < kMpLanes; ++l) s = nofma_add(s, buf[l]);
+        return s;
     }
-    for (int j = 0; j < MP_N && j < m; ++j) {
-        int kmax = j;
-        for (int k = j; k < MP_N; ++k)
-            if (st->rdiag[k] > st->rdiag[kmax]) kmax = k;
-        if (kmax != j) {
-            for (int i = 0; i < m; ++i) { const double t = a[j][i]; a[j][i] = a[kmax][i]; a[kmax][i] = t; }
-            st->rdiag[kmax] = st->rdiag[j];
-            wa[kmax] = wa[j];
-            const int t = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = t;
-        }
-        double ajnorm = mp_enorm(a[j] + j, m - j);
-        if (ajnorm != 0) {
-            if (a[j][j] < 0) ajnorm = -ajnorm;
-            for (int i = j; i < m; ++i) a[j][i] /= ajnorm;
-            a[j][j] = nofma_add(a[j][j], 1.0);
-            for (int k = j + 1; k < MP_N; ++k) {
-                const double sum = mp_dot(a[j], a[k], j, m);
-                const double temp = sum / a[j][j];
-                for (int i = j; i < m; ++i) a[k][i] = nofma_sub(a[k][i], nofma_mul(temp, a[j][i]));
-                if (st->rdiag[k] != 0) {
-                    const double t = a[k][j] / st->rdiag[k];
-                    const double u = nofma_sub(1.0, nofma_mul(t, t));
-                    st->rdiag[k] = nofma_mul(st->rdiag[k], sqrt(u > 0 ? u : 0.0));
-                    const double v = st->rdiag[k] / wa[k];
-                    if (nofma_mul(0.05, nofma_mul(v, v)) <= epsmch) {
-                        st->rdiag[k] = mp_enorm(a[k] + j + 1, m - j - 1);
-                        wa[k] = st->rdiag[k];
+    // enorm: the three magnitude classes of MINPACK's scaled sum of squares, merged over lanes
+    LSTED_HD double enorm(const double* x, int from, int to) {
+        const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+        const int n = to - from;
+        if (n <= 0) return 0.0;
+        const double agiant = rgiant / (double)n;
+        double* buf = red + (flip ^= 1) * 5 * kMpLanes;
+        cx.parallel_for(kMpLanes, [&](int lane) {
+            double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
+            for (int i = from + lane; i < to; i += kMpLanes) {
+                const double xabs = fabs(x[i]);
+                if (xabs > rdwarf && xabs < agiant) {
+                    s2 = nofma_add(s2, nofma_mul(xabs, xabs));
+                } else if (xabs <= rdwarf) {
+                    if (xabs > x3max) {
+                        const double t = x3max / xabs;
+                        s3 = nofma_add(1.0, nofma_mul(s3, nofma_mul(t, t)));
+                        x3max = xabs;
+                    } else if (xabs != 0) {
+                        const double t = xabs / x3max;
+                        s3 = nofma_add(s3, nofma_mul(t, t));
                     }
+                } else if (xabs > x1max) {
+                    const double t = x1max / xabs;
+                    s1 = nofma_add(1.0, nofma_mul(s1, nofma_mul(t, t)));
+                    x1max = xabs;
+                } else {
+                    const double t = xabs / x1max;
+                    s1 = nofma_add(s1, nofma_mul(t, t));
                 }
             }
+            buf[lane] = s1; buf[kMpLanes + lane] = x1max; buf[2 * kMpLanes + lane] = s2;
+            buf[3 * kMpLanes + lane] = s3; buf[4 * kMpLanes + lane] = x3max;
+        });
+        double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
+        for (int l = 0; l < kMpLanes; ++l) {
+            const double p1 = buf[l], m1 = buf[kMpLanes + l], p3 = buf[3 * kMpLanes + l],
+                         m3 = buf[4 * kMpLanes + l];
+            s2 = nofma_add(s2, buf[2 * kMpLanes + l]);
+            if (m1 > x1max) { const double t = x1max / m1; s1 = nofma_add(p1, nofma_mul(s1, nofma_mul(t, t))); x1max = m1; }
+            else if (m1 != 0) { const double t = m1 / x1max; s1 = nofma_add(s1, nofma_mul(p1, nofma_mul(t, t))); }
+            if (m3 > x3max) { const double t = x3max / m3; s3 = nofma_add(p3, nofma_mul(s3, nofma_mul(t, t))); x3max = m3; }
+            else if (m3 != 0) { const double t = m3 / x3max; s3 = nofma_add(s3, nofma_mul(p3, nofma_mul(t, t))); }
         }
-        st->rdiag[j] = -ajnorm;
+        if (s1 != 0) return nofma_mul(x1max, sqrt(nofma_add(s1, (s2 / x1max) / x1max)));
+        if (s2 != 0) {
+            if (s2 >= x3max) return sqrt(nofma_mul(s2, nofma_add(1.0, nofma_mul(x3max / s2, nofma_mul(x3max, s3)))));
+            return sqrt(nofma_mul(x3max, nofma_add(s2 / x3max, nofma_mul(x3max, s3))));
+        }
+        return nofma_mul(x3max, sqrt(s3));
     }
-    for (int j = 0; j < MP_N; ++j) st->ipvt[j] = (double)ipvt[j];
-}
+};
 
 // qrsolv on the 3 x 3 upper triangle r (row i, column j); the lower triangle is scratch
 LSTED_HD void mp_qrsolv(double r[MP_N][MP_N], const int* ipvt, const double* diag, const double* qtb,
@@ -502,173 +515,212 @@ LSTED_HD double mp_lmpar(double r[MP_N][MP_N], const int* ipvt, const double* di
     return par;
 }
 
-// out: A, mu, sigma, function evaluations, MINPACK info (1-4 = converged like scipy accepts)
+// out: A, mu, sigma, function evaluations, MINPACK info (1-4 = converged like scipy accepts).
+// All scalars of the algorithm live in registers, identical in every thread.
 template <class Ctx>
 LSTED_HD void gauss_fit_body(Ctx& cx, const double* y, int n, PsfReportSmem* sm, double* out) {
     const int m = n;
     const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
     const double epsmch = 2.220446049250313e-16;
     const int maxfev = 200 * (MP_N + 1);
-    MpState* const st = (MpState*)sm->sc_fit;
     double* const fvec = sm->fvec;
     double* const wa4 = sm->wa4;
     double* const col[MP_N] = {sm->jac, sm->jac + sm->nmax, sm->jac + 2 * (size_t)sm->nmax};
-    // residuals gauss(i; p) - y[i] (curve_fit's wrapped function), numpy's operation order
-    auto residuals = [&](const double* p, double* dst) {
-        cx.parallel_for(m, [&](int i) {
-            const double d = nofma_sub((double)i, p[1]);
-            const double den = nofma_mul(2.0, nofma_mul(p[2], p[2]));
-            const double e = exp(-nofma_mul(d, d) / den);
-            dst[i] = nofma_sub(nofma_mul(p[0], e), y[i]);
-        });
+    MpVec<Ctx> v(cx, sm->red);
+    // residual gauss(i; p) - y[i] (curve_fit's wrapped function), numpy's operation order
+    auto residual = [&](const double* p, int i) {
+        const double d = nofma_sub((double)i, p[1]);
+        const double den = nofma_mul(2.0, nofma_mul(p[2], p[2]));
+        const double e = exp(-nofma_mul(d, d) / den);
+        return nofma_sub(nofma_mul(p[0], e), y[i]);
     };
-    cx.parallel_for(1, [&](int) {
-        st->x[0] = 1.0; st->x[1] = (double)n / 2.0; st->x[2] = 1.0;
-        st->par = 0; st->iter = 1; st->info = 0; st->nfev = 1; st->delta = 0; st->xnorm = 0;
-    });
-    residuals(st->x, fvec);
-    cx.parallel_for(1, [&](int) { st->fnorm = mp_enorm(fvec, m); });
+    double x[MP_N] = {1.0, (double)n / 2.0, 1.0};
+    double diag[MP_N] = {0, 0, 0}, qtf[MP_N], rdiag[MP_N], acnorm[MP_N], wa[MP_N], trial[MP_N];
+    double r[MP_N][MP_N];
+    int ipvt[MP_N];
+    double par = 0, delta = 0, xnorm = 0, gnorm = 0;
+    int iter = 1, info = 0, nfev = 1;
+    v.sync();   // (the caller's writes of y)
+    cx.parallel_for(m, [&](int i) { fvec[i] = residual(x, i); });
+    double fnorm = v.enorm(fvec, 0, m);
     const double eps = sqrt(epsmch);
     for (;;) {   // outer loop
-        // forward-difference Jacobian (fdjac2), one column per parameter
+        // forward-difference Jacobian (fdjac2)
+        v.sync();
         for (int j = 0; j < MP_N; ++j) {
-            cx.parallel_for(1, [&](int) {
-                for (int k = 0; k < MP_N; ++k) st->trial[k] = st->x[k];
-                double h = nofma_mul(eps, fabs(st->x[j]));
-                if (h == 0) h = eps;
-                st->trial[j] = nofma_add(st->x[j], h);
-                st->wa1[0] = h;
-            });
-            residuals(st->trial, wa4);
-            cx.parallel_for(m, [&](int i) { col[j][i] = nofma_sub(wa4[i], fvec[i]) / st->wa1[0]; });
+            for (int k = 0; k < MP_N; ++k) trial[k] = x[k];
+            double h = nofma_mul(eps, fabs(x[j]));
+            if (h == 0) h = eps;
+            trial[j] = nofma_add(x[j], h);
+            cx.parallel_for(m, [&](int i) { col[j][i] = nofma_sub(residual(trial, i), fvec[i]) / h; });
         }
-        cx.parallel_for(1, [&](int) {
-            st->nfev += MP_N;
-            mp_qrfac(col, m, st);
-            if (st->iter == 1) {
-                double wa3[MP_N];
-                for (int j = 0; j < MP_N; ++j) {
-                    st->diag[j] = st->acnorm[j];
-                    if (st->acnorm[j] == 0) st->diag[j] = 1.0;
-                    wa3[j] = nofma_mul(st->diag[j], st->x[j]);
-                }
-                st->xnorm = mp_enorm(wa3, MP_N);
-                st->delta = nofma_mul(factor, st->xnorm);
-                if (st->delta == 0) st->delta = factor;
+        nfev += MP_N;
+        // qrfac: Householder QR with column pivoting
+        for (int j = 0; j < MP_N; ++j) {
+            acnorm[j] = v.enorm(col[j], 0, m);
+            rdiag[j] = acnorm[j]; wa[j] = rdiag[j]; ipvt[j] = j;
+        }
+        for (int j = 0; j < MP_N && j < m; ++j) {
+            int kmax = j;
+            for (int k = j; k < MP_N; ++k)
+                if (rdiag[k] > rdiag[kmax]) kmax = k;
+            if (kmax != j) {
+                v.sync();
+                cx.parallel_for(m, [&](int i) { const double t = col[j][i]; col[j][i] = col[kmax][i]; col[kmax][i] = t; });
+                rdiag[kmax] = rdiag[j]; wa[kmax] = wa[j];
+                const int t = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = t;
             }
-            // first n components of Q^T fvec; R's diagonal back into the columns
-            for (int i = 0; i < m; ++i) wa4[i] = fvec[i];
+            double ajnorm = v.enorm(col[j], j, m);
+            if (ajnorm != 0) {
+                if (col[j][j] < 0) ajnorm = -ajnorm;
+                v.sync();
+                cx.parallel_for(m - j, [&](int w) {
+                    const int i = j + w;
+                    double t = col[j][i] / ajnorm;
+                    if (i == j) t = nofma_add(t, 1.0);
+                    col[j][i] = t;
+                });
+                const double ajj = col[j][j];
+                for (int k = j + 1; k < MP_N; ++k) {
+                    const double sum = v.dot(col[j], col[k], j, m);
+                    const double temp = sum / ajj;
+                    v.sync();
+                    cx.parallel_for(m - j, [&](int w) {
+                        const int i = j + w;
+                        col[k][i] = nofma_sub(col[k][i], nofma_mul(temp, col[j][i]));
+                    });
+                    if (rdiag[k] != 0) {
+                        const double t = col[k][j] / rdiag[k];
+                        const double u = nofma_sub(1.0, nofma_mul(t, t));
+                        rdiag[k] = nofma_mul(rdiag[k], sqrt(u > 0 ? u : 0.0));
+                        const double q = rdiag[k] / wa[k];
+                        if (nofma_mul(0.05, nofma_mul(q, q)) <= epsmch) {
+                            rdiag[k] = v.enorm(col[k], j + 1, m);
+                            wa[k] = rdiag[k];
+                        }
+                    }
+                }
+            }
+            rdiag[j] = -ajnorm;
+        }
+        if (iter == 1) {
+            double wa3[MP_N];
             for (int j = 0; j < MP_N; ++j) {
-                if (col[j][j] != 0) {
-                    const double sum = mp_dot(col[j], wa4, j, m);
-                    const double temp = -sum / col[j][j];
-                    for (int i = j; i < m; ++i) wa4[i] = nofma_add(wa4[i], nofma_mul(col[j][i], temp));
-                }
-                col[j][j] = st->rdiag[j];
-                st->qtf[j] = wa4[j];
+                diag[j] = acnorm[j];
+                if (acnorm[j] == 0) diag[j] = 1.0;
+                wa3[j] = nofma_mul(diag[j], x[j]);
             }
-            double gnorm = 0;
-            if (st->fnorm != 0) {
-                for (int j = 0; j < MP_N; ++j) {
-                    const int l = (int)st->ipvt[j];
-                    if (st->acnorm[l] != 0) {
-                        double sum = 0;
-                        for (int i = 0; i <= j; ++i) sum = nofma_add(sum, nofma_mul(col[j][i], st->qtf[i] / st->fnorm));
-                        const double g = fabs(sum / st->acnorm[l]);
-                        gnorm = g > gnorm ? g : gnorm;
-                    }
-                }
-            }
-            st->gnorm = gnorm;
-            if (gnorm <= gtol) st->info = 4;
-            for (int j = 0; j < MP_N; ++j) st->diag[j] = st->diag[j] > st->acnorm[j] ? st->diag[j] : st->acnorm[j];
-        });
-        if (st->info != 0) break;
-        for (;;) {   // inner loop
-            cx.parallel_for(1, [&](int) {
-                double r[MP_N][MP_N];
-                int ipvt[MP_N];
-                for (int i = 0; i < MP_N; ++i) {
-                    ipvt[i] = (int)st->ipvt[i];
-                    for (int j = 0; j < MP_N; ++j) r[i][j] = i <= j ? col[j][i] : 0.0;
-                }
-                double p[MP_N];
-                st->par = mp_lmpar(r, ipvt, st->diag, st->qtf, st->delta, st->par, p);
-                double wa3[MP_N];
-                for (int j = 0; j < MP_N; ++j) {
-                    st->wa1[j] = -p[j];
-                    st->trial[j] = nofma_add(st->x[j], st->wa1[j]);
-                    wa3[j] = nofma_mul(st->diag[j], st->wa1[j]);
-                }
-                st->pnorm = mp_enorm(wa3, MP_N);
-                if (st->iter == 1) st->delta = st->delta < st->pnorm ? st->delta : st->pnorm;
-            });
-            residuals(st->trial, wa4);
-            cx.parallel_for(1, [&](int) {
-                st->nfev += 1;
-                const double fnorm = st->fnorm, pnorm = st->pnorm;
-                const double fnorm1 = mp_enorm(wa4, m);
-                double actred = -1.0;
-                if (nofma_mul(0.1, fnorm1) < fnorm) {
-                    const double t = fnorm1 / fnorm;
-                    actred = nofma_sub(1.0, nofma_mul(t, t));
-                }
-                double wa3[MP_N] = {0, 0, 0};
-                for (int j = 0; j < MP_N; ++j) {
-                    const int l = (int)st->ipvt[j];
-                    const double temp = st->wa1[l];
-                    for (int i = 0; i <= j; ++i) wa3[i] = nofma_add(wa3[i], nofma_mul(col[j][i], temp));
-                }
-                const double temp1 = mp_enorm(wa3, MP_N) / fnorm;
-                const double temp2 = nofma_mul(sqrt(st->par), pnorm) / fnorm;
-                const double t11 = nofma_mul(temp1, temp1), t22 = nofma_mul(temp2, temp2);
-                const double prered = nofma_add(t11, t22 / 0.5);
-                const double dirder = -nofma_add(t11, t22);
-                double ratio = 0;
-                if (prered != 0) ratio = actred / prered;
-                if (ratio <= 0.25) {
-                    double temp;
-                    if (actred >= 0) temp = 0.5;
-                    else temp = nofma_mul(0.5, dirder) / nofma_add(dirder, nofma_mul(0.5, actred));
-                    if (nofma_mul(0.1, fnorm1) >= fnorm || temp < 0.1) temp = 0.1;
-                    const double pn = pnorm / 0.1;
-                    st->delta = nofma_mul(temp, st->delta < pn ? st->delta : pn);
-                    st->par = st->par / temp;
-                } else if (st->par == 0 || ratio >= 0.75) {
-                    st->delta = pnorm / 0.5;
-                    st->par = nofma_mul(0.5, st->par);
-                }
-                if (ratio >= 1e-4) {   // successful iteration
-                    double wa2[MP_N];
-                    for (int j = 0; j < MP_N; ++j) {
-                        st->x[j] = st->trial[j];
-                        wa2[j] = nofma_mul(st->diag[j], st->x[j]);
-                    }
-                    for (int i = 0; i < m; ++i) fvec[i] = wa4[i];
-                    st->xnorm = mp_enorm(wa2, MP_N);
-                    st->fnorm = fnorm1;
-                    st->iter += 1;
-                }
-                const bool small = fabs(actred) <= ftol && prered <= ftol && nofma_mul(0.5, ratio) <= 1.0;
-                double info = 0;
-                if (small) info = 1;
-                if (st->delta <= nofma_mul(xtol, st->xnorm)) info = 2;
-                if (small && info == 2) info = 3;
-                if (info == 0) {
-                    if (st->nfev >= maxfev) info = 5;
-                    if (fabs(actred) <= epsmch && prered <= epsmch && nofma_mul(0.5, ratio) <= 1.0) info = 6;
-                    if (st->delta <= nofma_mul(epsmch, st->xnorm)) info = 7;
-                    if (st->gnorm <= epsmch) info = 8;
-                }
-                st->info = info;
-                st->stage = ratio >= 1e-4 ? 1.0 : 0.0;
-            });
-            if (st->info != 0 || st->stage != 0) break;
+            xnorm = mp_enorm(wa3, MP_N);
+            delta = nofma_mul(factor, xnorm);
+            if (delta == 0) delta = factor;
         }
-        if (st->info != 0) break;
+        // first n components of Q^T fvec
+        v.sync();
+        cx.parallel_for(m, [&](int i) { wa4[i] = fvec[i]; });
+        for (int j = 0; j < MP_N; ++j) {
+            const double cjj = col[j][j];
+            if (cjj != 0) {
+                const double sum = v.dot(col[j], wa4, j, m);
+                const double temp = -sum / cjj;
+                v.sync();
+                cx.parallel_for(m - j, [&](int w) {
+                    const int i = j + w;
+                    wa4[i] = nofma_add(wa4[i], nofma_mul(col[j][i], temp));
+                });
+            }
+            qtf[j] = wa4[j];
+        }
+        // R: the strict upper triangle sits in the columns, the diagonal in rdiag
+        for (int i = 0; i < MP_N; ++i)
+            for (int j = 0; j < MP_N; ++j) r[i][j] = i < j ? col[j][i] : (i == j ? rdiag[j] : 0.0);
+        gnorm = 0;
+        if (fnorm != 0) {
+            for (int j = 0; j < MP_N; ++j) {
+                const int l = ipvt[j];
+                if (acnorm[l] != 0) {
+                    double sum = 0;
+                    for (int i = 0; i <= j; ++i) sum = nofma_add(sum, nofma_mul(r[i][j], qtf[i] / fnorm));
+                    const double g = fabs(sum / acnorm[l]);
+                    gnorm = g > gnorm ? g : gnorm;
+                }
+            }
+        }
+        if (gnorm <= gtol) { info = 4; break; }
+        for (int j = 0; j < MP_N; ++j) diag[j] = diag[j] > acnorm[j] ? diag[j] : acnorm[j];
+        for (;;) {   // inner loop
+            double rr[MP_N][MP_N], p[MP_N], wa1[MP_N], wa3[MP_N];
+            for (int i = 0; i < MP_N; ++i)
+                for (int j = 0; j < MP_N; ++j) rr[i][j] = r[i][j];
+            par = mp_lmpar(rr, ipvt, diag, qtf, delta, par, p);
+            for (int j = 0; j < MP_N; ++j) {
+                wa1[j] = -p[j];
+                trial[j] = nofma_add(x[j], wa1[j]);
+                wa3[j] = nofma_mul(diag[j], wa1[j]);
+            }
+            const double pnorm = mp_enorm(wa3, MP_N);
+            if (iter == 1) delta = delta < pnorm ? delta : pnorm;
+            v.sync();
+            cx.parallel_for(m, [&](int i) { wa4[i] = residual(trial, i); });
+            nfev += 1;
+            const double fnorm1 = v.enorm(wa4, 0, m);
+            double actred = -1.0;
+            if (nofma_mul(0.1, fnorm1) < fnorm) {
+                const double t = fnorm1 / fnorm;
+                actred = nofma_sub(1.0, nofma_mul(t, t));
+            }
+            for (int i = 0; i < MP_N; ++i) wa3[i] = 0;
+            for (int j = 0; j < MP_N; ++j) {
+                const double temp = wa1[ipvt[j]];
+                for (int i = 0; i <= j; ++i) wa3[i] = nofma_add(wa3[i], nofma_mul(r[i][j], temp));
+            }
+            const double temp1 = mp_enorm(wa3, MP_N) / fnorm;
+            const double temp2 = nofma_mul(sqrt(par), pnorm) / fnorm;
+            const double t11 = nofma_mul(temp1, temp1), t22 = nofma_mul(temp2, temp2);
+            const double prered = nofma_add(t11, t22 / 0.5);
+            const double dirder = -nofma_add(t11, t22);
+            double ratio = 0;
+            if (prered != 0) ratio = actred / prered;
+            if (ratio <= 0.25) {
+                double temp;
+                if (actred >= 0) temp = 0.5;
+                else temp = nofma_mul(0.5, dirder) / nofma_add(dirder, nofma_mul(0.5, actred));
+                if (nofma_mul(0.1, fnorm1) >= fnorm || temp < 0.1) temp = 0.1;
+                const double pn = pnorm / 0.1;
+                delta = nofma_mul(temp, delta < pn ? delta : pn);
+                par = par / temp;
+            } else if (par == 0 || ratio >= 0.75) {
+                delta = pnorm / 0.5;
+                par = nofma_mul(0.5, par);
+            }
+            if (ratio >= 1e-4) {   // successful iteration
+                double wa2[MP_N];
+                for (int j = 0; j < MP_N; ++j) {
+                    x[j] = trial[j];
+                    wa2[j] = nofma_mul(diag[j], x[j]);
+                }
+                v.sync();
+                cx.parallel_for(m, [&](int i) { fvec[i] = wa4[i]; });
+                xnorm = mp_enorm(wa2, MP_N);
+                fnorm = fnorm1;
+                iter += 1;
+            }
+            const bool small = fabs(actred) <= ftol && prered <= ftol && nofma_mul(0.5, ratio) <= 1.0;
+            if (small) info = 1;
+            if (delta <= nofma_mul(xtol, xnorm)) info = 2;
+            if (small && info == 2) info = 3;
+            if (info != 0) break;
+            if (nfev >= maxfev) info = 5;
+            if (fabs(actred) <= epsmch && prered <= epsmch && nofma_mul(0.5, ratio) <= 1.0) info = 6;
+            if (delta <= nofma_mul(epsmch, xnorm)) info = 7;
+            if (gnorm <= epsmch) info = 8;
+            if (info != 0) break;
+            if (ratio >= 1e-4) break;
+        }
+        if (info != 0) break;
     }
+    v.sync();
     cx.parallel_for(1, [&](int) {
-        out[0] = st->x[0]; out[1] = st->x[1]; out[2] = st->x[2]; out[3] = st->nfev; out[4] = st->info;
+        out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = (double)nfev; out[4] = (double)info;
     });
 }
 
