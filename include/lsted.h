@@ -134,6 +134,11 @@ int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info);
  *          row spectra moved by tensor-map bulk copies; 2 = also the two-buffer ROW_MID), "real_otf", "row_dual", "row_plan2",
  *          "prefetch" */
 int lsted_deconv_set_option(lsted_deconv* h, const char* name, double value);
+/* record_iteration's error spectrum (:539-546): out[Ny][Nx] = log(1 + |fftshift(fft2(x -
+ * true_object))|) with x = `image` (host, [Ny][Nx]) or, when image is NULL, the estimate in
+ * HBM.  *done = 0 (and out untouched) when a side of the image has a prime factor above 5
+ * or does not fit one CTA: the caller then transforms on the host like the reference.     */
+int lsted_deconv_ft_error(lsted_deconv* h, const double* image, double* out, int* done);
 /* create_data_from_object (:496-512).  rescale != 0 applies total_brightness.
  * Noise: in-kernel Philox4x32-10 Poisson, stream selected by `seed`.               */
 int lsted_deconv_create_data(lsted_deconv* h, const double* object, double total_brightness,

@@ -69,6 +69,7 @@ _DECONV_SIGNATURES = {
                          c_double_p],
     'lsted_deconv_set': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                          c_double_p],
+    'lsted_deconv_ft_error': [ctypes.c_void_p, c_double_p, c_double_p, c_int_p],
     'lsted_deconv_H': [ctypes.c_void_p, c_double_p, c_double_p],
     'lsted_deconv_Ht': [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int],
     'lsted_deconv_sync': [ctypes.c_void_p],
@@ -261,6 +262,20 @@ class DeconvHandle:
         arr, p = as_f64(arr)
         assert arr.size == self.Ny * self.Nx
         self.lib.call('lsted_deconv_set', self._h, which, k, p)
+
+    def ft_error(self, image=None):
+        """log(1 + |fftshift(fft2(image - true_object))|), image = the estimate in HBM when
+        None; (1, Ny, Nx) float64, or None when the size has no on-device transform."""
+        out = pooled_pinned_empty((1, self.Ny, self.Nx), lib=self.lib)
+        done = ctypes.c_int(0)
+        if image is None:
+            p = None
+        else:
+            image, p = as_f64(image)
+            assert image.size == self.Ny * self.Nx
+        self.lib.call('lsted_deconv_ft_error', self._h, p, out.ctypes.data_as(c_double_p),
+                      ctypes.byref(done))
+        return out if done.value else None
 
     def H(self, x):
         x, p = as_f64(x)

@@ -230,6 +230,15 @@ extern "C" int lsted_deconv_set(lsted_deconv* h, int which, int k, const double*
     LSTED_CATCH
 }
 
+extern "C" int lsted_deconv_ft_error(lsted_deconv* h, const double* image, double* out, int* done) {
+    if (!h || !out || !done) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    h->bk->activate();
+    *done = h->e->ft_error(image, out) ? 1 : 0;
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
 extern "C" int lsted_deconv_H(lsted_deconv* h, const double* x, double* out) {
     if (!h || !x || !out) return set_error(LSTED_ERR_ARG, "null pointer");
     LSTED_TRY

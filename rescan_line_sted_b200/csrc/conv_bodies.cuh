@@ -226,7 +226,8 @@ enum { kMaxPeers = 8 };
 enum ColMode {
     COL_OTF = 0,  // zero-padded forward transform, scaled, all Ly rows stored
     COL_H = 1,    // one input spectrum -> K products -> K inverse transforms
-    COL_HT = 2    // K input spectra -> sum_k product -> one inverse transform
+    COL_HT = 2,   // K input spectra -> sum_k product -> one inverse transform
+    COL_LOGMAG = 3  // forward transform -> log(1 + |.|), fftshift-ed, full plane (record_iteration :539-546)
 };
 
 template <typename T> struct ColArgs {
@@ -241,6 +242,7 @@ template <typename T> struct ColArgs {
     int rows_in;            // valid input rows (zero padded up to Ly)
     int src_same;           // HT: every k reads the same input spectrum (H_t of all-ones images)
     T scale;                // OTF: 1/(Lx*Ly)
+    double* logmag;         // LOGMAG: [Ny][Nx] out (the transform lengths equal the image size)
     // HT of the fast path with orientations sharded over GPUs: the cross-GPU sum is done inside
     // the kernel over NVLink peer memory (see col_fast_body).  world <= 1: off.
     int p2p_world, p2p_rank;
@@ -280,6 +282,35 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
         cx.parallel_for(C * Ly, [&](int w) {
             const int y = w / C, c = w - y * C;
             dst[w] = scale(z[c * Lp + pad<T>(y)], a.scale);
+        });
+        return;
+    }
+    if (MODE == COL_LOGMAG) {
+        // log(1 + |fftshift(fft2(x))|) of a real image: the Lx/2+1 stored columns give the
+        // rest by Hermitian symmetry, |F[ky][Nx-kx]| = |F[-ky][kx]|; fftshift moves k to
+        // (k + N/2) mod N
+        const int Nx = g.Nx;
+        const cplx<T>* src = a.src + (size_t)xb * slab_ny;
+        cx.parallel_for(C * Ly, [&](int w) {
+            const int y = w / C, c = w - y * C;
+            b0[c * Lp + pad<T>(y)] = src[slab2_index(y, c, C)];
+        });
+        SmemSrc<T> s0 = {b0, Lp};
+        const cplx<T>* z = fft_batch<-1, T>(cx, g.py, a.tw, s0, b1, b0, C, Lp);
+        cx.parallel_for(C * Ly, [&](int w) {
+            const int y = w / C, c = w - y * C;
+            const int x = xb * C + c;
+            if (x >= g.Lxh) return;
+            const cplx<T> v = z[c * Lp + pad<T>(y)];
+            const double mag = log(1.0 + sqrt((double)v.x * (double)v.x + (double)v.y * (double)v.y));
+            int ys = y + Ny / 2; if (ys >= Ny) ys -= Ny;
+            int xs = x + Nx / 2; if (xs >= Nx) xs -= Nx;
+            a.logmag[(size_t)ys * Nx + xs] = mag;
+            if (x > 0 && 2 * x != Nx) {
+                int ym = (y == 0 ? 0 : Ny - y) + Ny / 2; if (ym >= Ny) ym -= Ny;
+                int xm = (Nx - x) + Nx / 2; if (xm >= Nx) xm -= Nx;
+                a.logmag[(size_t)ym * Nx + xm] = mag;
+            }
         });
         return;
     }

@@ -50,6 +50,7 @@ class EngineBase {
     virtual void p2p_export(char* handles_out) = 0;                       // kIpcBytes
     virtual void p2p_attach(const char* all_handles) = 0;                 // [world][kIpcBytes]
     virtual void info(EngineInfo* out) = 0;
+    virtual bool ft_error(const double* image_host, double* out_host) = 0;
 };
 
 template <typename T, class BK> class DeconvEngine : public EngineBase {
@@ -336,6 +337,47 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         if (id == ARR_NORMALIZATION) have_norm = true;
     }
 
+    // record_iteration's error spectrum (ref:539-546): log(1 + |fftshift(fft2(x - true_object))|)
+    // with x = the estimate in HBM (image_host == 0) or a host image.  An un-padded Ny x Nx
+    // transform with the generic kernels; false when a side is not 2^a 3^b 5^c (or does not fit a
+    // CTA): the caller falls back to numpy.
+    bool ft_error(const double* image_host, double* out_host) {
+        if (!ft_tried) {
+            ft_tried = true;
+            const char* why = make_geom(g.Ny, g.Nx, 1, 1, (int)sizeof(cplx<T>), &gft);
+            ft_ok = !why[0] && gft.Ly == g.Ny && gft.Lx == g.Nx;
+            if (ft_ok) {
+                std::vector<cplx<T> > tw;
+                tw.resize(gft.Lx); fill_twiddles<T>(gft.Lx, tw.data());
+                tw_fx = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * gft.Lx);
+                bk.upload(tw_fx, tw.data(), sizeof(cplx<T>) * gft.Lx);
+                tw.resize(gft.Ly); fill_twiddles<T>(gft.Ly, tw.data());
+                tw_fy = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * gft.Ly);
+                bk.upload(tw_fy, tw.data(), sizeof(cplx<T>) * gft.Ly);
+                spec_ft = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * spec_elems(gft, gft.Ny));
+                bk.sync();
+            }
+        }
+        if (!ft_ok) return false;
+        const T* x = estimate;
+        if (image_host) {
+            bk.upload(stage64, image_host, sizeof(double) * npix);
+            bk.cast_in(scratch, stage64, npix, 1.0);
+            x = scratch;
+        }
+        bk.subtract(scratch, x, true_object, npix);
+        RowArgs<T> ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.g = gft; ra.tw = tw_fx; ra.nimg = 1; ra.real_in = scratch; ra.spec_out = spec_ft;
+        bk.template launch_row<ROW_FWD, T>(row_blocks(gft), ra);
+        ColArgs<T> ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.g = gft; ca.tw = tw_fy; ca.src = spec_ft; ca.K = 1; ca.rows_in = gft.Ny; ca.logmag = stage64;
+        bk.launch_col_logmag(gft.nxb, ca);
+        bk.download(out_host, stage64, sizeof(double) * npix);
+        return true;
+    }
+
     // Host-array forms of H / H_t for the Python methods.
     void H_host(const double* x, double* out) {
         bk.upload(stage64, x, sizeof(double) * npix);
@@ -365,6 +407,9 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     cplx<T>*tw_x, *tw_y, *otf, *spec1, *specK;
     T *true_object, *estimate, *norm, *scratch, *noiseless, *noisy;
     double *stage64, *object64, *partial;
+    ConvGeom gft;                       // un-padded transform of the error spectrum (ft_error)
+    bool ft_tried = false, ft_ok = false;
+    cplx<T>*tw_fx = 0, *tw_fy = 0, *spec_ft = 0;
     T* tmpK;  // K images, allocated on first use by the host-array forms of H / H_t
     cplx<T>* p2p_recv; unsigned* p2p_flags; size_t p2p_words;
     bool tmaps_tried; void* tmap_specK; void* tmap_spec1;

@@ -5,7 +5,7 @@
 
 namespace lsted {
 
-enum EwOp { EW_CAST_IN = 0, EW_CAST_OUT = 1, EW_FILL = 2, EW_DIVIDE = 3, EW_RL_UPDATE = 4 };
+enum EwOp { EW_CAST_IN = 0, EW_CAST_OUT = 1, EW_FILL = 2, EW_DIVIDE = 3, EW_RL_UPDATE = 4, EW_SUB = 5 };
 
 template <typename T> struct EwArgs {
     T* t0;            // destination (or in/out)
@@ -23,6 +23,7 @@ template <int OP, typename T> LSTED_HD void ew_apply(const EwArgs<T>& a, size_t 
     else if (OP == EW_FILL) a.t0[i] = (T)a.s;
     else if (OP == EW_DIVIDE) a.t0[i] = a.t0[i] / a.t1[i];
     else if (OP == EW_RL_UPDATE) a.t0[i] = a.t0[i] * (a.t1[i] / a.t2[i]);  // est *= H_t(ratio)/norm
+    else if (OP == EW_SUB) a.t0[i] = a.t1[i] - a.t2[i];
 }
 
 }  // namespace lsted

@@ -766,6 +766,19 @@ class CudaBackend {
         lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = io; a.t1 = den; a.n = n;
         ew<lsted::EW_DIVIDE, T>(a);
     }
+    template <typename T> void subtract(T* dst, const T* a, const T* b, size_t n) {
+        lsted::EwArgs<T> e; memset(&e, 0, sizeof(e)); e.t0 = dst; e.t1 = a; e.t2 = b; e.n = n;
+        ew<lsted::EW_SUB, T>(e);
+    }
+    // generic column kernel in COL_LOGMAG mode (record_iteration's error spectrum)
+    template <typename T> void launch_col_logmag(int grid, const lsted::ColArgs<T>& a) {
+        const size_t smem = lsted::col_smem_bytes(a.g, (int)sizeof(lsted::cplx<T>), 2);
+        ensure_smem(col_kernel<lsted::COL_LOGMAG, T>, smem);
+        const int threads = sizeof(T) == 4 ? kColThreads32 : kColThreads64;
+        before(KK_EW);
+        col_kernel<lsted::COL_LOGMAG, T><<<grid, threads, smem, stream_>>>(a);
+        after();
+    }
     template <typename T> void rl_update(T* est, const T* num, const T* den, size_t n) {
         lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = est; a.t1 = num; a.t2 = den; a.n = n;
         ew<lsted::EW_RL_UPDATE, T>(a);

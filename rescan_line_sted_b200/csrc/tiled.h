@@ -85,6 +85,7 @@ template <typename T, class BK> class TiledEngine : public EngineBase {
         ratio = (T*)bk.alloc(sizeof(T) * bpix * K);
         have_norm = false; have_estimate = false;
     }
+    bool ft_error(const double*, double*) { return false; }   // tiled objects: host transform
     void info(EngineInfo* o) {
         tile.info(o);
         o->Ny = Ny; o->Nx = Nx; o->iterations_done = iterations_done;

@@ -804,10 +804,20 @@ class Deconvolver:
             if cache and cache[0][0] != self._data_version:
                 del cache[:]                       # new object: start over
             if len(cache) < len(self.estimate_history):
-                true_object = self.true_object     # one device read
-                for est in self.estimate_history[len(cache):]:
-                    cache.append((self._data_version, np.log(1 + np.abs(np.fft.fftshift(
-                        np.fft.fftn(est - true_object, axes=(1, 2)), axes=(1, 2))))))
+                # on the device (un-padded 2-D transform + log-magnitude + fftshift in the
+                # column kernel's epilogue); numpy where the size has no device transform
+                h = self._need(_lib.TRUE_OBJECT, 'true_object')
+                true_object = None
+                first_new = len(cache)
+                for i, est in enumerate(self.estimate_history[first_new:], first_new):
+                    newest = i == len(self.estimate_history) - 1   # = the estimate in HBM
+                    spectrum = h.ft_error(None if newest else est)
+                    if spectrum is None:
+                        if true_object is None:
+                            true_object = self.true_object
+                        spectrum = np.log(1 + np.abs(np.fft.fftshift(
+                            np.fft.fftn(est - true_object, axes=(1, 2)), axes=(1, 2))))
+                    cache.append((self._data_version, spectrum))
             spectrum = np.concatenate([c[1] for c in cache], axis=0)
             np_tif.array_to_tif(
                 spectrum, self.output_prefix + 'estimate_FT_error_history.tif')

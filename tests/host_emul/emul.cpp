@@ -316,6 +316,15 @@ class HostBackend {
         lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = io; a.t1 = den; a.n = n;
         ew<lsted::EW_DIVIDE, T>(a);
     }
+    template <typename T> void subtract(T* dst, const T* a, const T* b, size_t n) {
+        lsted::EwArgs<T> e; memset(&e, 0, sizeof(e)); e.t0 = dst; e.t1 = a; e.t2 = b; e.n = n;
+        ew<lsted::EW_SUB, T>(e);
+    }
+    template <typename T> void launch_col_logmag(int grid, const lsted::ColArgs<T>& a) {
+        std::vector<lsted::cplx<T> > smem((size_t)3 * a.g.C * a.g.Lpy);
+        HostCtx cx;
+        for (int b = 0; b < grid; ++b) lsted::col_body<lsted::COL_LOGMAG, T>(cx, b, a, smem.data());
+    }
     template <typename T> void rl_update(T* est, const T* num, const T* den, size_t n) {
         lsted::EwArgs<T> a; memset(&a, 0, sizeof(a)); a.t0 = est; a.t1 = num; a.t2 = den; a.n = n;
         ew<lsted::EW_RL_UPDATE, T>(a);
