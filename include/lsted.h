@@ -190,6 +190,64 @@ int lsted_deconv_timer_stop(lsted_deconv* h, float* milliseconds);
 enum { LSTED_NUM_KERNEL_KINDS = 9 };
 int lsted_deconv_profile(lsted_deconv* h, int reset, double* total_ms, long long* launches);
 
+/* ---------------- figure-3 scan-position engine, line_sted_figure_3.py:76-273 -------------
+ * The explicit acquisition simulation `simulate_imaging` of the reference: for every scan
+ * position the excitation is shifted over the (rotated, zero-padded) object, the glow is
+ * (de)scanned, blurred onto the detector and summed the way each method reads its detector.
+ * One handle = one (imaging type, object shape, scan) ; lsted_scan_run does one orientation
+ * with ALL scan positions in flight at once; lsted_scan_frames returns the display planes the
+ * reference hands to its generate_figure (:262-271) for the positions kept by the run.
+ * imaging_type: 0 descan_point, 1 nondescan_multipoint, 2 descan_line, 3 rescan_line (:95-96). */
+typedef struct lsted_scan lsted_scan;
+typedef struct {
+    int imaging_type;
+    int n_y, n_x, pad;      /* object shape before padding, zero padding on every side (:100-102) */
+    int step;               /* scan step in pixels, round(psf_width / (4 R))             (:91)     */
+    int exc_sep;            /* multipoint: spot separation (:131), else 0                          */
+    int num_positions;      /* scan positions (:109-137)                                           */
+    double zoom_factor;     /* rescan line: scale_y factor 1 / (R^2 + 1) (:221-223), else 0        */
+    int blur_radius;        /* detector blur gaussian_filter(., psf_sigma): taps radius (truncate 4) */
+    int exc_radius;         /* excitation blur (sted sigma, truncate=8, :139): taps radius         */
+    size_t chunk_bytes;     /* device memory for the per-position planes in flight; 0 = 4 GiB      */
+} lsted_scan_params_t;
+/* positions [num_positions][2] = (shift_y, shift_x) in the reference's order; blur_taps
+ * [2*blur_radius+1], exc_taps [2*exc_radius+1]: normalised Gaussian taps as scipy builds them. */
+int lsted_scan_create(lsted_scan** out, int device, const lsted_scan_params_t* params,
+                      const int* positions, const double* blur_taps, const double* exc_taps);
+int lsted_scan_destroy(lsted_scan* h);
+/* centered_exc (:104-140), out [n_y+2pad][n_x+2pad] */
+int lsted_scan_excitation(lsted_scan* h, double* out);
+/* One orientation (:152-229).  obj_padded [n0][n1] (n = n + 2 pad); rot_xform = NULL for 0
+ * degrees, else the 6 numbers (2x2 matrix, offset) scipy.ndimage.rotate builds for
+ * rotate(obj, rot) (:382-391: order 3, mode='nearest', clip to [0, 1.1 max]).
+ * frame_positions [num_frames]: ascending scan-position indices whose planes are kept for
+ * lsted_scan_frames (may be NULL / 0).  Outputs (each may be NULL): maxima [num_positions][5]
+ * = maxima of glow, inst_detector_sig, cum_detector_sig, reconstruction, new_signal after every
+ * position (:231-235); reconstruction and cum_detector_sig [n0][n1] after the last position;
+ * device_ms = CUDA-event time of the call's device work.                                     */
+int lsted_scan_run(lsted_scan* h, const double* obj_padded, const double* rot_xform,
+                   const int* frame_positions, int num_frames, double* maxima,
+                   double* reconstruction, double* cum_detector_sig, double* device_ms);
+/* Kept frames first .. first+count-1 of the last run: out [count][6][n_y][n_x] = de-rotated
+ * excitation, de-rotated glow, inst_detector_sig, cum_detector_sig, new_signal, reconstruction,
+ * cropped by `pad` and divided by display_max[6] (:262-271).  inv_xform = NULL for 0 degrees,
+ * else scipy's matrix/offset of rotate(., -rot) (:169-170).                                   */
+int lsted_scan_frames(lsted_scan* h, int first, int count, const double* display_max,
+                      const double* inv_xform, double* out);
+
+/* The resampling helpers of figure 3 (:382-409) as one operator: cubic-spline
+ * scipy.ndimage.affine_transform of `batch` planes [n0][n1] -> [m0][m1], output pixel (i, j)
+ * reads input coordinate matrix*(i, j) + offset (xform [batch][6] = m00 m01 m10 m11 o0 o1).
+ * mode 0 = 'constant' (cval 0; what shift :393-396 and zoom :398-409 use),
+ * mode 1 = 'nearest' (12-sample edge pad before the prefilter; what rotate :382-391 uses).
+ * clip != 0: clip every plane to [0, 1.1 * max(input plane)] like the reference's wrappers.   */
+int lsted_img_spline(int device, int batch, int n0, int n1, const double* planes,
+                     const double* xform, int m0, int m1, int mode, int clip, double* out);
+/* scipy.ndimage.gaussian_filter(mode='reflect') of `batch` planes along axis 0 (taps0) and
+ * axis 1 (taps1); a NULL tap pointer leaves that axis alone (sigma 0), :139,:173,:202,:221.   */
+int lsted_img_gauss(int device, int batch, int n0, int n1, const double* planes,
+                    const double* taps0, int radius0, const double* taps1, int radius1, double* out);
+
 #ifdef __cplusplus
 }
 #endif

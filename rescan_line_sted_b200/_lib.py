@@ -41,6 +41,17 @@ class DeconvInfo(ctypes.Structure):
                 ('band_y0', ctypes.c_int), ('band_y1', ctypes.c_int)]
 
 
+class ScanParams(ctypes.Structure):
+    """lsted_scan_params_t of include/lsted.h"""
+    _fields_ = [('imaging_type', ctypes.c_int),
+                ('n_y', ctypes.c_int), ('n_x', ctypes.c_int), ('pad', ctypes.c_int),
+                ('step', ctypes.c_int), ('exc_sep', ctypes.c_int),
+                ('num_positions', ctypes.c_int),
+                ('zoom_factor', ctypes.c_double),
+                ('blur_radius', ctypes.c_int), ('exc_radius', ctypes.c_int),
+                ('chunk_bytes', ctypes.c_size_t)]
+
+
 # name -> (argtypes); all return int status except the two noted below
 _DECONV_SIGNATURES = {
     'lsted_deconv_create': [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
@@ -102,9 +113,26 @@ _CORE_SIGNATURES = {
                          c_double_p, c_double_p, ctypes.c_double, c_double_p],
 }
 
+# figure-3 scan-position engine and the plane operators it is built from
+_SCAN_SIGNATURES = {
+    'lsted_scan_create': [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                          ctypes.POINTER(ScanParams), c_int_p, c_double_p, c_double_p],
+    'lsted_scan_destroy': [ctypes.c_void_p],
+    'lsted_scan_excitation': [ctypes.c_void_p, c_double_p],
+    'lsted_scan_run': [ctypes.c_void_p, c_double_p, c_double_p, c_int_p, ctypes.c_int,
+                       c_double_p, c_double_p, c_double_p, c_double_p],
+    'lsted_scan_frames': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p,
+                          c_double_p, c_double_p],
+    'lsted_img_spline': [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
+                         c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                         c_double_p],
+    'lsted_img_gauss': [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
+                        c_double_p, ctypes.c_int, c_double_p, ctypes.c_int, c_double_p],
+}
+
 # every symbol include/lsted.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTED_SYMBOLS = (['lsted_last_error'] + sorted(_CORE_SIGNATURES) +
-                    sorted(_DECONV_SIGNATURES))
+                    sorted(_DECONV_SIGNATURES) + sorted(_SCAN_SIGNATURES))
 
 
 class Library:
@@ -152,6 +180,7 @@ def get():
                 'fallback.' % LIBRARY_PATH)
         sigs = dict(_CORE_SIGNATURES)
         sigs.update(_DECONV_SIGNATURES)
+        sigs.update(_SCAN_SIGNATURES)
         _library = Library(LIBRARY_PATH, sigs)
     return _library
 

@@ -1166,3 +1166,85 @@ extern "C" int lsted_psf_rescan(int device, int batch, int n, const double* taps
         return LSTED_OK;
     } catch (const lsted::ApiError& e) { return set_error(e.code, e.msg); }
 }
+
+// ---------------------------------------------------------------------------
+// Figure-3 scan-position engine and the spline / Gaussian plane operators (fp64)
+// ---------------------------------------------------------------------------
+#include "scan_kernels.cuh"
+
+namespace lsted {
+// every scan kernel is an element functor (scan_kernels.cuh) under one grid-stride shell
+template <class F> __global__ void __launch_bounds__(256) scan_for_each_kernel(const F f, size_t n) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+         e += (size_t)gridDim.x * blockDim.x)
+        f(e);
+}
+}  // namespace lsted
+
+namespace {
+struct ScanCudaBackend {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    int sm_count;
+    std::vector<void*> live;
+    explicit ScanCudaBackend(int dev) : device(dev), stream(0), ev0(0), ev1(0), sm_count(148) {
+        select_device(dev);
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreate(&ev0));
+        CUDA_CHECK(cudaEventCreate(&ev1));
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    ~ScanCudaBackend() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (void* p : live) cudaFree(p);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    void activate() { CUDA_CHECK(cudaSetDevice(device)); }
+    template <class T> T* alloc(size_t n) {
+        void* p = 0;
+        CUDA_CHECK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+        live.push_back(p);
+        return (T*)p;
+    }
+    void free(void* p) {
+        for (size_t i = 0; i < live.size(); ++i)
+            if (live[i] == p) { live[i] = live.back(); live.pop_back(); break; }
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaFree(p));
+    }
+    void upload(void* d, const void* h, size_t bytes) {
+        CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    void download(void* h, const void* d, size_t bytes) {
+        CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    void copy(void* d, const void* s, size_t bytes) {
+        CUDA_CHECK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, stream));
+    }
+    void zero(void* d, size_t bytes) { CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, stream)); }
+    void sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
+    void timer_start() { CUDA_CHECK(cudaEventRecord(ev0, stream)); }
+    double timer_stop() {
+        CUDA_CHECK(cudaEventRecord(ev1, stream));
+        CUDA_CHECK(cudaEventSynchronize(ev1));
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+        return ms;
+    }
+    template <class F> void for_each(size_t n, const F& f) {
+        if (!n) return;
+        const size_t want = (n + 255) / 256, cap = (size_t)sm_count * 32;
+        lsted::scan_for_each_kernel<F><<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(f, n);
+        CUDA_CHECK(cudaGetLastError());
+    }
+};
+}  // namespace
+
+#define LSTED_SCAN_BACKEND ScanCudaBackend
+#include "api_scan.inl"

@@ -28,4 +28,5 @@ def emulator_library():
     for name in ('lsted_psf_illumination', 'lsted_psf_rescan', 'lsted_psf_rotate',
                  'lsted_psf_report_batch', 'lsted_gauss_fit'):
         sigs[name] = _lib._CORE_SIGNATURES[name]
+    sigs.update(_lib._SCAN_SIGNATURES)
     return _lib.Library(build_emulator(), sigs)

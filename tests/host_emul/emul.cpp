@@ -514,3 +514,37 @@ extern "C" int emul_fft2_2160(int dir, int precision, const double* in, double* 
 extern "C" int emul_p2p_block_at(int pos, int me, int world, int nxb) {
     return lsted::p2p_block_at(pos, me, world, nxb);
 }
+
+// Figure-3 scan engine and plane operators: the same element functors, run serially
+// (OpenMP over elements where the build has it -- every element is independent).
+#include "../../rescan_line_sted_b200/csrc/scan_kernels.cuh"
+struct ScanHostBackend {
+    std::vector<void*> live;
+    explicit ScanHostBackend(int) {}
+    ~ScanHostBackend() { for (void* p : live) ::free(p); }
+    void activate() {}
+    template <class T> T* alloc(size_t n) {
+        void* p = calloc(n ? n : 1, sizeof(T));
+        if (!p) throw std::bad_alloc();
+        live.push_back(p);
+        return (T*)p;
+    }
+    void free(void* p) {
+        for (size_t i = 0; i < live.size(); ++i)
+            if (live[i] == p) { live[i] = live.back(); live.pop_back(); break; }
+        ::free(p);
+    }
+    void upload(void* d, const void* h, size_t bytes) { memcpy(d, h, bytes); }
+    void download(void* h, const void* d, size_t bytes) { memcpy(h, d, bytes); }
+    void copy(void* d, const void* s, size_t bytes) { memcpy(d, s, bytes); }
+    void zero(void* d, size_t bytes) { memset(d, 0, bytes); }
+    void sync() {}
+    void timer_start() {}
+    double timer_stop() { return 0.0; }
+    template <class F> void for_each(size_t n, const F& f) {
+#pragma omp parallel for schedule(static)
+        for (long long e = 0; e < (long long)n; ++e) f((size_t)e);
+    }
+};
+#define LSTED_SCAN_BACKEND ScanHostBackend
+#include "../../rescan_line_sted_b200/csrc/api_scan.inl"
