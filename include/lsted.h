@@ -125,6 +125,8 @@ int lsted_deconv_destroy(lsted_deconv* h);
 int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info);
 /* options: "exact_clip" (0|1: clip every H_t term before the sum, like :587),
  *          "profile" (0|1: per-kernel CUDA-event timing),
+ *          "graph" (0|1, default 1: replay the four launches of a steady RL iteration as one
+ *          captured CUDA graph -- what makes iterate() at the reference's 128^2 frames cheap),
  *          "forget_normalization" (drop the cached H_t_normalization, :590),
  *          "reset_estimate" (the next iterate() starts from an all-ones estimate, :521-522;
  *          new data alone do not reset it, as in the reference),

@@ -111,6 +111,7 @@ extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double
     if (!h || !name) return set_error(LSTED_ERR_ARG, "null pointer");
     LSTED_TRY
     h->bk->activate();
+    h->e->options_changed();
     if (!strcmp(name, "exact_clip")) {
         h->e->set_exact_clip(value != 0);
         return LSTED_OK;
@@ -131,6 +132,7 @@ extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double
     if (!strcmp(name, "col_sub")) { h->bk->set_col_sub(value != 0); return LSTED_OK; }
     if (!strcmp(name, "real_otf")) { h->bk->set_real_otf(value != 0); return LSTED_OK; }   // before set_psfs
     if (!strcmp(name, "profile")) { h->bk->set_profile(value != 0); return LSTED_OK; }
+    if (!strcmp(name, "graph")) { h->bk->set_graph(value != 0); return LSTED_OK; }
     return set_error(LSTED_ERR_ARG, std::string("unknown option ") + name);
     LSTED_CATCH
 }

@@ -47,6 +47,7 @@ class EngineBase {
     virtual void reset_estimate() = 0;     // the next iterate() starts from ones (ref:521-522)
     virtual void set_sharding(int rank, int world, int k_offset) = 0;
     virtual void set_exact_clip(bool on) = 0;
+    virtual void options_changed() {}      // a kernel-selection switch moved: drop captured launches
     virtual void p2p_export(char* handles_out) = 0;                       // kIpcBytes
     virtual void p2p_attach(const char* all_handles) = 0;                 // [world][kIpcBytes]
     virtual void info(EngineInfo* out) = 0;
@@ -94,6 +95,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         partial = (double*)bk.alloc(sizeof(double) * kReduceBlocks);
     }
     ~DeconvEngine() {
+        options_changed();
         void* all[] = {tw_x, tw_y, otf, spec1, specK, true_object, estimate, norm,
                        scratch, noiseless, noisy, stage64, object64, partial, tmpK, p2p_recv, p2p_flags,
                        otf_real, tmap_specK, tmap_spec1};
@@ -114,6 +116,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
 
     // K7: PSFs (host, float64, [K][ny][nx]) -> OTFs, 1/(Lx*Ly) folded in.
     void set_psfs(const double* psfs_host) {
+        options_changed();
         const size_t n = (size_t)K * ny * nx;
         double* d64 = (double*)bk.alloc(sizeof(double) * n);
         T* dT = (T*)bk.alloc(sizeof(T) * n);
@@ -237,6 +240,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     void set_sharding(int rank_, int world_, int k_offset_) {
         rank = rank_; world = world_; k_offset = k_offset_;
         have_norm = false;
+        options_changed();
     }
     // Fused cross-GPU H_t reduction (fast path only): receive slabs for the partial sums of
     // every (source rank, column block) and the flag / counter words, exported to the peers.
@@ -257,6 +261,45 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         if (world > 1) bk.all_reduce_sum((T*)spec, 2 * spec_elems(g, g.Ny));
     }
 
+    // The steady-state RL iteration is four launches with fixed arguments.  For small objects
+    // (the reference's own 128^2 / 160^2 frames) launch overhead is most of an iterate() call, so
+    // after one plain pass (lazy attribute / tensor-map set-up) the four launches are captured
+    // into a CUDA graph and replayed -- one driver call per iteration.  Any option change,
+    // new PSFs or sharding drops the graph.
+    void* iter_graph = 0;
+    int steady_passes = 0;
+    void options_changed() {
+        if (iter_graph) { bk.graph_destroy(iter_graph); iter_graph = 0; }
+        steady_passes = 0;
+    }
+    void launch_steady_iteration() {
+        // expected = H(estimate); ratio = measurement / expected -> row spectra
+        ColArgs<T> ca = col_args(g);
+        ca.src = spec1; ca.dst = specK; ca.K = K;
+        bk.template launch_col<COL_H, T>(g.nxb, ca);
+        RowArgs<T> rm = row_args(g);
+        rm.nimg = K; rm.spec_in = specK; rm.spec_out = specK; rm.aux = noisy;
+        rm.tmap_in = rm.tmap_out = tmap_specK;
+        bk.template launch_row<ROW_MID, T>(row_blocks(g) * K, rm);
+        ColArgs<T> ct = col_args(g);
+        ct.src = specK; ct.dst = spec1; ct.K = K;
+        if (world > 1 && bk.p2p_ready(g, (int)sizeof(cplx<T>))) {
+            // orientation shards: the sum over ranks happens inside the kernel (peer memory)
+            bk.p2p_fill(ct);
+            bk.template launch_col<COL_HT, T>(g.nxb, ct);
+            bk.p2p_wait(g.nxb);
+        } else {
+            bk.template launch_col<COL_HT, T>(g.nxb, ct);
+            reduce_over_ranks(spec1);   // orientation shards: NCCL sum of partial spectra
+        }
+        RowArgs<T> rf = row_args(g);
+        rf.nimg = 1; rf.spec_in = spec1; rf.spec_out = spec1;
+        rf.real_out = estimate; rf.aux = norm;
+        rf.tmap_in = rf.tmap_out = tmap_spec1;
+        rf.prefetch_ahead = bk.row_final_prefetch_distance();
+        bk.template launch_row<ROW_FINAL, T>(row_blocks(g), rf);
+    }
+
     void iterate(int n) {
         for (int it = 0; it < n; ++it) {
             ensure_norm();
@@ -267,34 +310,30 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
                 bk.template launch_row<ROW_FWD, T>(row_blocks(g), ra);
                 have_estimate = true;
             }
-            // expected = H(estimate); ratio = measurement / expected -> row spectra
-            ColArgs<T> ca = col_args(g);
-            ca.src = spec1; ca.dst = specK; ca.K = K;
-            bk.template launch_col<COL_H, T>(g.nxb, ca);
-            ensure_tmaps();
-            RowArgs<T> rm = row_args(g);
-            rm.nimg = K; rm.spec_in = specK; rm.spec_out = specK; rm.aux = noisy;
-            rm.tmap_in = rm.tmap_out = tmap_specK;
-            bk.template launch_row<ROW_MID, T>(row_blocks(g) * K, rm);
             if (!exact_clip) {
-                ColArgs<T> ct = col_args(g);
-                ct.src = specK; ct.dst = spec1; ct.K = K;
-                if (world > 1 && bk.p2p_ready(g, (int)sizeof(cplx<T>))) {
-                    // orientation shards: the sum over ranks happens inside the kernel (peer memory)
-                    bk.p2p_fill(ct);
-                    bk.template launch_col<COL_HT, T>(g.nxb, ct);
-                    bk.p2p_wait(g.nxb);
+                ensure_tmaps();
+                if (world == 1 && bk.graph_capable()) {
+                    if (!iter_graph && steady_passes >= 1) {
+                        bk.graph_begin();
+                        try { launch_steady_iteration(); }
+                        catch (...) { bk.graph_abort(); throw; }
+                        iter_graph = bk.graph_end();
+                    }
+                    if (iter_graph) bk.graph_launch(iter_graph);
+                    else launch_steady_iteration();
+                    ++steady_passes;
                 } else {
-                    bk.template launch_col<COL_HT, T>(g.nxb, ct);
-                    reduce_over_ranks(spec1);   // orientation shards: NCCL sum of partial spectra
+                    launch_steady_iteration();
                 }
-                RowArgs<T> rf = row_args(g);
-                rf.nimg = 1; rf.spec_in = spec1; rf.spec_out = spec1;
-                rf.real_out = estimate; rf.aux = norm;
-                rf.tmap_in = rf.tmap_out = tmap_spec1;
-                rf.prefetch_ahead = bk.row_final_prefetch_distance();
-                bk.template launch_row<ROW_FINAL, T>(row_blocks(g), rf);
             } else {
+                ColArgs<T> ca = col_args(g);
+                ca.src = spec1; ca.dst = specK; ca.K = K;
+                bk.template launch_col<COL_H, T>(g.nxb, ca);
+                ensure_tmaps();
+                RowArgs<T> rm = row_args(g);
+                rm.nimg = K; rm.spec_in = specK; rm.spec_out = specK; rm.aux = noisy;
+                rm.tmap_in = rm.tmap_out = tmap_specK;
+                bk.template launch_row<ROW_MID, T>(row_blocks(g) * K, rm);
                 ht_from_specK(scratch);
                 bk.rl_update(estimate, scratch, norm, npix);
                 RowArgs<T> ra = row_args(g);

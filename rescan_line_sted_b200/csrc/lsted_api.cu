@@ -457,6 +457,27 @@ class CudaBackend {
         return ms;
     }
     void set_profile(bool on) { profile_ = on; }
+    // ---- CUDA graphs: the steady RL iteration replayed as one driver call (engine.h) ----
+    void set_graph(bool on) { graph_ = on; }
+    bool graph_capable() const { return graph_ && !profile_; }
+    void graph_begin() { CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal)); }
+    void graph_abort() {
+        cudaGraph_t g = 0;
+        cudaStreamEndCapture(stream_, &g);
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+    }
+    void* graph_end() {
+        cudaGraph_t g = 0;
+        CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
+        cudaGraphExec_t exec = 0;
+        cudaError_t err = cudaGraphInstantiate(&exec, g, 0);
+        cudaGraphDestroy(g);
+        CUDA_CHECK(err);
+        return (void*)exec;
+    }
+    void graph_launch(void* exec) { CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)exec, stream_)); }
+    void graph_destroy(void* exec) { if (exec) cudaGraphExecDestroy((cudaGraphExec_t)exec); }
     void set_fast_path(bool on) { use_fast_ = on; }
     void set_row_dual(bool on) { row_dual_ = on; }
     void set_row_plan2(bool on) { row_plan2_ = on; }
@@ -799,6 +820,7 @@ class CudaBackend {
     cudaStream_t stream_;
     size_t bytes_;
     bool profile_, use_fast_;
+    bool graph_ = getenv("LSTED_GRAPH") ? atoi(getenv("LSTED_GRAPH")) != 0 : true;   // A/B switch, option "graph"
     std::map<void*, size_t> sizes_;   // live allocations (for lsted_deconv_info)
     std::map<const void*, size_t> smem_cfg_;   // kernels whose dynamic shared-memory limit is raised
     void* p2p_local_[3] = {0, 0, 0};

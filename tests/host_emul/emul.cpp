@@ -75,6 +75,13 @@ class HostBackend {
     int row_prefetch_distance() const { return 3; }
     int row_final_prefetch_distance() const { return 5; }
     void set_prefetch(bool) {}
+    void set_graph(bool) {}
+    bool graph_capable() const { return false; }   // captured launches exist on the GPU only
+    void graph_begin() {}
+    void graph_abort() {}
+    void* graph_end() { return 0; }
+    void graph_launch(void*) {}
+    void graph_destroy(void*) {}
     static int fast_cols(int L, int cplx_bytes) {
         if (L == Plan2160f::L) return cplx_bytes == 8 ? (int)Plan2160f::C : (int)Plan2160d::C;
         return 0;

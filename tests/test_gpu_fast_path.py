@@ -97,3 +97,38 @@ def test_sub_block_column_ctas_are_bit_identical(shape, K):
         h.close()
     assert np.isfinite(est[1]).all() and est[1].min() > 0
     assert np.array_equal(est[0], est[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape,K,precision', [((128, 128), 4, 32), ((128, 160), 3, 64),
+                                               ((2048, 2048), 2, 32)])
+def test_graph_replay_of_the_iteration_is_bit_identical(shape, K, precision):
+    """The steady RL iteration replayed as a captured CUDA graph (option `graph`, default on)
+    against four plain launches: same kernels, same arguments -> identical bits; new data,
+    a reset estimate, an option change and mixed iterate(1) / iterate(n) calls in between."""
+    from rescan_line_sted_b200 import _lib
+    lib = _lib.get()
+    rng = np.random.default_rng(11)
+    psfs = rng.random((K, 9, 11))
+    x = rng.random((1,) + shape) + 0.1
+    est = {}
+    for graph in (0, 1):
+        h = _lib.DeconvHandle(lib, psfs, shape, precision=precision)
+        h.set_option('graph', graph)
+        h.create_data(x, 1e6 * x.size, 1)
+        for _ in range(3):
+            h.iterate(1)
+        h.iterate(4)
+        a = h.get(_lib.ESTIMATE)
+        h.set_option('exact_clip', 1)
+        h.iterate(2)
+        h.set_option('exact_clip', 0)
+        h.iterate(3)
+        b = h.get(_lib.ESTIMATE)
+        h.create_data(x[:, ::-1].copy(), 2e6 * x.size, 2)      # new data, estimate restarts
+        h.iterate(5)
+        est[graph] = (a, b, h.get(_lib.ESTIMATE))
+        h.close()
+    for u, v in zip(est[0], est[1]):
+        assert np.isfinite(v).all() and v.min() > 0
+        assert np.array_equal(u, v)
