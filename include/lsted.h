@@ -110,6 +110,7 @@ typedef struct {
     int tiles_y, tiles_x;        /* overlap-save tiling of large objects (1 x 1: none) */
     int tile_out_y, tile_out_x;  /* pixels of the object each tile produces            */
     int band_y0, band_y1;        /* image rows owned by this rank (tiled + sharded)    */
+    int band_x0, band_x1;        /* image columns owned by this rank                    */
 } lsted_deconv_info_t;
 
 /* Deconvolver.__init__ (:479-494): psfs = [K][ny][nx].  precision 32 | 64.          */
@@ -158,10 +159,13 @@ int lsted_deconv_simulate(lsted_deconv* h, double total_brightness, int rescale,
  * on rank 0, distributed by the caller (e.g. torch.distributed broadcast).  NCCL is
  * dlopen()ed on first use; single-GPU users do not need it.
  * A TILED handle (lsted_deconv_create_tiled) shards differently: every rank gets ALL
- * PSFs and owns a horizontal band of the object (k_offset is ignored); measurements and
- * ratios live on the band plus the PSF halo (recomputed redundantly, identical noise
- * because the Poisson stream is keyed by the global pixel index) and the only exchange
- * is one ncclBroadcast of each band of the replicated estimate per RL iteration.      */
+ * PSFs and the overlap-save tiles are dealt to a 2-D grid of ranks (k_offset is ignored);
+ * a rank keeps measurements and ratios on its rectangle of the image (band_y0..band_x1 of
+ * lsted_deconv_info; identical noise on any rank count because the Poisson stream is keyed
+ * by the global pixel index) and per RL iteration receives the PSF-halo ring of the
+ * estimate and of the K ratio images from the neighbouring ranks (grouped ncclSend /
+ * ncclRecv of packed strips).  lsted_deconv_get(LSTED_ESTIMATE) on such a handle is a
+ * collective call (one all-reduce assembles the owners' rectangles on every rank).     */
 enum { LSTED_NCCL_UNIQUE_ID_BYTES = 128 };
 int lsted_nccl_unique_id(char* out);
 int lsted_deconv_shard(lsted_deconv* h, int rank, int world, int k_offset, const char* unique_id);

@@ -38,7 +38,8 @@ class DeconvInfo(ctypes.Structure):
                 ('bytes_iteration', ctypes.c_double),
                 ('tiles_y', ctypes.c_int), ('tiles_x', ctypes.c_int),
                 ('tile_out_y', ctypes.c_int), ('tile_out_x', ctypes.c_int),
-                ('band_y0', ctypes.c_int), ('band_y1', ctypes.c_int)]
+                ('band_y0', ctypes.c_int), ('band_y1', ctypes.c_int),
+                ('band_x0', ctypes.c_int), ('band_x1', ctypes.c_int)]
 
 
 class ScanParams(ctypes.Structure):

@@ -103,6 +103,7 @@ extern "C" int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info) {
     info->tiles_y = ei.tiles_y; info->tiles_x = ei.tiles_x;
     info->tile_out_y = ei.tile_out_y; info->tile_out_x = ei.tile_out_x;
     info->band_y0 = ei.band_y0; info->band_y1 = ei.band_y1;
+    info->band_x0 = ei.band_x0; info->band_x1 = ei.band_x1;
     return LSTED_OK;
     LSTED_CATCH
 }

@@ -29,6 +29,7 @@ struct EngineInfo {
     size_t row_smem, col_smem;
     int tiles_y, tiles_x, tile_out_y, tile_out_x;   // 1 x 1 unless the object is tiled
     int band_y0, band_y1;                           // image rows owned by this rank (tiled + sharded)
+    int band_x0, band_x1;                           // image columns owned by this rank
 };
 class EngineBase {
   public:
@@ -112,6 +113,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         o->col_smem = col_smem_bytes(g, (int)sizeof(cplx<T>));
         o->tiles_y = o->tiles_x = 1; o->tile_out_y = g.Ny; o->tile_out_x = g.Nx;
         o->band_y0 = 0; o->band_y1 = g.Ny;
+        o->band_x0 = 0; o->band_x1 = g.Nx;
     }
 
     // K7: PSFs (host, float64, [K][ny][nx]) -> OTFs, 1/(Lx*Ly) folded in.

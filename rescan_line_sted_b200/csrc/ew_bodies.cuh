@@ -54,8 +54,10 @@ template <typename T> struct WinArgs {
     int nimg, W, Ny, Nx;
     int y0, x0;       // image coordinates of tile pixel (0, 0)
     int iy0, iy1, ix0, ix1;  // interior of the window (tile coordinates)
-    int by0, brows;   // the big arrays hold image rows [by0, by0 + brows) (a band of a sharded object)
-    int sy0, sy1;     // only image rows [sy0, sy1) are written back
+    int by0, brows;   // the big arrays hold image rows [by0, by0 + brows) ...
+    int bx0, bcols;   // ... and columns [bx0, bx0 + bcols): the region a rank of a sharded object keeps
+    int sy0, sy1;     // only image rows [sy0, sy1) ...
+    int sx0, sx1;     // ... and columns [sx0, sx1) are written back (the rank's own tiles)
     unsigned long long seed;
     unsigned int img0;
 };
@@ -67,11 +69,14 @@ template <int OP, typename T> LSTED_HD void win_apply(const WinArgs<T>& a, size_
     const int wy = (int)(r / a.W), wx = (int)(r - (size_t)wy * a.W);
     const int gy = a.y0 + wy, gx = a.x0 + wx;
     const bool inside = gy >= 0 && gy < a.Ny && gx >= 0 && gx < a.Nx;
-    const bool held = inside && gy >= a.by0 && gy < a.by0 + a.brows;   // row present in `big`
-    const size_t gi = (size_t)img * a.brows * a.Nx + (size_t)(held ? gy - a.by0 : 0) * a.Nx + (held ? gx : 0);
+    const bool held = inside && gy >= a.by0 && gy < a.by0 + a.brows &&
+                      gx >= a.bx0 && gx < a.bx0 + a.bcols;             // pixel present in `big`
+    const size_t gi = (size_t)img * a.brows * a.bcols + (size_t)(held ? gy - a.by0 : 0) * a.bcols +
+                      (held ? gx - a.bx0 : 0);
     if (OP == WIN_LOAD) { a.tile[e] = held ? a.big[gi] : (T)0; return; }
     if (OP == WIN_ONES) { a.tile[e] = inside ? (T)1 : (T)0; return; }
-    if (!held || gy < a.sy0 || gy >= a.sy1 || wy < a.iy0 || wy >= a.iy1 || wx < a.ix0 || wx >= a.ix1)
+    if (!held || gy < a.sy0 || gy >= a.sy1 || gx < a.sx0 || gx >= a.sx1 ||
+        wy < a.iy0 || wy >= a.iy1 || wx < a.ix0 || wx >= a.ix1)
         return;
     const T v = a.tile[e];
     if (OP == WIN_STORE) a.big[gi] = v;
@@ -81,6 +86,23 @@ template <int OP, typename T> LSTED_HD void win_apply(const WinArgs<T>& a, size_
         a.big2[gi] = (T)(poisson_sample((double)v, a.seed, pix, a.img0 + img) + 1e-9);
     } else if (OP == WIN_RATIO) a.big[gi] = v > (T)0 ? a.big2[gi] / v : (T)0;   // see rl_ratio (conv_bodies.cuh)
     else if (OP == WIN_UPDATE) a.big[gi] = a.big[gi] * (v / a.big2[gi]);
+}
+
+// Rectangle copy between strided image stacks: packs / unpacks the halo strips a sharded tiled
+// object exchanges with its neighbours, and places a rank's region in a full-size image.
+template <typename T> struct RectArgs {
+    T* dst; const T* src;
+    int nimg, h, w;                        // rectangle: h rows of w pixels in each of nimg images
+    size_t dst_img, dst_pitch, dst_off;    // element strides; offset of the rectangle's first pixel
+    size_t src_img, src_pitch, src_off;
+};
+template <typename T> LSTED_HD void rect_apply(const RectArgs<T>& a, size_t e) {
+    const int x = (int)(e % a.w);
+    const size_t t = e / a.w;
+    const int y = (int)(t % a.h);
+    const size_t img = t / a.h;
+    a.dst[a.dst_off + img * a.dst_img + (size_t)y * a.dst_pitch + x] =
+        a.src[a.src_off + img * a.src_img + (size_t)y * a.src_pitch + x];
 }
 
 }  // namespace lsted

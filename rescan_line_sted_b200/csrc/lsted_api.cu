@@ -184,6 +184,14 @@ __global__ void __launch_bounds__(kEwThreads) win_kernel(const lsted::WinArgs<T>
 }
 
 template <typename T>
+__global__ void __launch_bounds__(kEwThreads) rect_kernel(const lsted::RectArgs<T> a) {
+    const size_t n = (size_t)a.nimg * a.h * a.w;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+        lsted::rect_apply<T>(a, e);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) otf_center_kernel(const lsted::OtfCenterArgs<T> a) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
@@ -235,10 +243,14 @@ struct NcclApi {
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*CommDestroy)(ncclComm_t);
     const char* (*GetErrorString)(ncclResult_t);
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
     bool ok;
 };
 static NcclApi& nccl_api() {
-    static NcclApi api = {0, 0, 0, 0, 0, 0, false};
+    static NcclApi api = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, false};
     if (api.ok) return api;
     void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -255,7 +267,11 @@ static NcclApi& nccl_api() {
                                      cudaStream_t))dlsym(lib, "ncclBroadcast");
     api.CommDestroy = (ncclResult_t(*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
     api.GetErrorString = (const char* (*)(ncclResult_t))dlsym(lib, "ncclGetErrorString");
-    if (!api.Broadcast || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString) {
+    api.Send = (ncclResult_t(*)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclSend");
+    api.Recv = (ncclResult_t(*)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclRecv");
+    api.GroupStart = (ncclResult_t(*)())dlsym(lib, "ncclGroupStart");
+    api.GroupEnd = (ncclResult_t(*)())dlsym(lib, "ncclGroupEnd");
+    if (!api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd || !api.Broadcast || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString) {
         lsted::ApiError e; e.code = LSTED_ERR_NCCL; e.msg = "libnccl lacks a required symbol";
         throw e;
     }
@@ -351,6 +367,30 @@ class CudaBackend {
     void broadcast(double* p, size_t n, int root) {
         before(KK_EW);
         NCCL_CHECK(nccl_api().Broadcast(p, p, n, ncclDouble, root, comm_, stream_));
+        after();
+    }
+    // Halo exchange of a tile-sharded object (tiled.h): one grouped ncclSend / ncclRecv pair per
+    // neighbour, contiguous staging buffers (counts in elements of T).
+    template <typename T> void exchange(int npeers, const int* peers, T* const* send, const size_t* nsend,
+                                        T* const* recv, const size_t* nrecv) {
+        const ncclDataType_t dt = sizeof(T) == 4 ? ncclFloat : ncclDouble;
+        before(KK_EW);
+        NCCL_CHECK(nccl_api().GroupStart());
+        for (int i = 0; i < npeers; ++i) {
+            if (nsend[i]) NCCL_CHECK(nccl_api().Send(send[i], nsend[i], dt, peers[i], comm_, stream_));
+            if (nrecv[i]) NCCL_CHECK(nccl_api().Recv(recv[i], nrecv[i], dt, peers[i], comm_, stream_));
+        }
+        NCCL_CHECK(nccl_api().GroupEnd());
+        after();
+    }
+    template <typename T> void launch_rect(const lsted::RectArgs<T>& a) {
+        const size_t n = (size_t)a.nimg * a.h * a.w;
+        if (n == 0) return;
+        size_t blocks = (n + kEwThreads - 1) / kEwThreads;
+        const size_t cap = (size_t)num_sms_ * 16;
+        if (blocks > cap) blocks = cap;
+        before(KK_EW);
+        rect_kernel<T><<<(int)blocks, kEwThreads, 0, stream_>>>(a);
         after();
     }
     // ---- fused cross-GPU reduction over peer memory (orientation sharding, fast path) ----

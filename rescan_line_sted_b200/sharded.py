@@ -113,11 +113,12 @@ class OrientationShardedDeconvolver:
 
 
 class TileShardedDeconvolver:
-    """A large object processed in overlap-save tiles with the image rows split
-    into one horizontal band per rank (BASELINE config 5).  Every rank passes
-    the same PSFs, object and seed; measurements and ratios exist only on the
-    rank's band (plus the PSF halo, recomputed redundantly), the estimate is a
-    replica refreshed by one NCCL broadcast per band per RL iteration."""
+    """A large object processed in overlap-save tiles, the tiles dealt to a 2-D grid of
+    ranks (BASELINE config 5: 4 x 4 tiles of 8192^2 on a 2 x 4 grid of 8 GPUs).  Every rank
+    passes the same PSFs, object and seed; measurements and ratios exist only on the rank's
+    rectangle `rows` x `cols`; per RL iteration the PSF-halo ring of the estimate and of the K
+    ratio images is exchanged with the neighbouring ranks (grouped ncclSend / ncclRecv).
+    `estimate` assembles the full image from the owners: call it on every rank."""
 
     def __init__(self, psfs, image_shape, precision=64, device=0, group=None,
                  lib=None, tile_fft_len=2160):
@@ -136,12 +137,13 @@ class TileShardedDeconvolver:
         self.handle.shard(self.rank, self.world, 0, unique_id[0])
         info = self.handle.info()
         self.rows = (info.band_y0, info.band_y1)
+        self.cols = (info.band_x0, info.band_x1)
 
     def create_data(self, obj, total_brightness, seed):
         self.handle.create_data(obj, total_brightness, seed)
 
     def set_noisy(self, k, image):
-        """Full-size image; the rank keeps the rows of its band."""
+        """Full-size image; the rank keeps its rectangle."""
         self.handle.set(_lib.NOISY, k, image)
 
     def iterate(self, n=1):
@@ -152,7 +154,7 @@ class TileShardedDeconvolver:
         return self.handle.get(_lib.ESTIMATE)
 
     def local_measurement(self, k, which=_lib.NOISY):
-        """Rows of the band (and its halo); zeros elsewhere."""
+        """The rank's rectangle of the image; zeros elsewhere."""
         return self.handle.get(which, k)
 
     def close(self):

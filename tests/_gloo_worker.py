@@ -39,6 +39,25 @@ def main():
 
     lib.cdll.emul_set_broadcast(broadcast)
 
+    # halo exchange of the tile-sharded engine (grouped ncclSend / ncclRecv on the GPU)
+    dp, sp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_size_t)
+
+    @ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(dp), sp,
+                      ctypes.POINTER(dp), sp)
+    def exchange(npeers, peers, send, nsend, recv, nrecv):
+        ops, keep = [], []
+        for i in range(npeers):
+            if nsend[i]:
+                t = torch.from_numpy(np.ctypeslib.as_array(send[i], shape=(nsend[i],)))
+                ops.append(dist.P2POp(dist.isend, t, peers[i]))
+            if nrecv[i]:
+                t = torch.from_numpy(np.ctypeslib.as_array(recv[i], shape=(nrecv[i],)))
+                ops.append(dist.P2POp(dist.irecv, t, peers[i]))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    lib.cdll.emul_set_exchange(exchange)
+
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'fig2_2p0x_lr.npz'))
     out = {}
     for precision, tag in ((64, 'fp64'), (32, 'fp32')):
@@ -64,7 +83,8 @@ def main():
         out[tag] = {'noiseless': err_nl, 'est1': e1, 'norm': en, 'est8': e8,
                     'replica_diff': float((t - ref).abs().max())}
         d.close()
-    # tiled object sharded into row bands (config-5 style), against one unsharded handle
+    # tiled object, tiles dealt to a grid of ranks with halo exchange (config-5 style), against
+    # one unsharded handle
     rng = np.random.default_rng(4)
     psfs = rng.random((3, 9, 11))
     obj = rng.random((1, 150, 170))
@@ -73,12 +93,12 @@ def main():
     single.iterate(4)
     t = sharded.TileShardedDeconvolver(psfs, (150, 170), precision=64, lib=lib, tile_fft_len=64)
     t.create_data(obj, 1e7, 9)
-    a, b = t.rows
-    noisy_same = all(np.array_equal(t.local_measurement(k)[0, a:b], single.get(_lib.NOISY, k)[0, a:b])
-                     for k in range(3))
+    (a, b), (c, d2) = t.rows, t.cols
+    noisy_same = all(np.array_equal(t.local_measurement(k)[0, a:b, c:d2],
+                                    single.get(_lib.NOISY, k)[0, a:b, c:d2]) for k in range(3))
     t.iterate(4)
     est = single.get(_lib.ESTIMATE)
-    out['tiles'] = {'rows': [int(a), int(b)], 'noisy_same': bool(noisy_same),
+    out['tiles'] = {'rows': [int(a), int(b)], 'cols': [int(c), int(d2)], 'noisy_same': bool(noisy_same),
                     'est': float(np.linalg.norm(t.estimate - est) / np.linalg.norm(est))}
     t.close(), single.close()
     # sweep sharding: 6 operating points dealt round-robin, gathered in order

@@ -74,7 +74,7 @@ def main():
         os.environ.pop('LSTED_P2P', None)
         out[tag] = dict(res, tol=tol)
         single.close()
-    # tiled object, row bands over the GPUs, 2160-point tiles (fast path), fp64
+    # tiled object, tiles dealt to the GPUs with halo exchange, 2160-point tiles (fast path), fp64
     rng = np.random.default_rng(4)
     psfs = rng.random((2, 9, 11))
     obj = rng.random((1, 2300, 2200))
@@ -84,12 +84,12 @@ def main():
     single.iterate(2)
     t = sharded.TileShardedDeconvolver(psfs, (2300, 2200), precision=64, device=local)
     t.create_data(obj, 1e9, 9)
-    a, b = t.rows
-    same = all(np.array_equal(t.local_measurement(k)[0, a:b], single.get(_lib.NOISY, k)[0, a:b])
-               for k in range(2))
+    (a, b), (c, d2) = t.rows, t.cols
+    same = all(np.array_equal(t.local_measurement(k)[0, a:b, c:d2],
+                              single.get(_lib.NOISY, k)[0, a:b, c:d2]) for k in range(2))
     t.iterate(2)
     est = single.get(_lib.ESTIMATE)
-    out['tiles'] = {'noisy_same': bool(same),
+    out['tiles'] = {'noisy_same': bool(same), 'rect': [int(a), int(b), int(c), int(d2)],
                     'est': float(np.linalg.norm(t.estimate - est) / np.linalg.norm(est))}
     t.close(), single.close()
     if rank == 0:

@@ -47,6 +47,12 @@ template <> struct PlanFor<double> { typedef Plan2160d type; };
 
 typedef void (*allreduce_cb)(double* buf, size_t n);
 typedef void (*broadcast_cb)(double* buf, size_t n, int root);
+// halo exchange of a tile-sharded object: npeers, peers, send pointers / counts, receive
+// pointers / counts (float64 elements); the test routes it to torch.distributed isend / irecv
+typedef void (*exchange_cb)(int npeers, const int* peers, double* const* send, const size_t* nsend,
+                            double* const* recv, const size_t* nrecv);
+static exchange_cb g_exchange = 0;
+extern "C" void emul_set_exchange(exchange_cb cb) { g_exchange = cb; }
 static allreduce_cb g_allreduce = 0;
 static broadcast_cb g_broadcast = 0;
 extern "C" void emul_set_allreduce(allreduce_cb cb) { g_allreduce = cb; }
@@ -302,6 +308,28 @@ class HostBackend {
     }
     template <int OP, typename T> void ew(const lsted::EwArgs<T>& a) {
         for (size_t i = 0; i < a.n; ++i) lsted::ew_apply<OP, T>(a, i);
+    }
+    template <typename T> void launch_rect(const lsted::RectArgs<T>& a) {
+        const size_t n = (size_t)a.nimg * a.h * a.w;
+        for (size_t e = 0; e < n; ++e) lsted::rect_apply<T>(a, e);
+    }
+    void exchange(int npeers, const int* peers, double* const* send, const size_t* nsend,
+                  double* const* recv, const size_t* nrecv) {
+        if (!g_exchange) throw std::string("no exchange callback installed");
+        g_exchange(npeers, peers, send, nsend, recv, nrecv);
+    }
+    void exchange(int npeers, const int* peers, float* const* send, const size_t* nsend,
+                  float* const* recv, const size_t* nrecv) {
+        std::vector<std::vector<double> > s(npeers), r(npeers);
+        std::vector<double*> sp(npeers), rp(npeers);
+        for (int i = 0; i < npeers; ++i) {
+            s[i].assign(send[i], send[i] + nsend[i]);
+            r[i].resize(nrecv[i]);
+            sp[i] = s[i].data(); rp[i] = r[i].data();
+        }
+        exchange(npeers, peers, sp.data(), nsend, rp.data(), nrecv);
+        for (int i = 0; i < npeers; ++i)
+            for (size_t k = 0; k < nrecv[i]; ++k) recv[i][k] = (float)r[i][k];
     }
     template <int OP, typename T> void launch_win(const lsted::WinArgs<T>& a) {
         const size_t n = (size_t)a.nimg * a.W * a.W;
