@@ -245,6 +245,12 @@ LSTED_HD double scan_src(const ScanGeom& g, int p, int y, int x) {
     return g.rot_obj[(size_t)oy * g.n1 + ox] * g.cexc[(size_t)y * g.n1 + x];
 }
 
+// scipy 'reflect' index without the integer division of reflect_idx (|i| is within a few n here)
+LSTED_HD int reflect_near(int i, int n) {
+    while ((unsigned)i >= (unsigned)n) i = i < 0 ? -1 - i : 2 * n - 1 - i;
+    return i;
+}
+
 struct ScanBlur0Fn {   // first pass of the detector blur (axis 0) of positions p0 .. p0+count-1
     ScanGeom g;
     int p0, radius;
@@ -257,8 +263,99 @@ struct ScanBlur0Fn {   // first pass of the detector blur (axis 0) of positions 
         const int p = p0 + (int)(t / g.n0);
         double acc = scan_src(g, p, y, x) * taps[radius];
         for (int d = radius; d >= 1; --d)
-            acc += (scan_src(g, p, reflect_idx(y - d, g.n0), x) +
-                    scan_src(g, p, reflect_idx(y + d, g.n0), x)) * taps[radius - d];
+            acc += (scan_src(g, p, reflect_near(y - d, g.n0), x) +
+                    scan_src(g, p, reflect_near(y + d, g.n0), x)) * taps[radius - d];
+        out[e] = acc;
+    }
+};
+
+// The excitation of a line / point scan is confined to a band (box) around the optical axis,
+// so the descanned glow is, and after the blur its support has only grown by the blur radius.
+// When that support stays clear of the image edges (the reflect boundary never folds it) both
+// blur passes work on the support alone: `src` = rows / columns where the blur's input can be
+// non-zero, `dst` = where its output can be.
+struct ScanSupport {
+    int src_y0, src_y1, src_x0, src_x1;
+    int dst_y0, dst_y1;          // rows after pass 0 (and after pass 1)
+    int dst_x0, dst_x1;          // columns after pass 1
+};
+enum { kBlurStrip = 8 };
+
+// Pass 0 on the support: one thread = kBlurStrip consecutive output rows of one column; every
+// source sample is loaded once for the whole strip and the taps it meets slide through
+// registers.  taps_ext = the taps with kBlurStrip zeros on either side.  Writes rows
+// [dst_y0, dst_y1) x columns [src_x0, src_x1) of `out` only (pass 1 reads nothing else).
+struct ScanBlur0StripFn {
+    ScanGeom g;
+    ScanSupport sp;
+    int p0, radius, nstrips;
+    const double* taps_ext;
+    double* out;        // [count][n0][n1]
+    LSTED_HD void operator()(size_t e) const {
+        const int wx = sp.src_x1 - sp.src_x0;
+        const int x = sp.src_x0 + (int)(e % wx);
+        const size_t t = e / wx;
+        const int ya = sp.dst_y0 + (int)(t % nstrips) * kBlurStrip;
+        const size_t pl = t / nstrips;
+        const int p = p0 + (int)pl;
+        double acc[kBlurStrip];
+#pragma unroll
+        for (int j = 0; j < kBlurStrip; ++j) acc[j] = 0.0;
+        // sample u sits at row ya - radius + u and meets output j with tap u - j
+        const int first = ya - radius;
+        const int nsamp = kBlurStrip + 2 * radius;
+        for (int u0 = 0; u0 < nsamp; u0 += kBlurStrip) {
+            double w[2 * kBlurStrip - 1];   // taps u0 - (kBlurStrip-1) .. u0 + kBlurStrip - 1
+#pragma unroll
+            for (int i = 0; i < 2 * kBlurStrip - 1; ++i) w[i] = taps_ext[u0 + 1 + i];
+#pragma unroll
+            for (int q = 0; q < kBlurStrip; ++q) {
+                const int row = first + u0 + q;
+                const double v = row >= sp.src_y0 && row < sp.src_y1 ? scan_src(g, p, row, x) : 0.0;
+#pragma unroll
+                for (int j = 0; j < kBlurStrip; ++j) acc[j] += v * w[q - j + kBlurStrip - 1];
+            }
+        }
+        double* o = out + (pl * g.n0 + ya) * (size_t)g.n1 + x;
+#pragma unroll
+        for (int j = 0; j < kBlurStrip; ++j)
+            if (ya + j < sp.dst_y1) o[(size_t)j * g.n1] = acc[j];
+    }
+};
+
+// Pass 1 on the support: zeros outside [dst_y0, dst_y1) x [dst_x0, dst_x1); inside, the taps
+// that reach source columns [src_x0, src_x1), centre first and pairs from the outside in.
+struct ScanBlur1SupportFn {
+    const double* in; double* out;
+    ScanSupport sp;
+    int n0, n1, radius;
+    int full_width;     // the source spans every column (line scans): reflect at the row ends
+    const double* taps;
+    LSTED_HD void operator()(size_t e) const {
+        const int x = (int)(e % n1);
+        const size_t t = e / n1;
+        const int y = (int)(t % n0);
+        double acc = 0.0;
+        if (y >= sp.dst_y0 && y < sp.dst_y1 && x >= sp.dst_x0 && x < sp.dst_x1) {
+            const double* row = in + t * (size_t)n1;
+            if (full_width) {
+                acc = row[x] * taps[radius];
+                if (x >= radius && x + radius < n1) {
+                    for (int d = radius; d >= 1; --d) acc += (row[x - d] + row[x + d]) * taps[radius - d];
+                } else {
+                    for (int d = radius; d >= 1; --d)
+                        acc += (row[reflect_near(x - d, n1)] + row[reflect_near(x + d, n1)]) * taps[radius - d];
+                }
+            } else {
+                if (x >= sp.src_x0 && x < sp.src_x1) acc = row[x] * taps[radius];
+                for (int d = radius; d >= 1; --d) {
+                    const int a = x - d, b = x + d;
+                    const double va = a >= sp.src_x0 && a < sp.src_x1 ? row[a] : 0.0;
+                    const double vb = b >= sp.src_x0 && b < sp.src_x1 ? row[b] : 0.0;
+                    acc += (va + vb) * taps[radius - d];
+                }
+            }
+        }
         out[e] = acc;
     }
 };
@@ -488,7 +585,9 @@ public:
     BK& bk;
     std::vector<int> h_pos;
     int* d_pos = nullptr;
-    double *d_blur = nullptr, *d_exc_taps = nullptr;
+    double *d_blur = nullptr, *d_blur_ext = nullptr, *d_exc_taps = nullptr;
+    ScanSupport sup;
+    bool use_support = false;
     double *d_obj = nullptr, *d_rot = nullptr, *d_cexc = nullptr;
     double *d_colsum = nullptr, *d_total = nullptr, *d_regsum = nullptr, *d_cum = nullptr;
     double *d_partial = nullptr, *d_max = nullptr;   // [chunk][segments], [P][3]: glow, inst, cum
@@ -533,6 +632,13 @@ public:
         bk.upload(d_pos, positions, sizeof(int) * 2 * (size_t)p.num_pos);
         d_blur = bk.template alloc<double>(2 * p.blur_radius + 1);
         bk.upload(d_blur, blur_taps, sizeof(double) * (2 * p.blur_radius + 1));
+        {   // taps with kBlurStrip zeros on either side (strip kernel)
+            std::vector<double> ext(2 * p.blur_radius + 1 + 4 * kBlurStrip, 0.0);
+            for (int i = 0; i <= 2 * p.blur_radius; ++i) ext[kBlurStrip + i] = blur_taps[i];
+            d_blur_ext = bk.template alloc<double>(ext.size());
+            bk.upload(d_blur_ext, ext.data(), sizeof(double) * ext.size());
+        }
+        find_support();
         d_exc_taps = bk.template alloc<double>(2 * p.exc_radius + 1);
         bk.upload(d_exc_taps, exc_taps, sizeof(double) * (2 * p.exc_radius + 1));
         d_obj = bk.template alloc<double>(plane);
@@ -552,9 +658,30 @@ public:
         make_excitation();
     }
     ~ScanEngine() {
-        void* all[] = {d_pos, d_blur, d_exc_taps, d_obj, d_rot, d_cexc, d_colsum, d_total, d_regsum,
+        void* all[] = {d_pos, d_blur, d_blur_ext, d_exc_taps, d_obj, d_rot, d_cexc, d_colsum, d_total, d_regsum,
                        d_cum, d_partial, d_max, d_a, d_b, d_inst_store, d_cum_store, d_frame_pos, d_slot};
         for (void* p : all) if (p) bk.free(p);
+    }
+
+    // Where the descanned glow and its blur can be non-zero (see ScanSupport).  Multipoint
+    // excitation covers the frame, and a support that reaches an edge may be folded back by the
+    // reflect boundary: both keep the general kernels.
+    void find_support() {
+        use_support = false;
+        if (g.type == SCAN_MULTIPOINT) return;
+        const int re = prm.exc_radius, rb = prm.blur_radius;
+        sup.src_y0 = g.n0 / 2 - re; sup.src_y1 = g.n0 / 2 + re + 1;
+        if (g.type == SCAN_DESCAN_POINT) { sup.src_x0 = g.n1 / 2 - re; sup.src_x1 = g.n1 / 2 + re + 1; }
+        else { sup.src_x0 = 0; sup.src_x1 = g.n1; }
+        sup.dst_y0 = sup.src_y0 - rb; sup.dst_y1 = sup.src_y1 + rb;
+        if (sup.dst_y0 < 0 || sup.dst_y1 > g.n0) return;
+        if (g.type == SCAN_DESCAN_POINT) {
+            sup.dst_x0 = sup.src_x0 - rb; sup.dst_x1 = sup.src_x1 + rb;
+            if (sup.dst_x0 < 0 || sup.dst_x1 > g.n1) return;
+        } else {   // a line runs edge to edge: pass 1 reflects at the left / right edge
+            sup.dst_x0 = 0; sup.dst_x1 = g.n1;
+        }
+        use_support = true;
     }
 
     // centred excitation (:104-140): delta line / point / spot lattice, blurred by the STED width
@@ -651,10 +778,19 @@ public:
             bk.for_each((size_t)cnt * kReduceSegments, gm);
             PlaneReduceFinalFn gf{d_partial, d_max + 3 * (size_t)p0 + 0, 3, 1, 1.0};
             bk.for_each(cnt, gf);
-            ScanBlur0Fn b0{g, p0, prm.blur_radius, d_blur, d_a};
-            bk.for_each(elems, b0);
-            ImgFirFn b1{d_a, d_b, g.n0, g.n1, 1, prm.blur_radius, d_blur};
-            bk.for_each(elems, b1);
+            if (use_support) {
+                const int nstrips = (sup.dst_y1 - sup.dst_y0 + kBlurStrip - 1) / kBlurStrip;
+                ScanBlur0StripFn b0{g, sup, p0, prm.blur_radius, nstrips, d_blur_ext, d_a};
+                bk.for_each((size_t)cnt * nstrips * (sup.src_x1 - sup.src_x0), b0);
+                ScanBlur1SupportFn b1{d_a, d_b, sup, g.n0, g.n1, prm.blur_radius,
+                                      g.type != SCAN_DESCAN_POINT, d_blur};
+                bk.for_each(elems, b1);
+            } else {
+                ScanBlur0Fn b0{g, p0, prm.blur_radius, d_blur, d_a};
+                bk.for_each(elems, b0);
+                ImgFirFn b1{d_a, d_b, g.n0, g.n1, 1, prm.blur_radius, d_blur};
+                bk.for_each(elems, b1);
+            }
             double* inst = d_b;
             if (g.type == SCAN_RESCAN_LINE) {
                 ImgPrefilterFn pf{d_b, g.n0, g.n1, 0, 0};
