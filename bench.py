@@ -526,6 +526,15 @@ def main():
                                 'lmdif width fits, rescan PSF, doses), points dealt round-robin over '
                                 'the GPUs, reports gathered once; wall clock, max over ranks')
 
+    # ---- config 2 (the reference's own 128^2 frames) and the figure-3 scan engine, N = 1 ----
+    config2_record = scan_record = None
+    if world == 1 and not args.no_sweep:
+        sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+        import config2_times
+        import scan_times
+        config2_record = config2_times.bench_record()
+        scan_record = scan_times.bench_record()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -604,6 +613,10 @@ def main():
         extra['fp64'] = fp64_record
     if sweep_record:
         extra['config3_sweep'] = sweep_record
+    if config2_record:
+        extra['config2'] = config2_record
+    if scan_record:
+        extra['scan_engine'] = scan_record
     if orientation_record:
         line['orientation_sharded'] = orientation_record
     if extra:

@@ -21,10 +21,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
-def make_psfs(K, n=107):
-    from oracle import line_sted_oracle as orc
-    rep = orc.psf_report('line', 0.21672180512595912, 11.766131198861775, 25, 5, use_closed_form=True)
-    return orc.orientation_psfs(rep['psfs']['rescan_sted'], K, 3.0227)
+def make_psfs(K):
+    """K orientations of the figure-2 '2p0x_lr' rescan PSF (107^2), through the product API."""
+    from rescan_line_sted_b200 import line_sted_tools as st, orientations
+    rep = st.psf_report('line', 0.21672180512595912, 11.766131198861775, 25, 5, verbose=False)
+    return orientations.line_orientation_psfs(rep['psfs']['rescan_sted'], K, 3.0227)
 
 
 def test_object(N=128):
@@ -68,6 +69,28 @@ def time_cpu(psfs, obj, iterations):
     for _ in range(iterations):
         d.iterate()
     return (time.perf_counter() - t) / iterations, kind
+
+
+def bench_record(iterations=128):
+    """Short form for bench.py's `extra.config2`: K = 4, 24 concurrent deconvolvers."""
+    from rescan_line_sted_b200 import line_sted_tools as st
+    obj = test_object()
+    psfs = make_psfs(4)
+    prev = os.environ.get('LSTED_PRECISION')
+    rec = {'object': 128, 'psf': 107, 'K': 4, 'deconvolvers': 24,
+           'api': 'line_sted_tools.Deconvolver.iterate() round-robin over 24 deconvolvers '
+                  '(line_sted_figure_2.py:53-56), wall clock incl. the final read of every estimate'}
+    try:
+        for precision in ('fp32', 'fp64'):
+            s = time_gpu(st, psfs, obj, 24, max(iterations // 8, 8), precision)
+            rec['%s_rl_iterations_per_s' % precision] = 1.0 / s
+            rec['%s_us_per_iteration' % precision] = s * 1e6
+    finally:
+        if prev is None:
+            os.environ.pop('LSTED_PRECISION', None)
+        else:
+            os.environ['LSTED_PRECISION'] = prev
+    return rec
 
 
 def main():

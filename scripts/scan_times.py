@@ -53,6 +53,28 @@ def cpu_seconds_per_position(obj, typ, width, R, pad, sample):
     return (time.perf_counter() - t) / len(pick), len(pick)
 
 
+def bench_record():
+    """Short form for bench.py's `extra.scan_engine`: the figure-3 rescan-line and descan-point
+    cases at the script's largest size (2x2 field of view, R = 3)."""
+    from rescan_line_sted_b200 import scan_engine as se
+    rec = {}
+    for typ, n_or, pad in (('rescan_line', 6, int(0.45 * 256)), ('descan_point', 1, 25)):
+        obj = synthetic_object(256)
+        se.simulate_imaging(obj, typ, 25, 3, 1, 1, pad, verbose=False)      # warm-up
+        out = se.simulate_imaging(obj, typ, 25, 3, n_or, 1, pad, verbose=False)
+        P = len(out['scan_positions'])
+        runs = (n_or if typ.endswith('line') else 1) + 1
+        n0 = 256 + 2 * pad
+        rec[typ] = {'object': 256, 'padded': n0, 'R': 3, 'orientations': n_or, 'scan_positions': P,
+                    'device_ms': out['device_ms'],
+                    'positions_per_s': P * runs / (out['device_ms'] * 1e-3),
+                    'algorithmic_GBps': 2 * 8 * n0 * n0 * P * runs / (out['device_ms'] * 1e-3) / 1e9}
+    rec['note'] = ('simulate_imaging (line_sted_figure_3.py:76-273) on the device, all scan positions of '
+                   'an orientation in flight; device_ms = CUDA events inside liblsted over the scan of '
+                   'every orientation + the display-maxima pass')
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=None)
