@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_HERE, 'liblsted.so')
+# LSTED_LIBRARY selects another build of the same C ABI (the debug build with in-kernel checks)
+LIBRARY_PATH = os.environ.get('LSTED_LIBRARY') or os.path.join(_HERE, 'liblsted.so')
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)

@@ -52,7 +52,11 @@ LSTED_HD int even_rows(int rows) { return (rows + 1) & ~1; }
 // window is as long as the transform (N == L, crop offset s > 0): the last s outputs wrap
 // around -- they lie outside the alias-free interior and are discarded by the caller, but the
 // read must stay inside the sequence.
-LSTED_HD int crop_pos(int s, int i, int L) { const int p = s + i; return p >= L ? p - L : p; }
+LSTED_HD int crop_pos(int s, int i, int L) {
+    const int p = s + i;
+    LSTED_DCHECK(p >= 0 && p < 2 * L);
+    return p >= L ? p - L : p;
+}
 LSTED_HD size_t slab2_index(int y, int c, int C) { return (size_t)(y & ~1) * C + 2 * c + (y & 1); }
 LSTED_HD size_t xb2_index(int xb, int y, int c, int rows, int C) {
     return (size_t)xb * even_rows(rows) * C + slab2_index(y, c, C);

@@ -246,6 +246,9 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     cplx<T>* const buf0 = smem;
     cplx<T>* const buf1 = smem + (size_t)CC * LSM;
     const int K = a.K;
+    // debug build: the column block and sub-block of this CTA exist, the OTF slab is a whole
+    // number of 16-byte units inside [nxb][C][Ly] of orientation 0 .. K-1
+    LSTED_DCHECK(xb >= 0 && xb < g.nxb && sub >= 0 && sub < (SUB ? (int)P::NSUB : 1) && K >= 1);
 
 #define LSTED_COL_IDS                                          \
     const int t = tid / CC, cl = tid - t * CC, c = sub * CC + cl;  \

@@ -22,6 +22,36 @@
 #define LSTED_NOUNROLL
 #endif
 
+// Debug build (make debug -> liblsted_debug.so, -DLSTED_DEBUG): in-kernel checks of every
+// tensor-map box, bulk-copy range / alignment and crop index.  compute-sanitizer is not
+// available on the GPU pool, and an out-of-range TMA box once produced silent garbage
+// (DESIGN.md section 4); a failed check prints its location and traps the kernel, which the
+// next API call reports as a CUDA error.
+#ifdef LSTED_DEBUG
+#include <stdio.h>
+#ifdef __CUDA_ARCH__
+#define LSTED_DCHECK(cond)                                                                      \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            printf("LSTED_DCHECK failed: %s  at %s:%d (block %d, thread %d)\n", #cond, __FILE__, \
+                   __LINE__, (int)blockIdx.x, (int)threadIdx.x);                                \
+            __trap();                                                                           \
+        }                                                                                       \
+    } while (0)
+#else
+#include <stdlib.h>
+#define LSTED_DCHECK(cond)                                                                      \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            fprintf(stderr, "LSTED_DCHECK failed: %s  at %s:%d\n", #cond, __FILE__, __LINE__);  \
+            abort();                                                                            \
+        }                                                                                       \
+    } while (0)
+#endif
+#else
+#define LSTED_DCHECK(cond) do { } while (0)
+#endif
+
 namespace lsted {
 
 template <typename T> struct alignas(2 * sizeof(T)) cplx { T x, y; };
@@ -238,6 +268,8 @@ LSTED_HD void mbar_init(mbar_t* bar) {
 }
 // bytes: multiple of 16; dst / src 16-byte aligned
 LSTED_HD void bulk_load(void* dst_smem, const void* src, unsigned bytes, mbar_t* bar) {
+    LSTED_DCHECK(bytes % 16 == 0 && bytes > 0);
+    LSTED_DCHECK(((size_t)src & 15) == 0 && ((size_t)dst_smem & 15) == 0);
 #ifdef __CUDA_ARCH__
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -263,6 +295,8 @@ LSTED_HD void bulk_expect(mbar_t* bar, unsigned total_bytes) {
 #endif
 }
 LSTED_HD void bulk_copy(void* dst_smem, const void* src, unsigned bytes, mbar_t* bar) {
+    LSTED_DCHECK(bytes % 16 == 0 && bytes > 0);
+    LSTED_DCHECK(((size_t)src & 15) == 0 && ((size_t)dst_smem & 15) == 0);
 #ifdef __CUDA_ARCH__
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -285,6 +319,11 @@ enum { kTmaBoxBlocks = 137 };
 template <typename T>
 LSTED_HD void tma_load_chunks(void* dst_smem, const void* tmap, const cplx<T>* base, int img, int y, int xb0,
                               int nxb, int rows_e, int C, int chunk_cplx, mbar_t* bar) {
+    // the box must lie inside the tensor: blocks [xb0, xb0 + kTmaBoxBlocks) of nxb, an even row
+    // of the slab, and a 128-byte aligned shared-memory destination
+    LSTED_DCHECK(xb0 >= 0 && xb0 + kTmaBoxBlocks <= nxb);
+    LSTED_DCHECK(y >= 0 && (y & 1) == 0 && y < rows_e && img >= 0);
+    LSTED_DCHECK(((size_t)dst_smem & 127) == 0);
 #ifdef __CUDA_ARCH__
     (void)base; (void)nxb; (void)rows_e;
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
@@ -308,6 +347,9 @@ LSTED_HD void tma_load_chunks(void* dst_smem, const void* tmap, const cplx<T>* b
 template <typename T>
 LSTED_HD void tma_store_chunks(const void* src_smem, const void* tmap, cplx<T>* base, int img, int y, int xb0,
                                int nxb, int rows_e, int C, int chunk_cplx) {
+    LSTED_DCHECK(xb0 >= 0 && xb0 + kTmaBoxBlocks <= nxb);
+    LSTED_DCHECK(y >= 0 && (y & 1) == 0 && y < rows_e && img >= 0);
+    LSTED_DCHECK(((size_t)src_smem & 127) == 0);
 #ifdef __CUDA_ARCH__
     (void)base; (void)nxb; (void)rows_e; (void)chunk_cplx;
     const unsigned d = (unsigned)__cvta_generic_to_shared(src_smem);

@@ -152,6 +152,7 @@ LSTED_HD double spline_value(const double* co, int c0, int c1, double y, double 
     for (int p = 0; p < 4; ++p) {
         const int i = sy + p;
         const int yy = mode == SPLINE_CONSTANT ? spline_mirror(i, c0) : (i < 0 ? 0 : (i >= c0 ? c0 - 1 : i));
+        LSTED_DCHECK(yy >= 0 && yy < c0 && xx[0] >= 0 && xx[3] < c1 && xx[0] < c1 && xx[3] >= 0);
         const double* row = co + (size_t)yy * c1;
         for (int q = 0; q < 4; ++q) v += wy[p] * wx[q] * row[xx[q]];
     }
@@ -316,6 +317,7 @@ struct ScanBlur0StripFn {
                 for (int j = 0; j < kBlurStrip; ++j) acc[j] += v * w[q - j + kBlurStrip - 1];
             }
         }
+        LSTED_DCHECK(ya >= 0 && ya < g.n0 && x >= 0 && x < g.n1 && p < g.num_pos);
         double* o = out + (pl * g.n0 + ya) * (size_t)g.n1 + x;
 #pragma unroll
         for (int j = 0; j < kBlurStrip; ++j)
@@ -550,6 +552,7 @@ struct ScanFrameFn {
         const size_t f = t / 6;
         const int p = frame_pos[f];
         const int Y = y + g.pad, X = x + g.pad;
+        LSTED_DCHECK(p >= 0 && p < g.num_pos && Y < g.n0 && X < g.n1);
         const size_t pix = (size_t)Y * g.n1 + X, plane = (size_t)g.n0 * g.n1;
         double v;
         switch (which) {
