@@ -74,10 +74,8 @@ extern "C" int lsted_scan_run(lsted_scan* h, const double* obj_padded, const dou
             return set_error(LSTED_ERR_ARG, "frame positions must be ascending scan-position indices");
     LSTED_TRY
     h->bk->activate();
-    h->bk->timer_start();
     h->e->run(obj_padded, rot_xform, frame_positions, num_frames, maxima, reconstruction, cum_detector_sig);
-    const double ms = h->bk->timer_stop();
-    if (device_ms) *device_ms = ms;
+    if (device_ms) *device_ms = h->e->last_ms;
     return LSTED_OK;
     LSTED_CATCH
 }

@@ -113,6 +113,17 @@ struct ImgPrefilterFn {   // one line per element: e = plane * lines + line
     }
 };
 
+// Column prefilter (mirror start) of rows [y0, y1) only: the data are zero outside a band well
+// inside that range, and the recursion's memory decays as 0.268^k (40 rows: 1e-23)
+struct ImgPrefilterRowsFn {
+    double* buf;
+    int n0, n1, y0, y1;
+    LSTED_HD void operator()(size_t e) const {
+        double* p = buf + (e / n1) * (size_t)n0 * n1 + (size_t)y0 * n1 + (e % n1);
+        spline_prefilter_line(p, y1 - y0, (size_t)n1);
+    }
+};
+
 // np.pad(plane, npad, 'edge') (scipy's _prepad_for_spline_filter for mode='nearest')
 struct ImgEdgePadFn {
     const double* in; double* out;
@@ -184,13 +195,26 @@ struct PlaneReducePartialFn {
     const double* in; double* partial;   // partial[plane][kReduceSegments]
     size_t plane_elems;
     int is_max;                           // 1: maximum, 0: sum
+    // optional rectangle [y0, y1) x [x0, x1) of planes with `pitch` columns (pitch 0: the
+    // whole plane): everything outside is known to be zero
+    int y0, y1, x0, x1, pitch;
     LSTED_HD void operator()(size_t e) const {
         const size_t b = e / kReduceSegments, s = e % kReduceSegments;
         const double* p = in + b * plane_elems;
         double acc = is_max ? -INFINITY : 0.0;
-        for (size_t k = s; k < plane_elems; k += kReduceSegments) {
-            const double v = p[k];
-            if (is_max) acc = v > acc ? v : acc; else acc += v;
+        if (pitch == 0) {
+            for (size_t k = s; k < plane_elems; k += kReduceSegments) {
+                const double v = p[k];
+                if (is_max) acc = v > acc ? v : acc; else acc += v;
+            }
+        } else {
+            const int w = x1 - x0;
+            const size_t n = (size_t)(y1 - y0) * w;
+            for (size_t k = s; k < n; k += kReduceSegments) {
+                const double v = p[(size_t)(y0 + (int)(k / w)) * pitch + x0 + (int)(k % w)];
+                if (is_max) acc = v > acc ? v : acc; else acc += v;
+            }
+            if (is_max && acc < 0.0 && n < plane_elems) acc = 0.0;   // the zeros outside the rectangle
         }
         partial[e] = acc;
     }
@@ -282,83 +306,67 @@ struct ScanSupport {
 };
 enum { kBlurStrip = 8 };
 
-// Pass 0 on the support: one thread = kBlurStrip consecutive output rows of one column; every
-// source sample is loaded once for the whole strip and the taps it meets slide through
-// registers.  taps_ext = the taps with kBlurStrip zeros on either side.  Writes rows
-// [dst_y0, dst_y1) x columns [src_x0, src_x1) of `out` only (pass 1 reads nothing else).
-struct ScanBlur0StripFn {
+// One pass of the detector blur as strips: a thread owns kBlurStrip consecutive outputs along
+// the filter axis at one coordinate across it; the lanes of a warp run across (coalesced
+// loads).  Every source sample is loaded once for the whole strip and the taps it meets slide
+// through registers (taps_ext = the taps with kBlurStrip zeros before and 3 kBlurStrip after).
+//   PASS 0 filters along rows; its input is the descanned glow formed on the fly; its output is
+//          written TRANSPOSED, mid[pl][column][row], so that
+//   PASS 1 filters along columns with the lanes across rows again, and writes out[pl][row][col].
+// Support mode (ScanSupport): samples outside the source support are zero and only the
+// destination support is computed; pass 1 writes rows [wr_y0, wr_y1) (zeros where the blur
+// cannot reach) and never touches the rest of `out`, which was zeroed once.  Frame mode
+// (fold != 0): everything is computed, samples beyond the frame come from the reflected index.
+template <int PASS> struct ScanBlurStripFn {
     ScanGeom g;
     ScanSupport sp;
-    int p0, radius, nstrips;
+    int p0, radius, nstrips, fold;
+    int wr_y0, wr_y1;            // PASS 1: rows written
     const double* taps_ext;
-    double* out;        // [count][n0][n1]
+    const double* mid_in;        // PASS 1 input
+    double* out;                 // PASS 0: mid[count][n1][n0]; PASS 1: [count][n0][n1]
     LSTED_HD void operator()(size_t e) const {
-        const int wx = sp.src_x1 - sp.src_x0;
-        const int x = sp.src_x0 + (int)(e % wx);
-        const size_t t = e / wx;
-        const int ya = sp.dst_y0 + (int)(t % nstrips) * kBlurStrip;
+        const int across0 = PASS == 0 ? sp.src_x0 : wr_y0;
+        const int across_n = PASS == 0 ? sp.src_x1 - sp.src_x0 : wr_y1 - wr_y0;
+        const int along0 = PASS == 0 ? sp.dst_y0 : sp.dst_x0, along1 = PASS == 0 ? sp.dst_y1 : sp.dst_x1;
+        const int src0 = PASS == 0 ? sp.src_y0 : sp.src_x0, src1 = PASS == 0 ? sp.src_y1 : sp.src_x1;
+        const int n_along = PASS == 0 ? g.n0 : g.n1;
+        const int a = across0 + (int)(e % across_n);
+        const size_t t = e / across_n;
+        const int first_out = along0 + (int)(t % nstrips) * kBlurStrip;
         const size_t pl = t / nstrips;
         const int p = p0 + (int)pl;
         double acc[kBlurStrip];
 #pragma unroll
         for (int j = 0; j < kBlurStrip; ++j) acc[j] = 0.0;
-        // sample u sits at row ya - radius + u and meets output j with tap u - j
-        const int first = ya - radius;
-        const int nsamp = kBlurStrip + 2 * radius;
-        for (int u0 = 0; u0 < nsamp; u0 += kBlurStrip) {
-            double w[2 * kBlurStrip - 1];   // taps u0 - (kBlurStrip-1) .. u0 + kBlurStrip - 1
+        const bool live = PASS == 0 || (a >= sp.dst_y0 && a < sp.dst_y1);
+        if (live) {
+            // sample u sits at first_out - radius + u and meets output j with tap u - j
+            const int first = first_out - radius;
+            const int nsamp = kBlurStrip + 2 * radius;
+            const double* mid = PASS == 1 ? mid_in + pl * (size_t)g.n0 * g.n1 + a : 0;
+            for (int u0 = 0; u0 < nsamp; u0 += kBlurStrip) {
+                double w[2 * kBlurStrip - 1];   // taps u0 - (kBlurStrip-1) .. u0 + kBlurStrip - 1
 #pragma unroll
-            for (int i = 0; i < 2 * kBlurStrip - 1; ++i) w[i] = taps_ext[u0 + 1 + i];
+                for (int i = 0; i < 2 * kBlurStrip - 1; ++i) w[i] = taps_ext[u0 + 1 + i];
 #pragma unroll
-            for (int q = 0; q < kBlurStrip; ++q) {
-                const int row = first + u0 + q;
-                const double v = row >= sp.src_y0 && row < sp.src_y1 ? scan_src(g, p, row, x) : 0.0;
+                for (int q = 0; q < kBlurStrip; ++q) {
+                    int idx = first + u0 + q;
+                    if (fold) idx = reflect_near(idx, n_along);
+                    double v = 0.0;
+                    if (idx >= src0 && idx < src1)
+                        v = PASS == 0 ? scan_src(g, p, idx, a) : mid[(size_t)idx * g.n0];
 #pragma unroll
-                for (int j = 0; j < kBlurStrip; ++j) acc[j] += v * w[q - j + kBlurStrip - 1];
+                    for (int j = 0; j < kBlurStrip; ++j) acc[j] += v * w[q - j + kBlurStrip - 1];
+                }
             }
         }
-        LSTED_DCHECK(ya >= 0 && ya < g.n0 && x >= 0 && x < g.n1 && p < g.num_pos);
-        double* o = out + (pl * g.n0 + ya) * (size_t)g.n1 + x;
+        LSTED_DCHECK(first_out >= 0 && first_out < n_along && a >= 0 && p < g.num_pos);
+        double* o = PASS == 0 ? out + (pl * g.n1 + a) * (size_t)g.n0 + first_out
+                              : out + (pl * g.n0 + a) * (size_t)g.n1 + first_out;
 #pragma unroll
         for (int j = 0; j < kBlurStrip; ++j)
-            if (ya + j < sp.dst_y1) o[(size_t)j * g.n1] = acc[j];
-    }
-};
-
-// Pass 1 on the support: zeros outside [dst_y0, dst_y1) x [dst_x0, dst_x1); inside, the taps
-// that reach source columns [src_x0, src_x1), centre first and pairs from the outside in.
-struct ScanBlur1SupportFn {
-    const double* in; double* out;
-    ScanSupport sp;
-    int n0, n1, radius;
-    int full_width;     // the source spans every column (line scans): reflect at the row ends
-    const double* taps;
-    LSTED_HD void operator()(size_t e) const {
-        const int x = (int)(e % n1);
-        const size_t t = e / n1;
-        const int y = (int)(t % n0);
-        double acc = 0.0;
-        if (y >= sp.dst_y0 && y < sp.dst_y1 && x >= sp.dst_x0 && x < sp.dst_x1) {
-            const double* row = in + t * (size_t)n1;
-            if (full_width) {
-                acc = row[x] * taps[radius];
-                if (x >= radius && x + radius < n1) {
-                    for (int d = radius; d >= 1; --d) acc += (row[x - d] + row[x + d]) * taps[radius - d];
-                } else {
-                    for (int d = radius; d >= 1; --d)
-                        acc += (row[reflect_near(x - d, n1)] + row[reflect_near(x + d, n1)]) * taps[radius - d];
-                }
-            } else {
-                if (x >= sp.src_x0 && x < sp.src_x1) acc = row[x] * taps[radius];
-                for (int d = radius; d >= 1; --d) {
-                    const int a = x - d, b = x + d;
-                    const double va = a >= sp.src_x0 && a < sp.src_x1 ? row[a] : 0.0;
-                    const double vb = b >= sp.src_x0 && b < sp.src_x1 ? row[b] : 0.0;
-                    acc += (va + vb) * taps[radius - d];
-                }
-            }
-        }
-        out[e] = acc;
+            if (first_out + j < along1) o[j] = acc[j];
     }
 };
 
@@ -366,12 +374,20 @@ struct ScanGlowMaxPartialFn {   // partial maxima of glow (:231)
     ScanGeom g;
     int p0;
     double* partial;             // [count][kReduceSegments]
+    // support of the centred excitation (rows / columns; the whole frame when unknown): the
+    // glow of position p is zero outside that rectangle shifted by the scan position
+    int ey0, ey1, ex0, ex1;
     LSTED_HD void operator()(size_t e) const {
         const int p = p0 + (int)(e / kReduceSegments);
-        const size_t plane = (size_t)g.n0 * g.n1;
-        double acc = -INFINITY;
-        for (size_t k = e % kReduceSegments; k < plane; k += kReduceSegments) {
-            const double v = scan_glow(g, p, (int)(k / g.n1), (int)(k % g.n1));
+        int y0 = ey0 + g.pos[2 * p], y1 = ey1 + g.pos[2 * p];
+        int x0 = ex0 + g.pos[2 * p + 1], x1 = ex1 + g.pos[2 * p + 1];
+        y0 = y0 < 0 ? 0 : y0; y1 = y1 > g.n0 ? g.n0 : y1;
+        x0 = x0 < 0 ? 0 : x0; x1 = x1 > g.n1 ? g.n1 : x1;
+        const int w = x1 - x0;
+        const size_t n = y1 > y0 && w > 0 ? (size_t)(y1 - y0) * w : 0;
+        double acc = n < (size_t)g.n0 * g.n1 ? 0.0 : -INFINITY;   // zeros outside the rectangle
+        for (size_t k = e % kReduceSegments; k < n; k += kReduceSegments) {
+            const double v = scan_glow(g, p, y0 + (int)(k / w), x0 + (int)(k % w));
             acc = v > acc ? v : acc;
         }
         partial[e] = acc;
@@ -381,12 +397,13 @@ struct ScanGlowMaxPartialFn {   // partial maxima of glow (:231)
 struct ScanColSumFn {   // descan line: inst.sum(axis=1), rows added in order (:179-181)
     const double* inst; double* colsum;   // colsum[(p0 + pl)][n1]
     int n0, n1, p0;
+    int y0, y1;                           // rows that can be non-zero
     LSTED_HD void operator()(size_t e) const {
         const size_t pl = e / n1;
         const int x = (int)(e % n1);
         const double* p = inst + pl * (size_t)n0 * n1 + x;
         double acc = 0.0;
-        for (int y = 0; y < n0; ++y) acc += p[(size_t)y * n1];
+        for (int y = y0; y < y1; ++y) acc += p[(size_t)y * n1];
         colsum[(size_t)(p0 + pl) * n1 + x] = acc;
     }
 };
@@ -421,6 +438,7 @@ struct ScanRescanFn {
     ScanGeom g;
     const double* coef; double* out;
     int p0;
+    int cy0, cy1;   // rows of `coef` that were prefiltered (coefficients are zero elsewhere)
     LSTED_HD void operator()(size_t e) const {
         const int x = (int)(e % g.n1);
         const size_t t = e / g.n1;
@@ -437,7 +455,10 @@ struct ScanRescanFn {
                 cubic_weights(cc, w);
                 const int s = (int)floor(cc) - 1;
                 const double* col = coef + pl * (size_t)g.n0 * g.n1 + xx;
-                for (int k = 0; k < 4; ++k) v += w[k] * col[(size_t)spline_mirror(s + k, g.n0) * g.n1];
+                for (int k = 0; k < 4; ++k) {
+                    const int r = spline_mirror(s + k, g.n0);
+                    if (r >= cy0 && r < cy1) v += w[k] * col[(size_t)r * g.n1];
+                }
             }
         }
         out[e] = v < 0.0 ? 0.0 : v;
@@ -589,14 +610,18 @@ public:
     std::vector<int> h_pos;
     int* d_pos = nullptr;
     double *d_blur = nullptr, *d_blur_ext = nullptr, *d_exc_taps = nullptr;
-    ScanSupport sup;
+    ScanSupport sup;             // blur supports (the whole frame when use_support is false)
     bool use_support = false;
+    int ey0 = 0, ey1 = 0, ex0 = 0, ex1 = 0;   // support of the centred excitation
+    int cy0 = 0, cy1 = 0;                     // rescan: rows of the blurred image that are prefiltered
     double *d_obj = nullptr, *d_rot = nullptr, *d_cexc = nullptr;
     double *d_colsum = nullptr, *d_total = nullptr, *d_regsum = nullptr, *d_cum = nullptr;
     double *d_partial = nullptr, *d_max = nullptr;   // [chunk][segments], [P][3]: glow, inst, cum
     double *d_a = nullptr, *d_b = nullptr;           // chunk planes
     double *d_inst_store = nullptr, *d_cum_store = nullptr;
     int *d_frame_pos = nullptr, *d_slot = nullptr;
+    double *d_rot_xf = nullptr, *d_rot_pad = nullptr;   // object rotation: transform + clip bound, padded plane
+    double last_ms = 0.0;                                // device time of the last run() (CUDA events)
     std::vector<int> h_frame_pos;
     int chunk = 1, frames_cap = 0;
     size_t plane;
@@ -656,13 +681,16 @@ public:
             d_regsum = bk.template alloc<double>((size_t)p.num_pos * g.spots_y * g.spots_x);
         d_a = bk.template alloc<double>((size_t)chunk * plane);
         d_b = bk.template alloc<double>((size_t)chunk * plane * (planes_per_pos - 1));
+        // support mode writes the blur's destination rectangle only: the rest stays zero
+        bk.zero(d_b, sizeof(double) * (size_t)chunk * plane);
         d_slot = bk.template alloc<int>(chunk);
         g.pos = d_pos; g.rot_obj = d_rot; g.cexc = d_cexc;
         make_excitation();
     }
     ~ScanEngine() {
         void* all[] = {d_pos, d_blur, d_blur_ext, d_exc_taps, d_obj, d_rot, d_cexc, d_colsum, d_total, d_regsum,
-                       d_cum, d_partial, d_max, d_a, d_b, d_inst_store, d_cum_store, d_frame_pos, d_slot};
+                       d_cum, d_partial, d_max, d_a, d_b, d_inst_store, d_cum_store, d_frame_pos, d_slot,
+                       d_rot_xf, d_rot_pad};
         for (void* p : all) if (p) bk.free(p);
     }
 
@@ -671,20 +699,27 @@ public:
     // reflect boundary: both keep the general kernels.
     void find_support() {
         use_support = false;
-        if (g.type == SCAN_MULTIPOINT) return;
         const int re = prm.exc_radius, rb = prm.blur_radius;
-        sup.src_y0 = g.n0 / 2 - re; sup.src_y1 = g.n0 / 2 + re + 1;
-        if (g.type == SCAN_DESCAN_POINT) { sup.src_x0 = g.n1 / 2 - re; sup.src_x1 = g.n1 / 2 + re + 1; }
-        else { sup.src_x0 = 0; sup.src_x1 = g.n1; }
-        sup.dst_y0 = sup.src_y0 - rb; sup.dst_y1 = sup.src_y1 + rb;
-        if (sup.dst_y0 < 0 || sup.dst_y1 > g.n0) return;
+        ScanSupport full = {0, g.n0, 0, g.n1, 0, g.n0, 0, g.n1};
+        sup = full;
+        ey0 = 0; ey1 = g.n0; ex0 = 0; ex1 = g.n1;
+        cy0 = 0; cy1 = g.n0;
+        if (g.type == SCAN_MULTIPOINT) return;
+        // excitation: a delta line / point blurred with radius re (reflections stay inside)
+        ey0 = std::max(0, g.n0 / 2 - re); ey1 = std::min(g.n0, g.n0 / 2 + re + 1);
+        if (g.type == SCAN_DESCAN_POINT) { ex0 = std::max(0, g.n1 / 2 - re); ex1 = std::min(g.n1, g.n1 / 2 + re + 1); }
+        ScanSupport t = full;
+        t.src_y0 = g.n0 / 2 - re; t.src_y1 = g.n0 / 2 + re + 1;
+        t.dst_y0 = t.src_y0 - rb; t.dst_y1 = t.src_y1 + rb;
+        if (t.dst_y0 < 0 || t.dst_y1 > g.n0) return;
         if (g.type == SCAN_DESCAN_POINT) {
-            sup.dst_x0 = sup.src_x0 - rb; sup.dst_x1 = sup.src_x1 + rb;
-            if (sup.dst_x0 < 0 || sup.dst_x1 > g.n1) return;
-        } else {   // a line runs edge to edge: pass 1 reflects at the left / right edge
-            sup.dst_x0 = 0; sup.dst_x1 = g.n1;
-        }
+            t.src_x0 = g.n1 / 2 - re; t.src_x1 = g.n1 / 2 + re + 1;
+            t.dst_x0 = t.src_x0 - rb; t.dst_x1 = t.src_x1 + rb;
+            if (t.dst_x0 < 0 || t.dst_x1 > g.n1) return;
+        }   // a line runs edge to edge: pass 1 covers the full width and reflects at the row ends
+        sup = t;
         use_support = true;
+        if (g.type == SCAN_RESCAN_LINE) { cy0 = std::max(0, t.dst_y0 - 40); cy1 = std::min(g.n0, t.dst_y1 + 40); }
     }
 
     // centred excitation (:104-140): delta line / point / spot lattice, blurred by the STED width
@@ -712,10 +747,13 @@ public:
     void get_excitation(double* out) { bk.download(out, d_cexc, sizeof(double) * plane); }
 
     void plane_reduce(const double* in, size_t planes, size_t elems, int is_max, double* out,
-                      size_t out_stride, double scale = 1.0) {
+                      size_t out_stride, double scale = 1.0, bool on_support = false) {
         for (size_t b0 = 0; b0 < planes; b0 += (size_t)std::max(chunk, 2)) {
             const size_t nb = std::min<size_t>(std::max(chunk, 2), planes - b0);
             PlaneReducePartialFn a{in + b0 * elems, d_partial, elems, is_max};
+            if (on_support && use_support) {
+                a.y0 = sup.dst_y0; a.y1 = sup.dst_y1; a.x0 = sup.dst_x0; a.x1 = sup.dst_x1; a.pitch = g.n1;
+            }
             bk.for_each(nb * kReduceSegments, a);
             PlaneReduceFinalFn b{d_partial, out + b0 * out_stride, out_stride, is_max, scale};
             bk.for_each(nb, b);
@@ -745,20 +783,12 @@ public:
     void run(const double* obj_padded, const double* rot_xform, const int* frame_positions,
              int num_frames, double* maxima, double* reconstruction, double* cum_detector_sig) {
         const int P = g.num_pos;
-        bk.upload(d_obj, obj_padded, sizeof(double) * plane);
-        if (rot_xform) {
+        // memory first (kept for the next orientation), then the timed device work
+        if (rot_xform && !d_rot_pad) {
             const int c0 = g.n0 + 2 * kSplinePrepad, c1 = g.n1 + 2 * kSplinePrepad;
-            double* d_xf = bk.template alloc<double>(8);
-            double* d_padded = bk.template alloc<double>((size_t)c0 * c1);
-            bk.upload(d_xf, rot_xform, sizeof(double) * 6);
-            plane_reduce(d_obj, 1, plane, 1, d_xf + 6, 1, 1.1);
-            rotate_planes(d_obj, 1, g.n0, g.n1, d_xf, d_xf + 6, d_padded, d_rot, g.n0, g.n1);
-            bk.sync();
-            bk.free(d_xf); bk.free(d_padded);
-        } else {
-            bk.copy(d_rot, d_obj, sizeof(double) * plane);
+            d_rot_xf = bk.template alloc<double>(8);
+            d_rot_pad = bk.template alloc<double>((size_t)c0 * c1);
         }
-        // frame bookkeeping
         h_frame_pos.assign(frame_positions, frame_positions + num_frames);
         std::vector<int> slot_of(P, -1);
         for (int f = 0; f < num_frames; ++f) slot_of[h_frame_pos[f]] = f;
@@ -771,34 +801,46 @@ public:
             d_frame_pos = bk.template alloc<int>(num_frames);
             frames_cap = num_frames;
         }
+        bk.upload(d_obj, obj_padded, sizeof(double) * plane);
+        if (rot_xform) bk.upload(d_rot_xf, rot_xform, sizeof(double) * 6);
+        bk.timer_start();
+        if (rot_xform) {
+            plane_reduce(d_obj, 1, plane, 1, d_rot_xf + 6, 1, 1.1);
+            rotate_planes(d_obj, 1, g.n0, g.n1, d_rot_xf, d_rot_xf + 6, d_rot_pad, d_rot, g.n0, g.n1);
+        } else {
+            bk.copy(d_rot, d_obj, sizeof(double) * plane);
+        }
         if (num_frames) bk.upload(d_frame_pos, h_frame_pos.data(), sizeof(int) * num_frames);
         bk.zero(d_cum, sizeof(double) * plane);
 
         for (int p0 = 0; p0 < P; p0 += chunk) {
             const int cnt = std::min(chunk, P - p0);
             const size_t elems = (size_t)cnt * plane;
-            ScanGlowMaxPartialFn gm{g, p0, d_partial};
+            ScanGlowMaxPartialFn gm{g, p0, d_partial, ey0, ey1, ex0, ex1};
             bk.for_each((size_t)cnt * kReduceSegments, gm);
             PlaneReduceFinalFn gf{d_partial, d_max + 3 * (size_t)p0 + 0, 3, 1, 1.0};
             bk.for_each(cnt, gf);
-            if (use_support) {
-                const int nstrips = (sup.dst_y1 - sup.dst_y0 + kBlurStrip - 1) / kBlurStrip;
-                ScanBlur0StripFn b0{g, sup, p0, prm.blur_radius, nstrips, d_blur_ext, d_a};
-                bk.for_each((size_t)cnt * nstrips * (sup.src_x1 - sup.src_x0), b0);
-                ScanBlur1SupportFn b1{d_a, d_b, sup, g.n0, g.n1, prm.blur_radius,
-                                      g.type != SCAN_DESCAN_POINT, d_blur};
-                bk.for_each(elems, b1);
-            } else {
-                ScanBlur0Fn b0{g, p0, prm.blur_radius, d_blur, d_a};
-                bk.for_each(elems, b0);
-                ImgFirFn b1{d_a, d_b, g.n0, g.n1, 1, prm.blur_radius, d_blur};
-                bk.for_each(elems, b1);
+            {   // detector blur: rows (output transposed into d_a), then columns into d_b
+                const bool rescan = g.type == SCAN_RESCAN_LINE;
+                const int fold = use_support ? 0 : 1;
+                ScanBlurStripFn<0> b0;
+                b0.g = g; b0.sp = sup; b0.p0 = p0; b0.radius = prm.blur_radius; b0.fold = fold;
+                b0.nstrips = (sup.dst_y1 - sup.dst_y0 + kBlurStrip - 1) / kBlurStrip;
+                b0.wr_y0 = b0.wr_y1 = 0; b0.taps_ext = d_blur_ext; b0.mid_in = nullptr; b0.out = d_a;
+                bk.for_each((size_t)cnt * b0.nstrips * (sup.src_x1 - sup.src_x0), b0);
+                ScanBlurStripFn<1> b1;
+                b1.g = g; b1.sp = sup; b1.p0 = p0; b1.radius = prm.blur_radius;
+                b1.fold = (use_support && g.type == SCAN_DESCAN_POINT) ? 0 : 1;   // lines: reflect at the row ends
+                b1.nstrips = (sup.dst_x1 - sup.dst_x0 + kBlurStrip - 1) / kBlurStrip;
+                b1.wr_y0 = rescan ? cy0 : sup.dst_y0; b1.wr_y1 = rescan ? cy1 : sup.dst_y1;
+                b1.taps_ext = d_blur_ext; b1.mid_in = d_a; b1.out = d_b;
+                bk.for_each((size_t)cnt * b1.nstrips * (b1.wr_y1 - b1.wr_y0), b1);
             }
             double* inst = d_b;
             if (g.type == SCAN_RESCAN_LINE) {
-                ImgPrefilterFn pf{d_b, g.n0, g.n1, 0, 0};
+                ImgPrefilterRowsFn pf{d_b, g.n0, g.n1, cy0, cy1};
                 bk.for_each((size_t)cnt * g.n1, pf);
-                ScanRescanFn rs{g, d_b, d_a, p0};
+                ScanRescanFn rs{g, d_b, d_a, p0, cy0, cy1};
                 bk.for_each(elems, rs);
                 inst = d_a;
                 double* cumf = d_b + (size_t)chunk * plane;
@@ -811,15 +853,15 @@ public:
                     bk.for_each(elems, ga);
                 }
             } else if (g.type == SCAN_DESCAN_LINE) {
-                ScanColSumFn cs{inst, d_colsum, g.n0, g.n1, p0};
+                ScanColSumFn cs{inst, d_colsum, g.n0, g.n1, p0, sup.dst_y0, sup.dst_y1};
                 bk.for_each((size_t)cnt * g.n1, cs);
             } else if (g.type == SCAN_DESCAN_POINT) {
-                plane_reduce(inst, cnt, plane, 0, d_total + p0, 1);
+                plane_reduce(inst, cnt, plane, 0, d_total + p0, 1, 1.0, true);
             } else {
                 ScanRegionSumFn rg{g, inst, d_regsum, p0};
                 bk.for_each((size_t)cnt * g.spots_y * g.spots_x, rg);
             }
-            plane_reduce(inst, cnt, plane, 1, d_max + 3 * (size_t)p0 + 1, 3);
+            plane_reduce(inst, cnt, plane, 1, d_max + 3 * (size_t)p0 + 1, 3, 1.0, g.type != SCAN_RESCAN_LINE);
             if (num_frames) {
                 bk.upload(d_slot, slot_of.data() + p0, sizeof(int) * cnt);
                 GatherPlanesFn ga{inst, d_inst_store, d_slot, plane};
@@ -828,10 +870,11 @@ public:
             bk.sync();   // d_slot / chunk planes are reused by the next chunk
         }
         // results
-        std::vector<double> mx(3 * (size_t)P);
-        bk.download(mx.data(), d_max, sizeof(double) * 3 * P);
         ScanReconFn rc{g, sums(), d_a};
         bk.for_each(plane, rc);
+        last_ms = bk.timer_stop();
+        std::vector<double> mx(3 * (size_t)P);
+        bk.download(mx.data(), d_max, sizeof(double) * 3 * P);
         if (reconstruction) bk.download(reconstruction, d_a, sizeof(double) * plane);
         if (cum_detector_sig) {
             if (g.type == SCAN_RESCAN_LINE) bk.download(cum_detector_sig, d_cum, sizeof(double) * plane);
