@@ -125,10 +125,27 @@ extern "C" int lsted_img_spline(int device, int batch, int n0, int n1, const dou
         lsted::ImgEdgePadFn pad{d_in, d_co, n0, n1, npad};
         bk.for_each(co_elems, pad);
     }
-    lsted::ImgPrefilterFn pf{d_co, c0, c1, 0, npad ? 1 : 0};
-    bk.for_each((size_t)batch * c1, pf);
-    pf.axis = 1;
-    bk.for_each((size_t)batch * c0, pf);
+    {   // prefilter along both axes: blocked passes (second buffer) for long lines
+        double* d_tmp = bk.alloc<double>(co_elems);
+        for (int axis = 0; axis < 2; ++axis) {
+            const int n = axis == 0 ? c0 : c1;
+            const size_t nlines = axis == 0 ? c1 : c0;
+            if (n < lsted::kPfMinLine) {
+                lsted::ImgPrefilterFn pf{d_co, c0, c1, axis, npad ? 1 : 0};
+                bk.for_each((size_t)batch * nlines, pf);
+                continue;
+            }
+            lsted::PrefilterLines L;
+            L.n = n; L.stride = axis == 0 ? (size_t)c1 : 1; L.nlines = nlines;
+            L.line_step = axis == 0 ? 1 : (size_t)c1; L.plane_step = (size_t)c0 * c1; L.offset = 0;
+            L.nblocks = (n + lsted::kPfBlock - 1) / lsted::kPfBlock;
+            lsted::SplineCausalBlockFn ca{d_co, d_tmp, L, (size_t)batch * nlines, npad ? 1 : 0};
+            bk.for_each((size_t)batch * nlines * L.nblocks, ca);
+            lsted::SplineAnticausalBlockFn an{d_tmp, d_co, L, (size_t)batch * nlines, npad ? 1 : 0};
+            bk.for_each((size_t)batch * nlines * L.nblocks, an);
+        }
+        bk.free(d_tmp);
+    }
     lsted::ImgSplineFn sp{d_co, d_xf, d_clip, d_out, c0, c1, m0, m1, npad, mode};
     bk.for_each(out_elems, sp);
     bk.download(out, d_out, sizeof(double) * out_elems);

@@ -113,6 +113,90 @@ struct ImgPrefilterFn {   // one line per element: e = plane * lines + line
     }
 };
 
+// Blocked form of the same prefilter for long lines.  The recursions c+[i] = x[i] + z c+[i-1]
+// and c[i] = z (c[i+1] - c+[i]) forget their start as z^k (z = sqrt(3) - 2; 0.268^48 = 4e-28),
+// so a thread can produce kPfBlock outputs after a warm-up of kPfWarm samples from a zero state
+// instead of walking the whole line: n / kPfBlock threads per line, two passes (causal into a
+// second buffer, anti-causal back).  Line starts / ends use the boundary formulas of
+// spline_prefilter_line_mode with their sums cut at kPfInit terms (z^64 = 3e-37).
+enum { kPfBlock = 32, kPfWarm = 48, kPfInit = 64, kPfMinLine = 160 };
+struct PrefilterLines {
+    int n;                 // samples per line
+    size_t stride;         // between consecutive samples of a line
+    size_t nlines;         // lines per plane
+    size_t line_step;      // between the first samples of consecutive lines
+    size_t plane_step;     // between planes
+    size_t offset;         // first sample of line 0 of plane 0
+    int nblocks;           // ceil(n / kPfBlock)
+    LSTED_HD size_t base(size_t line) const {
+        return offset + (line / nlines) * plane_step + (line % nlines) * line_step;
+    }
+};
+struct SplineCausalBlockFn {     // e = block * total_lines + line  (lanes across lines)
+    const double* in; double* tmp;
+    PrefilterLines L;
+    size_t total_lines;
+    int boundary;                // 0 mirror, 1 reflect
+    LSTED_HD void operator()(size_t e) const {
+        const double z = sqrt(3.0) - 2.0;
+        const double gain = (1.0 - z) * (1.0 - 1.0 / z);
+        const size_t b0 = L.base(e % total_lines);
+        const double* x = in + b0;
+        double* c = tmp + b0;
+        const int s = (int)(e / total_lines) * kPfBlock;
+        const int end = s + kPfBlock < L.n ? s + kPfBlock : L.n;
+        double state;
+        int i;
+        if (s <= kPfWarm) {      // from the start of the line: boundary sum (cut at kPfInit terms)
+            double sum = 0.0, zi = 1.0;
+            for (int k = 0; k < kPfInit && k < L.n; ++k) { sum += zi * (gain * x[(size_t)k * L.stride]); zi *= z; }
+            state = boundary == 0 ? sum : gain * x[0] + z * sum;
+            if (s == 0) c[0] = state;
+            i = 1;
+        } else {                 // zero history kPfWarm samples before the block
+            i = s - kPfWarm;
+            state = gain * x[(size_t)i * L.stride];
+            ++i;
+        }
+        for (; i < end; ++i) {
+            state = gain * x[(size_t)i * L.stride] + z * state;
+            if (i >= s) c[(size_t)i * L.stride] = state;
+        }
+    }
+};
+struct SplineAnticausalBlockFn {
+    const double* tmp; double* out;
+    PrefilterLines L;
+    size_t total_lines;
+    int boundary;
+    LSTED_HD void operator()(size_t e) const {
+        const double z = sqrt(3.0) - 2.0;
+        const size_t b0 = L.base(e % total_lines);
+        const double* cp = tmp + b0;
+        double* c = out + b0;
+        const int s = (int)(e / total_lines) * kPfBlock;
+        const int last = (s + kPfBlock < L.n ? s + kPfBlock : L.n) - 1;
+        const int n = L.n;
+        double state;
+        int i;
+        if (last + kPfWarm >= n - 1) {   // from the end of the line
+            state = boundary == 0
+                ? (z * cp[(size_t)(n - 2) * L.stride] + cp[(size_t)(n - 1) * L.stride]) * z / (z * z - 1.0)
+                : cp[(size_t)(n - 1) * L.stride] * (z / (z - 1.0));
+            if (last == n - 1) c[(size_t)(n - 1) * L.stride] = state;
+            i = n - 2;
+        } else {
+            i = last + kPfWarm;
+            state = -z * cp[(size_t)i * L.stride];
+            --i;
+        }
+        for (; i >= s; --i) {
+            state = z * (state - cp[(size_t)i * L.stride]);
+            if (i <= last) c[(size_t)i * L.stride] = state;
+        }
+    }
+};
+
 // Column prefilter (mirror start) of rows [y0, y1) only: the data are zero outside a band well
 // inside that range, and the recursion's memory decays as 0.268^k (40 rows: 1e-23)
 struct ImgPrefilterRowsFn {
@@ -760,19 +844,38 @@ public:
         }
     }
 
+    // cubic-spline prefilter of `planes` planes [c0][c1] along both axes, in place; `tmp` has the
+    // same size (used by the blocked passes for lines of kPfMinLine samples and more)
+    void prefilter_planes(double* buf, double* tmp, size_t planes, int c0, int c1, int boundary) {
+        for (int axis = 0; axis < 2; ++axis) {
+            const int n = axis == 0 ? c0 : c1;
+            const size_t nlines = axis == 0 ? c1 : c0;
+            if (n < kPfMinLine || !tmp) {
+                ImgPrefilterFn pf{buf, c0, c1, axis, boundary};
+                bk.for_each(planes * nlines, pf);
+                continue;
+            }
+            PrefilterLines L;
+            L.n = n; L.stride = axis == 0 ? (size_t)c1 : 1; L.nlines = nlines;
+            L.line_step = axis == 0 ? 1 : (size_t)c1; L.plane_step = (size_t)c0 * c1; L.offset = 0;
+            L.nblocks = (n + kPfBlock - 1) / kPfBlock;
+            SplineCausalBlockFn ca{buf, tmp, L, planes * nlines, boundary};
+            bk.for_each(planes * nlines * L.nblocks, ca);
+            SplineAnticausalBlockFn an{tmp, buf, L, planes * nlines, boundary};
+            bk.for_each(planes * nlines * L.nblocks, an);
+        }
+    }
+
     // rotate(obj, rot) (:382-391): scipy.ndimage.rotate, order 3, mode='nearest', clipped to
     // [0, 1.1 max]; xform = the matrix/offset scipy builds for the angle; null: rot == 0.
     void rotate_planes(const double* in, size_t planes, int n0, int n1, const double* d_xform,
-                       const double* d_clip, double* padded, double* out, int m0, int m1) {
+                       const double* d_clip, double* padded, double* tmp, double* out, int m0, int m1) {
         const int c0 = n0 + 2 * kSplinePrepad, c1 = n1 + 2 * kSplinePrepad;
         if (in) {
             ImgEdgePadFn pad{in, padded, n0, n1, kSplinePrepad};
             bk.for_each(planes * c0 * c1, pad);
         }
-        ImgPrefilterFn pf{padded, c0, c1, 0, 1};
-        bk.for_each(planes * c1, pf);
-        pf.axis = 1;
-        bk.for_each(planes * c0, pf);
+        prefilter_planes(padded, tmp, planes, c0, c1, 1);
         ImgSplineFn sp{padded, d_xform, d_clip, out, c0, c1, m0, m1, kSplinePrepad, SPLINE_NEAREST};
         bk.for_each(planes * m0 * m1, sp);
     }
@@ -787,7 +890,7 @@ public:
         if (rot_xform && !d_rot_pad) {
             const int c0 = g.n0 + 2 * kSplinePrepad, c1 = g.n1 + 2 * kSplinePrepad;
             d_rot_xf = bk.template alloc<double>(8);
-            d_rot_pad = bk.template alloc<double>((size_t)c0 * c1);
+            d_rot_pad = bk.template alloc<double>(2 * (size_t)c0 * c1);   // padded plane + prefilter buffer
         }
         h_frame_pos.assign(frame_positions, frame_positions + num_frames);
         std::vector<int> slot_of(P, -1);
@@ -806,7 +909,9 @@ public:
         bk.timer_start();
         if (rot_xform) {
             plane_reduce(d_obj, 1, plane, 1, d_rot_xf + 6, 1, 1.1);
-            rotate_planes(d_obj, 1, g.n0, g.n1, d_rot_xf, d_rot_xf + 6, d_rot_pad, d_rot, g.n0, g.n1);
+            rotate_planes(d_obj, 1, g.n0, g.n1, d_rot_xf, d_rot_xf + 6, d_rot_pad,
+                          d_rot_pad + (size_t)(g.n0 + 2 * kSplinePrepad) * (g.n1 + 2 * kSplinePrepad),
+                          d_rot, g.n0, g.n1);
         } else {
             bk.copy(d_rot, d_obj, sizeof(double) * plane);
         }
@@ -838,8 +943,19 @@ public:
             }
             double* inst = d_b;
             if (g.type == SCAN_RESCAN_LINE) {
-                ImgPrefilterRowsFn pf{d_b, g.n0, g.n1, cy0, cy1};
-                bk.for_each((size_t)cnt * g.n1, pf);
+                if (cy1 - cy0 >= kPfMinLine) {   // blocked column prefilter, d_a (free here) as second buffer
+                    PrefilterLines L;
+                    L.n = cy1 - cy0; L.stride = (size_t)g.n1; L.nlines = (size_t)g.n1; L.line_step = 1;
+                    L.plane_step = plane; L.offset = (size_t)cy0 * g.n1;
+                    L.nblocks = (L.n + kPfBlock - 1) / kPfBlock;
+                    SplineCausalBlockFn ca{d_b, d_a, L, (size_t)cnt * g.n1, 0};
+                    bk.for_each((size_t)cnt * g.n1 * L.nblocks, ca);
+                    SplineAnticausalBlockFn an{d_a, d_b, L, (size_t)cnt * g.n1, 0};
+                    bk.for_each((size_t)cnt * g.n1 * L.nblocks, an);
+                } else {
+                    ImgPrefilterRowsFn pf{d_b, g.n0, g.n1, cy0, cy1};
+                    bk.for_each((size_t)cnt * g.n1, pf);
+                }
                 ScanRescanFn rs{g, d_b, d_a, p0, cy0, cy1};
                 bk.for_each(elems, rs);
                 inst = d_a;
@@ -944,7 +1060,7 @@ public:
         if (inv_xform) {
             const int c0 = g.n0 + 2 * kSplinePrepad, c1 = g.n1 + 2 * kSplinePrepad;
             const size_t planes = 2 * (size_t)count;
-            d_padded = bk.template alloc<double>(planes * c0 * c1);
+            d_padded = bk.template alloc<double>(2 * planes * c0 * c1);   // + the prefilter's second buffer
             d_rotated = bk.template alloc<double>(planes * crop);
             d_xf = bk.template alloc<double>(6 * planes);
             d_clip = bk.template alloc<double>(planes);
@@ -960,7 +1076,8 @@ public:
             ScanPadExcGlowFn pe{g, d_frame_pos + first, d_padded};
             bk.for_each(planes * c0 * c1, pe);
             plane_reduce_any(d_padded, planes, (size_t)c0 * c1, d_clip);
-            rotate_planes(nullptr, planes, g.n0, g.n1, d_xf, d_clip, d_padded, d_rotated, g.n_y, g.n_x);
+            rotate_planes(nullptr, planes, g.n0, g.n1, d_xf, d_clip, d_padded, d_padded + planes * c0 * c1,
+                          d_rotated, g.n_y, g.n_x);
         }
         ScanFrameFn ff;
         ff.g = g; ff.s = sums(); ff.frame_pos = d_frame_pos + first;

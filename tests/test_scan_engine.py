@@ -136,6 +136,15 @@ def check_helpers(se):
         assert np.abs(se.shift(x, s) - scan_oracle.shift(x, s)).max() < 1e-12, s
     for f in (0.5, 0.2, 0.1, 1 / 3):
         assert np.abs(se.scale_y(x, f) - scan_oracle.scale_y(x, f)).max() < 1e-12, f
+    # lines of 160 samples and more take the blocked prefilter (warm-up windows instead of a walk
+    # along the whole line): same numbers
+    x3 = rng.random((1, 200, 170))
+    assert np.abs(se.rotate(x3, 33.0) - scan_oracle.rotate(x3, 33.0)).max() < 1e-12
+    assert np.abs(se.shift(x3, (0, 3.5, -2.25)) - scan_oracle.shift(x3, (0, 3.5, -2.25))).max() < 1e-12
+    assert np.abs(se.scale_y(x3, 0.2) - scan_oracle.scale_y(x3, 0.2)).max() < 1e-12
+    spike = np.zeros((1, 230, 161)); spike[0, 0, 0] = spike[0, -1, -1] = spike[0, 100, 80] = 1.0
+    assert np.abs(se.rotate(spike, 10.0) - scan_oracle.rotate(spike, 10.0)).max() < 1e-13
+    assert np.abs(se.shift(spike, (0, 0.5, 0.5)) - scan_oracle.shift(spike, (0, 0.5, 0.5))).max() < 1e-13
     for sigma, trunc in ((4.2, 4), ((0, 2.5, 0), 8), ((0, 3.1, 3.1), 8), (30.0, 4)):
         ref = ndi.gaussian_filter(x, sigma, truncate=trunc)
         assert np.abs(se.gaussian_filter(x, sigma, truncate=trunc) - ref).max() < 1e-13, sigma
@@ -231,3 +240,18 @@ def test_gpu_matches_oracle_on_a_tiled_object():
                 assert np.abs(a[k] - b[k]).max() <= 1e-11 * np.abs(b[k]).max(), (typ, a['rot'], k)
         for k, v in ref['maxima'].items():
             assert abs(got['maxima'][k] - v) <= 1e-11 * abs(v), k
+
+
+def test_rescan_line_with_long_columns_on_cpu_replay(emulated):
+    """A frame tall enough (190 rows) for the blocked column prefilter of scale_y, excitation
+    wide enough to reach the frame edges (no support limiting: reflect folds in both blur
+    passes), two orientations: camera images and maxima against the oracle."""
+    obj = lines_object(100)
+    got = emulated.simulate_imaging(obj, 'rescan_line', 20, 1, 2, 1, 45, verbose=False)
+    ref = scan_oracle.simulate_imaging(obj, 'rescan_line', 20, 1, 2, 1, 45, keep_frames=False)
+    for a, b in zip(got['orientations'], ref['orientations']):
+        assert a['rot'] == b['rot'] and a['camera_exposures'] == b['camera_exposures']
+        for k in ('reconstruction', 'cum_detector_sig'):
+            assert np.abs(a[k] - b[k]).max() <= 1e-11 * np.abs(b[k]).max(), (a['rot'], k)
+    for k, v in ref['maxima'].items():
+        assert abs(got['maxima'][k] - v) <= 1e-11 * abs(v), k
