@@ -112,7 +112,11 @@ extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double
     if (!h || !name) return set_error(LSTED_ERR_ARG, "null pointer");
     LSTED_TRY
     h->bk->activate();
-    h->e->options_changed();
+    // switches that select kernels or their arguments invalidate the captured iteration
+    static const char* const kernel_switches[] = {"prefetch", "fast_path", "row_dual", "row_plan2",
+                                                  "row_tma", "col_sub", "real_otf", "graph"};
+    for (size_t i = 0; i < sizeof(kernel_switches) / sizeof(kernel_switches[0]); ++i)
+        if (!strcmp(name, kernel_switches[i])) h->e->options_changed();
     if (!strcmp(name, "exact_clip")) {
         h->e->set_exact_clip(value != 0);
         return LSTED_OK;

@@ -64,7 +64,7 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_, int CS_
     static_assert(Inv::MA == 1 && Inv::NA == NT_, "row unpack assumes one pass-A butterfly per thread");
     static_assert(RC % 2 == 1, "row split assumes an odd last radix");
     static_assert(C_ % CS_ == 0, "sub-blocks must tile a column block");
-    static_assert(RA * RC < 256 && RC * RA < 256 && NT_ <= 256 && NT_ * CS_ >= 256 && RA * RB * RC >= 256,
+    static_assert(RA * RC < 256 && RC * RA < 256 && NT_ <= 256 && RA * RB * RC >= 256,
                   "base twiddles of both transforms must sit in the first COL_TW table entries");
     static_assert((RC - QH) * PX <= LSM_ROW, "mirror exchange must fit one row buffer");
     static_assert(2 * L * sizeof(T_) + sizeof(mbar_t) <= LSM_ROW * 2 * sizeof(T_),
@@ -273,7 +273,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
 #define LSTED_OTF_AT(base) (SUB ? (const T*)(base) + cl : real_otf_at<P>((const T*)(base), c))
     cx.phase(regs, [&](int tid, ColRegs<P>& r) {
         // (hoisting base twiddles into registers costs spills at 96 registers / 576 threads)
-        if (tid < P::COL_TW) tw_s[tid] = a.tw[tid];   // (NTHR >= COL_TW)
+        for (int i = tid; i < (int)P::COL_TW; i += NTHR) tw_s[i] = a.tw[i];
         if (MODE == COL_HT) {
             LSTED_UNROLL
             for (int i = 0; i < P::NKEEP; ++i) r.keep[i] = mk<T>(0, 0);
@@ -450,7 +450,7 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
 
     cx.phase(regs, [&](int tid, ColRegs<P>& r) {
         (void)r;
-        if (tid < P::COL_TW) tw_s[tid] = a.tw[tid];
+        for (int i = tid; i < (int)P::COL_TW; i += (int)P::COL_THREADS) tw_s[i] = a.tw[i];
         if (tid == 0) mbar_init(mbar);
     });
     unsigned seq = 0;                  // OTF slabs consumed so far (mbarrier phase parity)

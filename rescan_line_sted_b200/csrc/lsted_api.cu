@@ -77,7 +77,13 @@ struct DeviceCtx {
 #define LSTED_FAST_PR 1
 #endif
 typedef lsted::FastPlan<float, 16, 9, 15, 144, LSTED_FAST_C32, LSTED_FAST_PR, LSTED_FAST_CS32> Plan2160f;
-typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
+#ifndef LSTED_FP64_PR
+#define LSTED_FP64_PR 1   // row pairs per CTA of the fp64 plan (A/B at build time; 2: row_mid +13 %)
+#endif
+#ifndef LSTED_FP64_CS
+#define LSTED_FP64_CS 1   // columns per column CTA of the fp64 plan (1 of 2: sub-block CTAs; 2: col_h +15 %, col_ht +35 %)
+#endif
+typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, LSTED_FP64_PR, LSTED_FP64_CS> Plan2160d;
 
 // G: image geometry known at compile time (the 2048-wide / 107-wide-PSF headline case) or not
 typedef lsted::RowGeomFixed<2048, 53> RowGeom2048;

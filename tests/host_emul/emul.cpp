@@ -40,7 +40,13 @@ struct HostCtx {
 };
 
 typedef lsted::FastPlan<float, 16, 9, 15, 144, 4, 1, 2> Plan2160f;
-typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, 2> Plan2160d;
+#ifndef LSTED_FP64_PR
+#define LSTED_FP64_PR 1   // row pairs per CTA of the fp64 plan (A/B at build time; 2: row_mid +13 %)
+#endif
+#ifndef LSTED_FP64_CS
+#define LSTED_FP64_CS 1   // columns per column CTA of the fp64 plan (1 of 2: sub-block CTAs; 2: col_h +15 %, col_ht +35 %)
+#endif
+typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, LSTED_FP64_PR, LSTED_FP64_CS> Plan2160d;
 template <typename T> struct PlanFor;
 template <> struct PlanFor<float> { typedef Plan2160f type; };
 template <> struct PlanFor<double> { typedef Plan2160d type; };
