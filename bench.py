@@ -497,7 +497,9 @@ def main():
             'frames_per_sec': 1000.0 / ms_sh, 'ms_per_frame': ms_sh,
             'speedup_vs_one_gpu': ms_step / ms_sh, 'efficiency': ms_step / ms_sh / world,
             'rel_l2_vs_unsharded': rel, 'rel_l2_tolerance': 2e-4,
-            'reduction': 'fused into the column kernel over NVLink peer memory (P2P)' if sd.p2p
+            'reduction': 'NVLS: multimem.ld_reduce / multimem.st through the NVSwitch (CUDA multicast object)'
+                         if getattr(sd, 'nvls', False)
+                         else 'fused into the column kernel over NVLink peer memory (P2P)' if sd.p2p
                          else 'ncclAllReduce of the Fourier-domain partial sum',
             'orientations_per_gpu': sd.k1 - sd.k0}
         sd.close()

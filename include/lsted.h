@@ -177,6 +177,22 @@ int lsted_deconv_shard(lsted_deconv* h, int rank, int world, int k_offset, const
 #define LSTED_P2P_HANDLE_BYTES 192
 int lsted_deconv_p2p_export(lsted_deconv* h, char* handles_out, int capacity);
 int lsted_deconv_p2p_attach(lsted_deconv* h, const char* all_handles, int world);
+/* Orientation sharding, fp32: sum the partial H_t spectra THROUGH THE NVSWITCH (NVLS).  The
+ * spectrum that carries the partial sums is bound to one CUDA multicast object shared by the
+ * ranks; after the column kernel every rank pulls the sum of its 1/world of the buffer with
+ * multimem.ld_reduce (added inside the switch) and pushes it to every replica with multimem.st
+ * -- one kernel, (world-1)/world of the buffer per NVLink direction, no staging.  Choreography
+ * (one process per GPU; rescan_line_sted_b200/sharded.py does it over torch.distributed and a
+ * Unix socket), after lsted_deconv_shard and before any data is on the handle:
+ *   rank 0:       lsted_deconv_nvls_create(h, world, &fd)   POSIX descriptor of the object
+ *   other ranks:  receive a duplicate of that descriptor (SCM_RIGHTS), lsted_deconv_nvls_import
+ *   every rank:   lsted_deconv_nvls_add_device; barrier; lsted_deconv_nvls_bind; barrier.
+ * Without these calls the reduction is the peer-memory kernel above or the NCCL all-reduce. */
+int lsted_deconv_nvls_supported(int device, int* supported);
+int lsted_deconv_nvls_create(lsted_deconv* h, int world, int* fd_out);
+int lsted_deconv_nvls_import(lsted_deconv* h, int world, int fd);
+int lsted_deconv_nvls_add_device(lsted_deconv* h);
+int lsted_deconv_nvls_bind(lsted_deconv* h);
 /* iterate() n times (:520-531); no host transfers.                                 */
 int lsted_deconv_iterate(lsted_deconv* h, int n);
 /* attribute access; k is the PSF index for the per-PSF lists, else 0.

@@ -77,6 +77,10 @@ _DECONV_SIGNATURES = {
                            ctypes.c_int, ctypes.c_char_p],
     'lsted_deconv_p2p_export': [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int],
     'lsted_deconv_p2p_attach': [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int],
+    'lsted_deconv_nvls_create': [ctypes.c_void_p, ctypes.c_int, c_int_p],
+    'lsted_deconv_nvls_import': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int],
+    'lsted_deconv_nvls_add_device': [ctypes.c_void_p],
+    'lsted_deconv_nvls_bind': [ctypes.c_void_p],
     'lsted_deconv_iterate': [ctypes.c_void_p, ctypes.c_int],
     'lsted_deconv_get': [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                          c_double_p],
@@ -99,6 +103,7 @@ _CORE_SIGNATURES = {
     'lsted_host_alloc': [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t],
     'lsted_host_free': [ctypes.c_void_p],
     'lsted_nccl_unique_id': [ctypes.c_char_p],
+    'lsted_deconv_nvls_supported': [ctypes.c_int, c_int_p],
     'lsted_psf_illumination': [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                ctypes.c_int, c_double_p, ctypes.c_int,
                                c_double_p, c_double_p, c_double_p, c_double_p,
@@ -273,6 +278,21 @@ class DeconvHandle:
         """all_handles: the exports of ranks 0..world-1, concatenated."""
         assert len(all_handles) == world * self.P2P_HANDLE_BYTES
         self.lib.call('lsted_deconv_p2p_attach', self._h, all_handles, int(world))
+
+    # NVLS (multicast) reduction of orientation shards: see include/lsted.h
+    def nvls_create(self, world):
+        fd = ctypes.c_int(-1)
+        self.lib.call('lsted_deconv_nvls_create', self._h, int(world), ctypes.byref(fd))
+        return fd.value
+
+    def nvls_import(self, world, fd):
+        self.lib.call('lsted_deconv_nvls_import', self._h, int(world), int(fd))
+
+    def nvls_add_device(self):
+        self.lib.call('lsted_deconv_nvls_add_device', self._h)
+
+    def nvls_bind(self):
+        self.lib.call('lsted_deconv_nvls_bind', self._h)
 
     def iterate(self, n=1):
         self.lib.call('lsted_deconv_iterate', self._h, int(n))

@@ -201,6 +201,46 @@ extern "C" int lsted_deconv_p2p_attach(lsted_deconv* h, const char* all_handles,
     LSTED_CATCH
 }
 
+extern "C" int lsted_deconv_nvls_supported(int device, int* supported) {
+    if (!supported) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    *supported = LSTED_BACKEND::nvls_device_supported(device) ? 1 : 0;
+    return LSTED_OK;
+    LSTED_CATCH
+}
+extern "C" int lsted_deconv_nvls_create(lsted_deconv* h, int world, int* fd_out) {
+    if (!h || !fd_out || world < 2) return set_error(LSTED_ERR_ARG, "bad arguments");
+    LSTED_TRY
+    h->bk->activate();
+    *fd_out = h->e->nvls_create(world);
+    return LSTED_OK;
+    LSTED_CATCH
+}
+extern "C" int lsted_deconv_nvls_import(lsted_deconv* h, int world, int fd) {
+    if (!h || world < 2 || fd < 0) return set_error(LSTED_ERR_ARG, "bad arguments");
+    LSTED_TRY
+    h->bk->activate();
+    h->e->nvls_import(world, fd);
+    return LSTED_OK;
+    LSTED_CATCH
+}
+extern "C" int lsted_deconv_nvls_add_device(lsted_deconv* h) {
+    if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    h->bk->activate();
+    h->e->nvls_add_device();
+    return LSTED_OK;
+    LSTED_CATCH
+}
+extern "C" int lsted_deconv_nvls_bind(lsted_deconv* h) {
+    if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
+    LSTED_TRY
+    h->bk->activate();
+    h->e->nvls_bind();
+    return LSTED_OK;
+    LSTED_CATCH
+}
+
 extern "C" int lsted_deconv_iterate(lsted_deconv* h, int n) {
     if (!h) return set_error(LSTED_ERR_ARG, "null pointer");
     LSTED_TRY

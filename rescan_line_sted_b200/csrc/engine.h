@@ -51,6 +51,11 @@ class EngineBase {
     virtual void options_changed() {}      // a kernel-selection switch moved: drop captured launches
     virtual void p2p_export(char* handles_out) = 0;                       // kIpcBytes
     virtual void p2p_attach(const char* all_handles) = 0;                 // [world][kIpcBytes]
+    // NVLS reduction of orientation shards (fp32): see lsted.h / CudaBackend::nvls_*
+    virtual int nvls_create(int) { throw std::string("the NVLS reduction needs an untiled fp32 handle"); }
+    virtual void nvls_import(int, int) { throw std::string("the NVLS reduction needs an untiled fp32 handle"); }
+    virtual void nvls_add_device() { throw std::string("the NVLS reduction needs an untiled fp32 handle"); }
+    virtual void nvls_bind() { throw std::string("the NVLS reduction needs an untiled fp32 handle"); }
     virtual void info(EngineInfo* out) = 0;
     virtual bool ft_error(const double* image_host, double* out_host) = 0;
 };
@@ -260,7 +265,31 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     }
     void p2p_attach(const char* all) { bk.p2p_attach(rank, world, all, p2p_words); }
     void reduce_over_ranks(cplx<T>* spec) {
-        if (world > 1) bk.all_reduce_sum((T*)spec, 2 * spec_elems(g, g.Ny));
+        if (world < 2) return;
+        if (bk.nvls_ready(spec)) bk.nvls_allreduce((T*)spec, 2 * spec_elems(g, g.Ny));   // through the switch
+        else bk.all_reduce_sum((T*)spec, 2 * spec_elems(g, g.Ny));
+    }
+    // NVLS: the spectrum that carries the partial H_t sums moves into memory bound to a CUDA
+    // multicast object shared by the ranks (call before any data is on the handle)
+    int nvls_create(int world_) {
+        if (sizeof(T) != 4) throw std::string("the NVLS reduction is built for fp32 spectra");
+        return bk.nvls_create(world_, sizeof(cplx<T>) * spec_elems(g, g.Ny));
+    }
+    void nvls_import(int world_, int fd) {
+        if (sizeof(T) != 4) throw std::string("the NVLS reduction is built for fp32 spectra");
+        bk.nvls_import(world_, sizeof(cplx<T>) * spec_elems(g, g.Ny), fd);
+    }
+    void nvls_add_device() { bk.nvls_add_device(); }
+    void nvls_bind() {
+        if (world < 2) throw std::string("nvls_bind: shard the handle first");
+        cplx<T>* region = (cplx<T>*)bk.nvls_bind(rank);
+        bk.sync();
+        bk.free(spec1);
+        spec1 = region;
+        if (tmap_spec1) { bk.free(tmap_spec1); bk.free(tmap_specK); tmap_spec1 = tmap_specK = 0; }
+        tmaps_tried = false;
+        have_estimate = false; have_norm = false;
+        options_changed();
     }
 
     // The steady-state RL iteration is four launches with fixed arguments.  For small objects
@@ -285,7 +314,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         bk.template launch_row<ROW_MID, T>(row_blocks(g) * K, rm);
         ColArgs<T> ct = col_args(g);
         ct.src = specK; ct.dst = spec1; ct.K = K;
-        if (world > 1 && bk.p2p_ready(g, (int)sizeof(cplx<T>))) {
+        if (world > 1 && !bk.nvls_ready(spec1) && bk.p2p_ready(g, (int)sizeof(cplx<T>))) {
             // orientation shards: the sum over ranks happens inside the kernel (peer memory)
             bk.p2p_fill(ct);
             bk.template launch_col<COL_HT, T>(g.nxb, ct);

@@ -189,6 +189,64 @@ __global__ void __launch_bounds__(kEwThreads) win_kernel(const lsted::WinArgs<T>
         lsted::win_apply<OP, T>(a, e);
 }
 
+// ---------------------------------------------------------------------------
+// All-reduce of the partial H_t spectra of orientation-sharded ranks THROUGH THE NVSWITCH
+// (NVLS): every rank's spectrum buffer is bound to one CUDA multicast object; rank r owns 1/world
+// of the buffer, pulls the sum of the `world` replicas with multimem.ld_reduce (the switch adds
+// them on the way) and pushes it back with multimem.st (the switch copies it into every
+// replica).  Per GPU the NVLink carries (world-1)/world of the buffer in each direction once;
+// nothing is staged, no rank reads another's memory element by element.
+// flags (in the same multicast region, 64-bit counters that only grow):
+//   [0] ranks whose partial sums are complete (the column kernel before this one has ended),
+//   [1] CTAs whose slice has been pushed to every replica.
+// The grid must be co-resident (one CTA per SM): CTAs spin on counters other CTAs raise.
+// ---------------------------------------------------------------------------
+enum { kNvlsUnroll = 2 };
+__device__ __forceinline__ void nvls_signal(unsigned long long* mc_flag) {
+    asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(mc_flag), "l"(1ull) : "memory");
+}
+__device__ __forceinline__ void nvls_wait(const unsigned long long* uc_flag, unsigned long long target) {
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(uc_flag) : "memory");
+    } while (v < target);
+}
+__global__ void __launch_bounds__(512) nvls_allreduce_f32_kernel(float* mc, size_t n4, unsigned long long* mc_flags,
+                                                                 const unsigned long long* uc_flags, int rank,
+                                                                 int world, unsigned long long epoch) {
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) nvls_signal(mc_flags + 0);
+        nvls_wait(uc_flags + 0, epoch * (unsigned long long)world);
+    }
+    __syncthreads();
+    const size_t lo = n4 * (size_t)rank / world, hi = n4 * (size_t)(rank + 1) / world;
+    // kNvlsUnroll reductions in flight per thread: a round trip through the switch is microseconds
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * kNvlsUnroll) {
+        float v[kNvlsUnroll][4];
+#pragma unroll
+        for (int u = 0; u < kNvlsUnroll; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i < hi)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(v[u][0]), "=f"(v[u][1]), "=f"(v[u][2]), "=f"(v[u][3]) : "l"(mc + 4 * i) : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < kNvlsUnroll; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i < hi)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                             ::"l"(mc + 4 * i), "f"(v[u][0]), "f"(v[u][1]), "f"(v[u][2]), "f"(v[u][3]) : "memory");
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        nvls_signal(mc_flags + 1);
+        nvls_wait(uc_flags + 1, epoch * (unsigned long long)world * gridDim.x);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads) rect_kernel(const lsted::RectArgs<T> a) {
     const size_t n = (size_t)a.nimg * a.h * a.w;
@@ -337,6 +395,7 @@ class CudaBackend {
     }
     ~CudaBackend() {
         cudaSetDevice(device_);
+        try { nvls_release(); } catch (...) {}
         for (size_t i = 0; i < p2p_opened_.size(); ++i) cudaIpcCloseMemHandle(p2p_opened_[i]);
         if (comm_) nccl_api().CommDestroy(comm_);
         for (size_t i = 0; i < ev_pool_.size(); ++i) cudaEventDestroy(ev_pool_[i]);
@@ -375,6 +434,146 @@ class CudaBackend {
         NCCL_CHECK(nccl_api().Broadcast(p, p, n, ncclDouble, root, comm_, stream_));
         after();
     }
+    // ---- NVLS: all-reduce through the NVSwitch over a CUDA multicast object (fp32 spectra) ----
+    // Driver entry points are looked up at run time (no libcuda link dependency).
+    template <class Fn> static Fn drv(const char* name) {
+        void* fn = 0;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess || !fn) {
+            lsted::ApiError e; e.code = LSTED_ERR_CUDA; e.msg = std::string("driver entry point missing: ") + name; throw e;
+        }
+        return (Fn)fn;
+    }
+    static void cu_check(CUresult r, const char* what) {
+        if (r == CUDA_SUCCESS) return;
+        lsted::ApiError e; e.code = LSTED_ERR_CUDA;
+        e.msg = std::string(what) + " failed with CUresult " + std::to_string((int)r);
+        throw e;
+    }
+    static bool nvls_device_supported(int device) {
+        int v = 0;
+        typedef CUresult (*attr_fn)(int*, CUdevice_attribute, CUdevice);
+        typedef CUresult (*get_fn)(CUdevice*, int);
+        CUdevice d;
+        if (drv<get_fn>("cuDeviceGet")(&d, device) != CUDA_SUCCESS) return false;
+        if (drv<attr_fn>("cuDeviceGetAttribute")(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, d) != CUDA_SUCCESS) return false;
+        return v != 0;
+    }
+    // multicast region = data (16-byte multiple) + 256 bytes of counters, rounded up to the
+    // granularity of multicast objects and of physical allocations on this device
+    size_t nvls_region_bytes(size_t data_bytes, int world) {
+        CUmulticastObjectProp mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.numDevices = world; mp.size = data_bytes + 256; mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        size_t g1 = 0, g2 = 0;
+        typedef CUresult (*gran_fn)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags);
+        cu_check(drv<gran_fn>("cuMulticastGetGranularity")(&g1, &mp, CU_MULTICAST_GRANULARITY_MINIMUM), "cuMulticastGetGranularity");
+        CUmemAllocationProp ap = nvls_alloc_prop();
+        typedef CUresult (*agran_fn)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+        cu_check(drv<agran_fn>("cuMemGetAllocationGranularity")(&g2, &ap, CU_MEM_ALLOC_GRANULARITY_MINIMUM), "cuMemGetAllocationGranularity");
+        const size_t g = g1 > g2 ? g1 : g2;
+        nvls_gran_ = g;
+        return (data_bytes + 256 + g - 1) / g * g;
+    }
+    CUmemAllocationProp nvls_alloc_prop() const {
+        CUmemAllocationProp ap;
+        memset(&ap, 0, sizeof(ap));
+        ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE; ap.location.id = device_;
+        ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        return ap;
+    }
+    // rank 0: create the multicast object, hand out a POSIX file descriptor of it
+    int nvls_create(int world, size_t data_bytes) {
+        nvls_world_ = world; nvls_data_bytes_ = (data_bytes + 15) / 16 * 16;
+        nvls_bytes_ = nvls_region_bytes(nvls_data_bytes_, world);
+        CUmulticastObjectProp mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.numDevices = world; mp.size = nvls_bytes_; mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        typedef CUresult (*create_fn)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*);
+        cu_check(drv<create_fn>("cuMulticastCreate")(&nvls_mc_, &mp), "cuMulticastCreate");
+        int fd = -1;
+        typedef CUresult (*export_fn)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long);
+        cu_check(drv<export_fn>("cuMemExportToShareableHandle")(&fd, nvls_mc_, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0),
+                 "cuMemExportToShareableHandle");
+        nvls_have_mc_ = true;
+        return fd;
+    }
+    // other ranks: import the object from a duplicate of rank 0's descriptor
+    void nvls_import(int world, size_t data_bytes, int fd) {
+        nvls_world_ = world; nvls_data_bytes_ = (data_bytes + 15) / 16 * 16;
+        nvls_bytes_ = nvls_region_bytes(nvls_data_bytes_, world);
+        typedef CUresult (*import_fn)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType);
+        cu_check(drv<import_fn>("cuMemImportFromShareableHandle")(&nvls_mc_, (void*)(uintptr_t)fd,
+                                                                  CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR),
+                 "cuMemImportFromShareableHandle");
+        nvls_have_mc_ = true;
+    }
+    void nvls_add_device() {
+        typedef CUresult (*get_fn)(CUdevice*, int);
+        typedef CUresult (*add_fn)(CUmemGenericAllocationHandle, CUdevice);
+        CUdevice d;
+        cu_check(drv<get_fn>("cuDeviceGet")(&d, device_), "cuDeviceGet");
+        cu_check(drv<add_fn>("cuMulticastAddDevice")(nvls_mc_, d), "cuMulticastAddDevice");
+    }
+    // after every rank has added its device: back the region with local memory, map both views
+    void* nvls_bind(int rank) {
+        typedef CUresult (*mcreate_fn)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+        typedef CUresult (*bind_fn)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long);
+        typedef CUresult (*reserve_fn)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+        typedef CUresult (*map_fn)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+        typedef CUresult (*access_fn)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+        CUmemAllocationProp ap = nvls_alloc_prop();
+        cu_check(drv<mcreate_fn>("cuMemCreate")(&nvls_mem_, nvls_bytes_, &ap, 0), "cuMemCreate");
+        cu_check(drv<bind_fn>("cuMulticastBindMem")(nvls_mc_, 0, nvls_mem_, 0, nvls_bytes_, 0), "cuMulticastBindMem");
+        CUmemAccessDesc ad;
+        memset(&ad, 0, sizeof(ad));
+        ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE; ad.location.id = device_; ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        cu_check(drv<reserve_fn>("cuMemAddressReserve")(&nvls_uc_, nvls_bytes_, nvls_gran_, 0, 0), "cuMemAddressReserve");
+        cu_check(drv<map_fn>("cuMemMap")(nvls_uc_, nvls_bytes_, 0, nvls_mem_, 0), "cuMemMap (unicast)");
+        cu_check(drv<access_fn>("cuMemSetAccess")(nvls_uc_, nvls_bytes_, &ad, 1), "cuMemSetAccess (unicast)");
+        cu_check(drv<reserve_fn>("cuMemAddressReserve")(&nvls_mcp_, nvls_bytes_, nvls_gran_, 0, 0), "cuMemAddressReserve");
+        cu_check(drv<map_fn>("cuMemMap")(nvls_mcp_, nvls_bytes_, 0, nvls_mc_, 0), "cuMemMap (multicast)");
+        cu_check(drv<access_fn>("cuMemSetAccess")(nvls_mcp_, nvls_bytes_, &ad, 1), "cuMemSetAccess (multicast)");
+        CUDA_CHECK(cudaMemsetAsync((void*)nvls_uc_, 0, nvls_bytes_, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        nvls_rank_ = rank; nvls_epoch_ = 0; nvls_bound_ = true;
+        bytes_ += nvls_bytes_;
+        return (void*)nvls_uc_;
+    }
+    void nvls_release() {
+        if (!nvls_have_mc_) return;
+        typedef CUresult (*unmap_fn)(CUdeviceptr, size_t);
+        typedef CUresult (*release_fn)(CUmemGenericAllocationHandle);
+        typedef CUresult (*afree_fn)(CUdeviceptr, size_t);
+        if (nvls_bound_) {
+            drv<unmap_fn>("cuMemUnmap")(nvls_mcp_, nvls_bytes_);
+            drv<unmap_fn>("cuMemUnmap")(nvls_uc_, nvls_bytes_);
+            drv<afree_fn>("cuMemAddressFree")(nvls_mcp_, nvls_bytes_);
+            drv<afree_fn>("cuMemAddressFree")(nvls_uc_, nvls_bytes_);
+            drv<release_fn>("cuMemRelease")(nvls_mem_);
+        }
+        drv<release_fn>("cuMemRelease")(nvls_mc_);
+        nvls_have_mc_ = nvls_bound_ = false;
+    }
+    bool nvls_ready(const void* buf) const { return nvls_bound_ && buf == (const void*)nvls_uc_; }
+    // in-place sum over the ranks of the fp32 buffer that nvls_bind returned
+    void nvls_allreduce(float* buf, size_t n) {
+        if (!nvls_ready(buf) || n * sizeof(float) > nvls_data_bytes_) {
+            lsted::ApiError e; e.code = LSTED_ERR_STATE; e.msg = "NVLS all-reduce on a buffer that is not bound"; throw e;
+        }
+        unsigned long long* mc_flags = (unsigned long long*)((char*)nvls_mcp_ + nvls_data_bytes_);
+        const unsigned long long* uc_flags = (const unsigned long long*)((char*)nvls_uc_ + nvls_data_bytes_);
+        before(KK_EW);
+        nvls_allreduce_f32_kernel<<<num_sms_, 512, 0, stream_>>>((float*)nvls_mcp_, (n + 3) / 4, mc_flags, uc_flags,
+                                                                 nvls_rank_, nvls_world_, ++nvls_epoch_);
+        after();
+    }
+    void nvls_allreduce(double*, size_t) {
+        lsted::ApiError e; e.code = LSTED_ERR_STATE; e.msg = "the NVLS all-reduce is built for fp32 spectra"; throw e;
+    }
+
     // Halo exchange of a tile-sharded object (tiled.h): one grouped ncclSend / ncclRecv pair per
     // neighbour, contiguous staging buffers (counts in elements of T).
     template <typename T> void exchange(int npeers, const int* peers, T* const* send, const size_t* nsend,
@@ -480,6 +679,7 @@ class CudaBackend {
     }
     void free(void* p) {
         if (!p) return;
+        if (p == (void*)nvls_uc_) return;   // multicast-bound region: unmapped by nvls_release()
         std::map<void*, size_t>::iterator it = sizes_.find(p);
         if (it != sizes_.end()) { bytes_ -= it->second; sizes_.erase(it); }
         cudaFree(p);
@@ -865,6 +1065,13 @@ class CudaBackend {
     int device_;
     cudaStream_t stream_;
     size_t bytes_;
+    // NVLS state
+    CUmemGenericAllocationHandle nvls_mc_ = 0, nvls_mem_ = 0;
+    CUdeviceptr nvls_uc_ = 0, nvls_mcp_ = 0;
+    size_t nvls_bytes_ = 0, nvls_data_bytes_ = 0, nvls_gran_ = 0;
+    int nvls_world_ = 1, nvls_rank_ = 0;
+    unsigned long long nvls_epoch_ = 0;
+    bool nvls_have_mc_ = false, nvls_bound_ = false;
     bool profile_, use_fast_;
     bool graph_ = getenv("LSTED_GRAPH") ? atoi(getenv("LSTED_GRAPH")) != 0 : true;   // A/B switch, option "graph"
     std::map<void*, size_t> sizes_;   // live allocations (for lsted_deconv_info)

@@ -9,6 +9,7 @@ plumbing:
 * `shard_items` / `gather_reports` -- independent units (frames, sweep
   points of `psf_report_batch`) dealt round-robin, results gathered once.
 """
+import ctypes
 import os
 
 import numpy as np
@@ -70,12 +71,24 @@ class OrientationShardedDeconvolver:
                 unique_id[0] = _lib.nccl_unique_id(lib)
             dist.broadcast_object_list(unique_id, src=0, group=group)
         self.handle.shard(self.rank, self.world, self.k0, unique_id[0])
+        info = self.handle.info()
+        # fp32: the per-iteration sum over ranks goes THROUGH THE NVSWITCH (NVLS): the spectrum of
+        # the partial sums is bound to one CUDA multicast object; multimem.ld_reduce adds the
+        # replicas in the switch, multimem.st copies the result into all of them.  Measured on
+        # B200 (2048^2, K = 16): 8 GPUs 85.2 vs 72.1 frames/s with the peer-memory kernel below,
+        # 2 GPUs 44.9 vs 46.8 (a rank's own replica also travels through the switch), so the
+        # default is NVLS from 4 ranks up; LSTED_NVLS=1 / 0 forces / forbids it.  Boxes without
+        # multicast support fall through to the paths below.
+        self.nvls = False
+        want_nvls = os.environ.get('LSTED_NVLS', 'auto')
+        if (self.world > 1 and precision == 32 and info.tiles_y * info.tiles_x == 1
+                and (want_nvls == '1' or (want_nvls != '0' and self.world >= 4))):
+            self.nvls = self._attach_nvls(lib, device, group)
         # Fast path (2160-point transforms): the per-iteration sum over ranks runs inside the
         # column kernel over NVLink peer memory; the CUDA-IPC handles travel through the
         # process group.  LSTED_P2P=0 keeps the NCCL all-reduce.
         self.p2p = False
-        info = self.handle.info()
-        if (self.world > 1 and os.environ.get('LSTED_P2P', '1') != '0'
+        if (self.world > 1 and not self.nvls and os.environ.get('LSTED_P2P', '1') != '0'
                 and info.Ly == 2160 and info.tiles_y * info.tiles_x == 1):
             mine = self.handle.p2p_export()
             parts = [None] * self.world
@@ -83,6 +96,53 @@ class OrientationShardedDeconvolver:
             self.handle.p2p_attach(b''.join(parts), self.world)
             dist.barrier(group=group)
             self.p2p = True
+
+    def _attach_nvls(self, lib, device, group):
+        """Bind this rank's partial-sum spectrum to a multicast object shared by the group.
+        The object is created on rank 0; its POSIX file descriptor reaches the other
+        processes as SCM_RIGHTS ancillary data over a Unix socket (the one way to move a
+        descriptor between unrelated processes)."""
+        import socket
+        import torch.distributed as dist
+        ok = ctypes.c_int(0)
+        try:
+            lib.call('lsted_deconv_nvls_supported', int(device), ctypes.byref(ok))
+        except RuntimeError:
+            ok = ctypes.c_int(0)
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(ok.value), group=group)
+        if not all(flags):
+            return False
+        path = [None]
+        server = None
+        if self.rank == 0:
+            fd = self.handle.nvls_create(self.world)
+            path[0] = '\0lsted_nvls_%d_%d' % (os.getpid(), id(self))    # abstract socket name
+            server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            server.bind(path[0])
+            server.listen(self.world)
+        dist.broadcast_object_list(path, src=0, group=group)
+        if self.rank == 0:
+            for _ in range(self.world - 1):
+                conn, _ = server.accept()
+                socket.send_fds(conn, [b'mc'], [fd])
+                conn.recv(2)                     # the peer has imported the object
+                conn.close()
+            server.close()
+            os.close(fd)
+        else:
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            c.connect(path[0])
+            _, fds, _, _ = socket.recv_fds(c, 16, 1)
+            self.handle.nvls_import(self.world, fds[0])
+            c.send(b'ok')
+            c.close()
+            os.close(fds[0])
+        self.handle.nvls_add_device()
+        dist.barrier(group=group)                # every device is in the multicast team
+        self.handle.nvls_bind()
+        dist.barrier(group=group)                # every replica is bound before the first use
+        return True
 
     def create_data(self, obj, total_brightness, seed):
         """Each rank simulates only its orientations; the Poisson streams are

@@ -33,7 +33,8 @@ def main():
         t = torch.from_numpy(est.copy()).cuda()
         ref = t.clone()
         dist.broadcast(ref, src=0)
-        out[tag] = {'est1': e1, 'est8': e8, 'replica_diff': float((t - ref).abs().max())}
+        out[tag] = {'est1': e1, 'est8': e8, 'replica_diff': float((t - ref).abs().max()),
+                    'nvls': bool(d.nvls)}
         # in-kernel Poisson field must not depend on the GPU count
         d.create_data(g['object_u8'].astype(np.float64), 5e10, 123)
         noisy = d.local_measurements(_lib.NOISY)
@@ -57,11 +58,17 @@ def main():
         single.iterate(3)
         want = single.get(_lib.ESTIMATE)
         res = {}
-        for mode in ('1', '0'):
-            os.environ['LSTED_P2P'] = mode
+        # reductions: 'nvls' multicast through the switch (fp32), '1' peer-memory kernel, '0' NCCL
+        for mode in (('nvls',) if precision == 32 else ()) + ('1', '0'):
+            os.environ['LSTED_NVLS'] = '1' if mode == 'nvls' else '0'
+            os.environ['LSTED_P2P'] = '0' if mode == '0' else '1'
             d = sharded.OrientationShardedDeconvolver(psfs, (2100, 2100), precision=precision,
                                                       device=local)
-            assert d.p2p == (mode == '1')
+            if mode == 'nvls' and not d.nvls:      # no multicast support on this box
+                res['nvls_unavailable'] = True
+                d.close()
+                continue
+            assert d.nvls == (mode == 'nvls') and d.p2p == (mode == '1')
             d.create_data(obj, 1e10, 3)
             d.iterate(3)
             est = d.estimate
@@ -72,6 +79,7 @@ def main():
             res[mode + '_replica_diff'] = float((t - ref).abs().max() / ref.abs().max())
             d.close()
         os.environ.pop('LSTED_P2P', None)
+        os.environ.pop('LSTED_NVLS', None)
         out[tag] = dict(res, tol=tol)
         single.close()
     # tiled object, tiles dealt to the GPUs with halo exchange, 2160-point tiles (fast path), fp64

@@ -87,6 +87,14 @@ class HostBackend {
     int row_prefetch_distance() const { return 3; }
     int row_final_prefetch_distance() const { return 5; }
     void set_prefetch(bool) {}
+    // NVLS needs the NVSwitch: never available on the CPU replay
+    static bool nvls_device_supported(int) { return false; }
+    bool nvls_ready(const void*) const { return false; }
+    int nvls_create(int, size_t) { throw std::string("NVLS: GPU only"); }
+    void nvls_import(int, size_t, int) { throw std::string("NVLS: GPU only"); }
+    void nvls_add_device() { throw std::string("NVLS: GPU only"); }
+    void* nvls_bind(int) { throw std::string("NVLS: GPU only"); }
+    template <typename T> void nvls_allreduce(T*, size_t) { throw std::string("NVLS: GPU only"); }
     void set_graph(bool) {}
     bool graph_capable() const { return false; }   // captured launches exist on the GPU only
     void graph_begin() {}

@@ -39,7 +39,9 @@ def test_orientation_sharding_nccl(tmp_path):
         assert r[tag]['replica_diff'] == 0.0
         assert r[tag]['noise_independent_of_world']
     # fast path: fused peer-memory reduction ('1') and NCCL all-reduce ('0') against one GPU
+    # (fp32 also through the NVSwitch multicast object, 'nvls', where the box supports it)
+    assert 'nvls' in r['p2p_fp32'] or r['p2p_fp32'].get('nvls_unavailable')
     for tag in ('p2p_fp32', 'p2p_fp64'):
-        for mode in ('1', '0'):
+        for mode in [m for m in ('nvls', '1', '0') if m in r[tag]]:
             assert r[tag][mode] < 10 * r[tag]['tol'], (tag, mode, r[tag])
             assert r[tag][mode + '_replica_diff'] == 0.0, (tag, mode, r[tag])
