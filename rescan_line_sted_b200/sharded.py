@@ -101,47 +101,78 @@ class OrientationShardedDeconvolver:
         """Bind this rank's partial-sum spectrum to a multicast object shared by the group.
         The object is created on rank 0; its POSIX file descriptor reaches the other
         processes as SCM_RIGHTS ancillary data over a Unix socket (the one way to move a
-        descriptor between unrelated processes)."""
+        descriptor between unrelated processes).  Every stage is agreed on by all ranks: a
+        failure anywhere before the bind makes every rank fall back to the other reductions."""
         import socket
         import torch.distributed as dist
+
+        def everyone(ok):
+            flags = [None] * self.world
+            dist.all_gather_object(flags, bool(ok), group=group)
+            return all(flags)
+
         ok = ctypes.c_int(0)
         try:
             lib.call('lsted_deconv_nvls_supported', int(device), ctypes.byref(ok))
         except RuntimeError:
             ok = ctypes.c_int(0)
-        flags = [None] * self.world
-        dist.all_gather_object(flags, bool(ok.value), group=group)
-        if not all(flags):
+        if not everyone(ok.value):
             return False
-        path = [None]
-        server = None
+        path, server, fd, good = [None], None, -1, True
         if self.rank == 0:
-            fd = self.handle.nvls_create(self.world)
-            path[0] = '\0lsted_nvls_%d_%d' % (os.getpid(), id(self))    # abstract socket name
-            server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-            server.bind(path[0])
-            server.listen(self.world)
+            try:
+                fd = self.handle.nvls_create(self.world)
+                path[0] = '\0lsted_nvls_%d_%d' % (os.getpid(), id(self))    # abstract socket name
+                server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                server.bind(path[0])
+                server.listen(self.world)
+                server.settimeout(60)
+            except (RuntimeError, OSError):
+                path[0], good = None, False
         dist.broadcast_object_list(path, src=0, group=group)
-        if self.rank == 0:
-            for _ in range(self.world - 1):
-                conn, _ = server.accept()
-                socket.send_fds(conn, [b'mc'], [fd])
-                conn.recv(2)                     # the peer has imported the object
-                conn.close()
-            server.close()
-            os.close(fd)
-        else:
-            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-            c.connect(path[0])
-            _, fds, _, _ = socket.recv_fds(c, 16, 1)
-            self.handle.nvls_import(self.world, fds[0])
-            c.send(b'ok')
-            c.close()
-            os.close(fds[0])
-        self.handle.nvls_add_device()
-        dist.barrier(group=group)                # every device is in the multicast team
-        self.handle.nvls_bind()
-        dist.barrier(group=group)                # every replica is bound before the first use
+        if path[0] is None:
+            return False
+        try:
+            if self.rank == 0:
+                for _ in range(self.world - 1):
+                    conn, _ = server.accept()
+                    socket.send_fds(conn, [b'mc'], [fd])
+                    conn.settimeout(60)
+                    conn.recv(2)                     # the peer has imported the object (or given up)
+                    conn.close()
+            else:
+                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                c.settimeout(60)
+                c.connect(path[0])
+                _, fds, _, _ = socket.recv_fds(c, 16, 1)
+                try:
+                    self.handle.nvls_import(self.world, fds[0])
+                except RuntimeError:
+                    good = False
+                c.send(b'ok')
+                c.close()
+                os.close(fds[0])
+        except OSError:
+            good = False
+        finally:
+            if server is not None:
+                server.close()
+            if fd >= 0:
+                os.close(fd)
+        if not everyone(good):
+            return False
+        try:
+            self.handle.nvls_add_device()
+        except RuntimeError:
+            good = False
+        if not everyone(good):                   # (also the barrier: every device is in the team)
+            return False
+        try:
+            self.handle.nvls_bind()
+        except RuntimeError:
+            good = False
+        if not everyone(good):                   # (also the barrier: every replica is bound)
+            raise RuntimeError('NVLS: binding the multicast object failed on a rank; set LSTED_NVLS=0')
         return True
 
     def create_data(self, obj, total_brightness, seed):
