@@ -138,6 +138,9 @@ extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double
     if (!strcmp(name, "real_otf")) { h->bk->set_real_otf(value != 0); return LSTED_OK; }   // before set_psfs
     if (!strcmp(name, "profile")) { h->bk->set_profile(value != 0); return LSTED_OK; }
     if (!strcmp(name, "graph")) { h->bk->set_graph(value != 0); return LSTED_OK; }
+    if (!strcmp(name, "nvls_ctas")) { h->bk->set_nvls_shape((int)value, 0); return LSTED_OK; }      // before the first iteration
+    if (!strcmp(name, "nvls_probe")) { h->bk->set_nvls_probe(value != 0); return LSTED_OK; }
+    if (!strcmp(name, "nvls_threads")) { h->bk->set_nvls_shape(-1, (int)value); return LSTED_OK; }
     return set_error(LSTED_ERR_ARG, std::string("unknown option ") + name);
     LSTED_CATCH
 }

@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(kEwThreads) win_kernel(const lsted::WinArgs<T>
 // nothing is staged, no rank reads another's memory element by element.
 // flags (in the same multicast region, 64-bit counters that only grow):
 //   [0] ranks whose partial sums are complete (the column kernel before this one has ended),
-//   [1] CTAs whose slice has been pushed to every replica.
-// The grid must be co-resident (one CTA per SM): CTAs spin on counters other CTAs raise.
+//   [1] ranks whose slice has been pushed to every replica ([2]: this rank's CTAs, local).
+// The grid must be co-resident (at most one CTA per SM): CTAs spin on counters other CTAs raise.
 // ---------------------------------------------------------------------------
 enum { kNvlsUnroll = 2 };
 __device__ __forceinline__ void nvls_signal(unsigned long long* mc_flag) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(512) nvls_allreduce_f32_kernel(float* mc, size
         nvls_wait(uc_flags + 0, epoch * (unsigned long long)world);
     }
     __syncthreads();
-    const size_t lo = n4 * (size_t)rank / world, hi = n4 * (size_t)(rank + 1) / world;
+    const size_t lo = n4 * (size_t)rank / world, hi = n4 * (size_t)(rank + 1) / world;   // (n4 == 0: barriers only, a timing probe)
     // kNvlsUnroll reductions in flight per thread: a round trip through the switch is microseconds
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * kNvlsUnroll) {
@@ -242,8 +242,11 @@ __global__ void __launch_bounds__(512) nvls_allreduce_f32_kernel(float* mc, size
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        nvls_signal(mc_flags + 1);
-        nvls_wait(uc_flags + 1, epoch * (unsigned long long)world * gridDim.x);
+        // the CTAs of this rank count themselves on a local word; the last one tells every rank
+        unsigned long long* local = (unsigned long long*)uc_flags + 2;
+        const unsigned long long seen = atomicAdd(local, 1ull) + 1;
+        if (seen == epoch * gridDim.x) nvls_signal(mc_flags + 1);
+        nvls_wait(uc_flags + 1, epoch * (unsigned long long)world);
     }
 }
 
@@ -566,7 +569,11 @@ class CudaBackend {
         unsigned long long* mc_flags = (unsigned long long*)((char*)nvls_mcp_ + nvls_data_bytes_);
         const unsigned long long* uc_flags = (const unsigned long long*)((char*)nvls_uc_ + nvls_data_bytes_);
         before(KK_EW);
-        nvls_allreduce_f32_kernel<<<num_sms_, 512, 0, stream_>>>((float*)nvls_mcp_, (n + 3) / 4, mc_flags, uc_flags,
+        // 32 CTAs x 512 threads: measured on 8 GPUs (17.8 MB): 0.061 ms, of which 0.024 ms are the two
+        // cross-GPU barriers; 148 CTAs: 0.072, 8 CTAs: 0.065 (scripts/nvls_sweep.py)
+        const int ctas = nvls_ctas_ > 0 && nvls_ctas_ <= num_sms_ ? nvls_ctas_ : (num_sms_ < 32 ? num_sms_ : 32);
+        const int threads = nvls_threads_ >= 32 && nvls_threads_ <= 512 ? nvls_threads_ / 32 * 32 : 512;
+        nvls_allreduce_f32_kernel<<<ctas, threads, 0, stream_>>>((float*)nvls_mcp_, nvls_probe_ ? 0 : (n + 3) / 4, mc_flags, uc_flags,
                                                                  nvls_rank_, nvls_world_, ++nvls_epoch_);
         after();
     }
@@ -703,6 +710,8 @@ class CudaBackend {
         return ms;
     }
     void set_profile(bool on) { profile_ = on; }
+    void set_nvls_probe(bool on) { nvls_probe_ = on; }
+    void set_nvls_shape(int ctas, int threads) { if (ctas >= 0) nvls_ctas_ = ctas; if (threads > 0) nvls_threads_ = threads; }
     // ---- CUDA graphs: the steady RL iteration replayed as one driver call (engine.h) ----
     void set_graph(bool on) { graph_ = on; }
     bool graph_capable() const { return graph_ && !profile_; }
@@ -1072,6 +1081,8 @@ class CudaBackend {
     int nvls_world_ = 1, nvls_rank_ = 0;
     unsigned long long nvls_epoch_ = 0;
     bool nvls_have_mc_ = false, nvls_bound_ = false;
+    int nvls_ctas_ = 0, nvls_threads_ = 512;   // options "nvls_ctas" / "nvls_threads" (tuning)
+    bool nvls_probe_ = false;                  // option "nvls_probe": barriers only (timing; results are wrong)
     bool profile_, use_fast_;
     bool graph_ = getenv("LSTED_GRAPH") ? atoi(getenv("LSTED_GRAPH")) != 0 : true;   // A/B switch, option "graph"
     std::map<void*, size_t> sizes_;   // live allocations (for lsted_deconv_info)

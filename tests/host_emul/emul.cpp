@@ -95,6 +95,8 @@ class HostBackend {
     void nvls_add_device() { throw std::string("NVLS: GPU only"); }
     void* nvls_bind(int) { throw std::string("NVLS: GPU only"); }
     template <typename T> void nvls_allreduce(T*, size_t) { throw std::string("NVLS: GPU only"); }
+    void set_nvls_shape(int, int) {}
+    void set_nvls_probe(bool) {}
     void set_graph(bool) {}
     bool graph_capable() const { return false; }   // captured launches exist on the GPU only
     void graph_begin() {}
