@@ -255,3 +255,35 @@ def test_rescan_line_with_long_columns_on_cpu_replay(emulated):
             assert np.abs(a[k] - b[k]).max() <= 1e-11 * np.abs(b[k]).max(), (a['rot'], k)
     for k, v in ref['maxima'].items():
         assert abs(got['maxima'][k] - v) <= 1e-11 * abs(v), k
+
+
+def compare_with_oracle(se, obj, typ, width, R, n_or, pad):
+    frames = {}
+    for name, sim in (('engine', se.simulate_imaging), ('oracle', oracle_sim)):
+        got = []
+
+        def record(filename, *a, got=got):
+            got.append((os.path.basename(filename), [np.array(x) for x in a[:7]], a[7], a[8]))
+        sim(obj, typ, width, R, n_or, 1, pad, comparison_name='case', generate_figure=record, verbose=False)
+        frames[name] = got
+    assert len(frames['engine']) == len(frames['oracle']) > 0
+    for (fa, aa, pa, ca), (fb, ab, pb, cb) in zip(frames['engine'], frames['oracle']):
+        assert fa.split('deg_')[1] == fb.split('deg_')[1] and pa == pb and ca == cb
+        for x, y in zip(aa, ab):
+            assert np.abs(x - y).max() <= TOL, fa
+
+
+def test_point_scan_on_the_excitation_support_on_cpu_replay(emulated):
+    """A descan-point scan whose excitation box and blur stay clear of the frame edges: both blur
+    passes, the reductions and the glow maximum then work on that box only (the golden point case
+    is too small for it).  Every drawn frame against the oracle."""
+    obj = lines_object(24)
+    h = emulated.ScanHandle('descan_point', obj.shape, 18, 8, 2)
+    assert h.padded_shape == (60, 60) and len(h.positions) == 625
+    h.close()
+    compare_with_oracle(emulated, obj, 'descan_point', 8, 2, 1, 18)
+
+
+@pytest.mark.gpu
+def test_point_scan_on_the_excitation_support_on_gpu():
+    compare_with_oracle(engine(), lines_object(24), 'descan_point', 8, 2, 1, 18)
