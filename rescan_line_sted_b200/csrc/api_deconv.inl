@@ -114,7 +114,7 @@ extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double
     h->bk->activate();
     // switches that select kernels or their arguments invalidate the captured iteration
     static const char* const kernel_switches[] = {"prefetch", "fast_path", "row_dual", "row_plan2",
-                                                  "row_tma", "col_sub", "real_otf", "graph"};
+                                                  "row_tma", "col_sub", "real_otf", "graph", "k_split"};
     for (size_t i = 0; i < sizeof(kernel_switches) / sizeof(kernel_switches[0]); ++i)
         if (!strcmp(name, kernel_switches[i])) h->e->options_changed();
     if (!strcmp(name, "exact_clip")) {
@@ -139,6 +139,7 @@ extern "C" int lsted_deconv_set_option(lsted_deconv* h, const char* name, double
     if (!strcmp(name, "profile")) { h->bk->set_profile(value != 0); return LSTED_OK; }
     if (!strcmp(name, "graph")) { h->bk->set_graph(value != 0); return LSTED_OK; }
     if (!strcmp(name, "nvls_ctas")) { h->bk->set_nvls_shape((int)value, 0); return LSTED_OK; }      // before the first iteration
+    if (!strcmp(name, "k_split")) { h->bk->set_k_split(value != 0); return LSTED_OK; }
     if (!strcmp(name, "nvls_probe")) { h->bk->set_nvls_probe(value != 0); return LSTED_OK; }
     if (!strcmp(name, "nvls_threads")) { h->bk->set_nvls_shape(-1, (int)value); return LSTED_OK; }
     return set_error(LSTED_ERR_ARG, std::string("unknown option ") + name);

@@ -243,6 +243,9 @@ template <typename T> struct ColArgs {
                             // and the OTFs are stored centred (then they are real; sy = sx = 0)
     cplx<T>* dst;           // OTF: [K] XB(Ly); H: [K] XB(Ny); HT: XB(Ny)
     int K;
+    int k_split;            // H (generic kernel): > 1 = the K orientations of a column block are spread
+                            // over k_split CTAs (grid nxb * k_split, block = part * nxb + xb), each
+                            // repeating the forward transform: small frames are latency-, not work-bound
     int rows_in;            // valid input rows (zero padded up to Ly)
     int src_same;           // HT: every k reads the same input spectrum (H_t of all-ones images)
     T scale;                // OTF: 1/(Lx*Ly)
@@ -263,8 +266,9 @@ template <int MODE, typename T, class Ctx>
 LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
     const ConvGeom& g = a.g;
     const int Ny = g.Ny, Ly = g.Ly, Lp = g.Lpy, C = g.C;
-    const int xb = (MODE == COL_OTF) ? block % g.nxb : block;
-    const int kk = (MODE == COL_OTF) ? block / g.nxb : 0;
+    const bool split = MODE == COL_H && a.k_split > 1;
+    const int xb = (MODE == COL_OTF || split) ? block % g.nxb : block;
+    const int kk = (MODE == COL_OTF || split) ? block / g.nxb : 0;
     cplx<T>* b0 = smem;
     cplx<T>* b1 = smem + (size_t)C * Lp;
     cplx<T>* b2 = smem + (size_t)2 * C * Lp;
@@ -327,7 +331,9 @@ LSTED_HD void col_body(Ctx& cx, int block, const ColArgs<T>& a, cplx<T>* smem) {
         SmemSrc<T> s0 = {b0, Lp};
         cplx<T>* A = fft_batch<-1, T>(cx, g.py, a.tw, s0, b1, b0, C, Lp);
         cplx<T>* f1 = (A == b0) ? b1 : b0;
-        for (int k = 0; k < a.K; ++k) {
+        const int k_lo = split ? (int)((long long)a.K * kk / a.k_split) : 0;
+        const int k_hi = split ? (int)((long long)a.K * (kk + 1) / a.k_split) : a.K;
+        for (int k = k_lo; k < k_hi; ++k) {
             const cplx<T>* otf = a.otf + (size_t)k * img_ly + (size_t)xb * slab_ly;
             cx.parallel_for(C * Ly, [&](int w) {
                 const int y = w / C, c = w - y * C;

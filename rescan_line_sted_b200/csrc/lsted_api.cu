@@ -362,6 +362,11 @@ static NcclApi& nccl_api() {
 enum KernelKind { KK_ROW_FWD = 0, KK_ROW_INV_STORE, KK_ROW_INV_SIM, KK_ROW_MID, KK_ROW_FINAL,
                   KK_COL_OTF, KK_COL_H, KK_COL_HT, KK_EW };
 
+// Deconvolver handles alive in this process: with many of them (figure 2 iterates 24 round-robin,
+// each on its own stream) the GPU is kept busy by the other handles' kernels and spreading one
+// frame's orientations over more CTAs only adds work (measured: 24 handles 6.5 -> 7.5 us / iteration).
+static int g_live_backends = 0;
+
 class CudaBackend {
   public:
     explicit CudaBackend(int device) : device_(device), stream_(0), bytes_(0), profile_(false),
@@ -379,6 +384,7 @@ class CudaBackend {
         CUDA_CHECK(cudaEventCreate(&t0_));
         CUDA_CHECK(cudaEventCreate(&t1_));
         CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device));
+        ++g_live_backends;
         memset(prof_ms_, 0, sizeof(prof_ms_));
         memset(prof_n_, 0, sizeof(prof_n_));
         const char* dual = getenv("LSTED_ROW_DUAL");   // A/B switch, same as option "row_dual"
@@ -398,6 +404,7 @@ class CudaBackend {
     }
     ~CudaBackend() {
         cudaSetDevice(device_);
+        --g_live_backends;
         try { nvls_release(); } catch (...) {}
         for (size_t i = 0; i < p2p_opened_.size(); ++i) cudaIpcCloseMemHandle(p2p_opened_[i]);
         if (comm_) nccl_api().CommDestroy(comm_);
@@ -710,6 +717,7 @@ class CudaBackend {
         return ms;
     }
     void set_profile(bool on) { profile_ = on; }
+    void set_k_split(bool on) { k_split_ = on; }
     void set_nvls_probe(bool on) { nvls_probe_ = on; }
     void set_nvls_shape(int ctas, int threads) { if (ctas >= 0) nvls_ctas_ = ctas; if (threads > 0) nvls_threads_ = threads; }
     // ---- CUDA graphs: the steady RL iteration replayed as one driver call (engine.h) ----
@@ -1003,6 +1011,17 @@ class CudaBackend {
         ensure_smem(col_kernel<MODE, T>, smem);
         const int kind = MODE == lsted::COL_OTF ? KK_COL_OTF : MODE == lsted::COL_H ? KK_COL_H : KK_COL_HT;
         const int threads = sizeof(T) == 4 ? kColThreads32 : kColThreads64;
+        if (MODE == lsted::COL_H && a.K > 1 && k_split_ && 2 * grid <= num_sms_ && g_live_backends <= 2) {
+            // a small frame (the reference's 128^2 objects: 25 column blocks): the K + 1 dependent
+            // transforms of a block are the latency of this launch; spread the orientations over
+            // the idle SMs, every CTA repeating the forward transform
+            lsted::ColArgs<T> b = a;
+            b.k_split = num_sms_ / grid < a.K ? num_sms_ / grid : a.K;
+            before(kind);
+            col_kernel<MODE, T><<<grid * b.k_split, threads, smem, stream_>>>(b);
+            after();
+            return;
+        }
         before(kind);
         col_kernel<MODE, T><<<grid, threads, smem, stream_>>>(a);
         after();
@@ -1083,6 +1102,7 @@ class CudaBackend {
     bool nvls_have_mc_ = false, nvls_bound_ = false;
     int nvls_ctas_ = 0, nvls_threads_ = 512;   // options "nvls_ctas" / "nvls_threads" (tuning)
     bool nvls_probe_ = false;                  // option "nvls_probe": barriers only (timing; results are wrong)
+    bool k_split_ = true;                      // option "k_split": orientations of small frames over idle SMs (col_h)
     bool profile_, use_fast_;
     bool graph_ = getenv("LSTED_GRAPH") ? atoi(getenv("LSTED_GRAPH")) != 0 : true;   // A/B switch, option "graph"
     std::map<void*, size_t> sizes_;   // live allocations (for lsted_deconv_info)

@@ -68,7 +68,9 @@ static int g_dual_launches = 0;
 static int g_row2_launches = 0;
 static int g_real_otf_launches = 0;
 static int g_row_tma_launches = 0;
+static int g_k_split_launches = 0;
 static int g_col_sub_launches = 0;
+extern "C" int emul_k_split_launches(void) { return g_k_split_launches; }
 extern "C" int emul_col_sub_launches(void) { return g_col_sub_launches; }
 extern "C" int emul_row_tma_launches(void) { return g_row_tma_launches; }
 extern "C" int emul_real_otf_launches(void) { return g_real_otf_launches; }
@@ -97,6 +99,7 @@ class HostBackend {
     template <typename T> void nvls_allreduce(T*, size_t) { throw std::string("NVLS: GPU only"); }
     void set_nvls_shape(int, int) {}
     void set_nvls_probe(bool) {}
+    void set_k_split(bool) {}
     void set_graph(bool) {}
     bool graph_capable() const { return false; }   // captured launches exist on the GPU only
     void graph_begin() {}
@@ -314,12 +317,21 @@ class HostBackend {
             }
             return;
         }
+        // small frames: the orientations of a column block spread over several "CTAs" like on
+        // the GPU (there: as many as idle SMs allow; here 3, an uneven split of most K)
+        lsted::ColArgs<T> b_args = a;
+        int total = grid;
+        if (MODE == lsted::COL_H && a.K > 1 && grid <= 74) {
+            b_args.k_split = a.K < 3 ? a.K : 3;
+            total = grid * b_args.k_split;
+            ++g_k_split_launches;
+        }
 #pragma omp parallel
         {
             std::vector<lsted::cplx<T> > smem((size_t)3 * a.g.C * a.g.Lpy);  // (no 227 KB limit here)
             HostCtx cx;
 #pragma omp for schedule(dynamic)
-            for (int b = 0; b < grid; ++b) lsted::col_body<MODE, T>(cx, b, a, smem.data());
+            for (int b = 0; b < total; ++b) lsted::col_body<MODE, T>(cx, b, b_args, smem.data());
         }
     }
     template <int OP, typename T> void ew(const lsted::EwArgs<T>& a) {

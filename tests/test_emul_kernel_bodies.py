@@ -445,3 +445,22 @@ def test_error_spectrum_on_device(lib, shape):
         h.iterate(1)        # the scratch image it used does not disturb the iteration state
         assert np.isfinite(h.get(_lib.ESTIMATE)).all()
         h.close()
+
+
+def test_small_frames_spread_orientations_over_ctas():
+    """Generic col_h on a small frame: the K orientations of a column block go to several CTAs
+    (each repeating the forward transform) -- same numbers as the oracle, and the path is taken."""
+    import ctypes
+    lib = emul_support.emulator_library()
+    lib.cdll.emul_k_split_launches.restype = ctypes.c_int
+    before = lib.cdll.emul_k_split_launches()
+    rng = np.random.default_rng(21)
+    for K in (2, 4, 5):
+        psfs = rng.random((K, 9, 7))
+        x = rng.random((1, 40, 52)) + 0.1
+        h = _lib.DeconvHandle(lib, psfs, (40, 52), precision=64)
+        o = orc.Deconvolver([p[None] for p in psfs])
+        got, want = h.H(x), np.concatenate(o.H(x))
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-12
+        h.close()
+    assert lib.cdll.emul_k_split_launches() > before

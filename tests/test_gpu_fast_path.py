@@ -132,3 +132,27 @@ def test_graph_replay_of_the_iteration_is_bit_identical(shape, K, precision):
     for u, v in zip(est[0], est[1]):
         assert np.isfinite(v).all() and v.min() > 0
         assert np.array_equal(u, v)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('K', [2, 4, 10])
+def test_orientations_of_small_frames_over_idle_sms_are_bit_identical(K):
+    """Generic col_h on the reference's own frame size (128^2, 107^2 PSFs): the K orientations
+    of a column block spread over the idle SMs (option `k_split`, default on) against one CTA
+    per block: same arithmetic per orientation -> identical bits."""
+    from rescan_line_sted_b200 import _lib
+    lib = _lib.get()
+    rng = np.random.default_rng(17)
+    psfs = rng.random((K, 107, 107))
+    x = rng.random((1, 128, 128)) + 0.1
+    est = {}
+    for split in (0, 1):
+        h = _lib.DeconvHandle(lib, psfs, (128, 128), precision=32)
+        h.set_option('k_split', split)
+        h.create_data(x, 1e6 * x.size, 1)
+        h.iterate(5)
+        est[split] = (h.get(_lib.ESTIMATE), h.get(_lib.NOISELESS, K - 1))
+        h.close()
+    for u, v in zip(est[0], est[1]):
+        assert np.isfinite(v).all() and v.min() >= 0
+        assert np.array_equal(u, v)
