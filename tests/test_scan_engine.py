@@ -287,3 +287,11 @@ def test_point_scan_on_the_excitation_support_on_cpu_replay(emulated):
 @pytest.mark.gpu
 def test_point_scan_on_the_excitation_support_on_gpu():
     compare_with_oracle(engine(), lines_object(24), 'descan_point', 8, 2, 1, 18)
+
+
+@pytest.mark.parametrize('typ,n_or,pad', [('descan_point', 1, 9), ('nondescan_multipoint', 1, 9),
+                                          ('descan_line', 2, 25), ('rescan_line', 2, 25)])
+def test_rectangular_objects_on_cpu_replay(emulated, typ, n_or, pad):
+    """Objects that are not square (rows != columns): every drawn frame against the oracle."""
+    obj = lines_object(56)[:, 8:44, :].copy()        # 36 x 56
+    compare_with_oracle(emulated, obj, typ, 9, 2, n_or, pad)
