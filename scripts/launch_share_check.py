@@ -13,7 +13,8 @@ import sys
 NAMES = [('row_fast_kernel<0', 'row_fwd'), ('row_fast_kernel<1', 'row_inv_store'),
          ('row_fast_kernel<2', 'row_inv_sim'), ('row_fast_kernel<3', 'row_mid'),
          ('row_mid_dual_kernel', 'row_mid'), ('row_fast_kernel<4', 'row_final'),
-         ('col_fast_kernel<1', 'col_h'), ('col_fast_kernel<2', 'col_ht')]
+         ('col_fast_kernel<1', 'col_h'), ('col_fast_kernel<2', 'col_ht'),
+         ('col_sub_kernel<1', 'col_h'), ('col_sub_kernel<2', 'col_ht')]
 
 
 def main(csv_path, json_path):
