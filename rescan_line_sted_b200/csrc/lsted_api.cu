@@ -494,8 +494,16 @@ class CudaBackend {
         ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
         return ap;
     }
+    // one multicast team per handle: a bound region is the handle's spectrum until it is destroyed
+    void nvls_refuse_rebind() {
+        if (nvls_bound_) {
+            lsted::ApiError e; e.code = LSTED_ERR_STATE; e.msg = "this handle is already bound to a multicast object"; throw e;
+        }
+        if (nvls_have_mc_) nvls_release();   // an attach that was abandoned half way
+    }
     // rank 0: create the multicast object, hand out a POSIX file descriptor of it
     int nvls_create(int world, size_t data_bytes) {
+        nvls_refuse_rebind();
         nvls_world_ = world; nvls_data_bytes_ = (data_bytes + 15) / 16 * 16;
         nvls_bytes_ = nvls_region_bytes(nvls_data_bytes_, world);
         CUmulticastObjectProp mp;
@@ -512,6 +520,7 @@ class CudaBackend {
     }
     // other ranks: import the object from a duplicate of rank 0's descriptor
     void nvls_import(int world, size_t data_bytes, int fd) {
+        nvls_refuse_rebind();
         nvls_world_ = world; nvls_data_bytes_ = (data_bytes + 15) / 16 * 16;
         nvls_bytes_ = nvls_region_bytes(nvls_data_bytes_, world);
         typedef CUresult (*import_fn)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType);
@@ -529,6 +538,9 @@ class CudaBackend {
     }
     // after every rank has added its device: back the region with local memory, map both views
     void* nvls_bind(int rank) {
+        if (!nvls_have_mc_ || nvls_bound_) {
+            lsted::ApiError e; e.code = LSTED_ERR_STATE; e.msg = "nvls_bind: create / import the multicast object first (once)"; throw e;
+        }
         typedef CUresult (*mcreate_fn)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
         typedef CUresult (*bind_fn)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long);
         typedef CUresult (*reserve_fn)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
