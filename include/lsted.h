@@ -139,8 +139,10 @@ int lsted_deconv_info(lsted_deconv* h, lsted_deconv_info_t* info);
 int lsted_deconv_set_option(lsted_deconv* h, const char* name, double value);
 /* record_iteration's error spectrum (:539-546): out[Ny][Nx] = log(1 + |fftshift(fft2(x -
  * true_object))|) with x = `image` (host, [Ny][Nx]) or, when image is NULL, the estimate in
- * HBM.  *done = 0 (and out untouched) when a side of the image has a prime factor above 5
- * or does not fit one CTA: the caller then transforms on the host like the reference.     */
+ * HBM.  Sides with a prime factor above 5 (or longer than one CTA holds) and tiled objects
+ * take a direct O(N)-per-bin transform, also on the device.  *done = 0 (out untouched) only
+ * for image == NULL on a rank of a sharded tiled object, which holds a region of the
+ * estimate: pass the gathered estimate as `image` there.                                  */
 int lsted_deconv_ft_error(lsted_deconv* h, const double* image, double* out, int* done);
 /* create_data_from_object (:496-512).  rescale != 0 applies total_brightness.
  * Noise: in-kernel Philox4x32-10 Poisson, stream selected by `seed`.               */

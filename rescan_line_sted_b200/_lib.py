@@ -316,7 +316,8 @@ class DeconvHandle:
 
     def ft_error(self, image=None):
         """log(1 + |fftshift(fft2(image - true_object))|), image = the estimate in HBM when
-        None; (1, Ny, Nx) float64, or None when the size has no on-device transform."""
+        None; (1, Ny, Nx) float64.  None only on a rank of a sharded tiled object asked for its
+        own estimate (it holds a region of it): pass the gathered image instead."""
         out = pooled_pinned_empty((1, self.Ny, self.Nx), lib=self.lib)
         done = ctypes.c_int(0)
         if image is None:

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "plan.h"
+#include "ew_bodies.cuh"
 
 namespace lsted {
 
@@ -104,7 +105,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
         options_changed();
         void* all[] = {tw_x, tw_y, otf, spec1, specK, true_object, estimate, norm,
                        scratch, noiseless, noisy, stage64, object64, partial, tmpK, p2p_recv, p2p_flags,
-                       otf_real, tmap_specK, tmap_spec1};
+                       otf_real, tmap_specK, tmap_spec1, tw_fx, tw_fy, spec_ft, tw_dx, tw_dy, spec_direct};
         for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) bk.free(all[i]);
     }
 
@@ -409,8 +410,9 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
 
     // record_iteration's error spectrum (ref:539-546): log(1 + |fftshift(fft2(x - true_object))|)
     // with x = the estimate in HBM (image_host == 0) or a host image.  An un-padded Ny x Nx
-    // transform with the generic kernels; false when a side is not 2^a 3^b 5^c (or does not fit a
-    // CTA): the caller falls back to numpy.
+    // transform with the generic kernels; when a side is not 2^a 3^b 5^c (or does not fit a
+    // CTA) the direct transform of ew_bodies.cuh (dft_direct_apply) does it instead -- always
+    // on the device, always true.
     bool ft_error(const double* image_host, double* out_host) {
         if (!ft_tried) {
             ft_tried = true;
@@ -426,9 +428,18 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
                 bk.upload(tw_fy, tw.data(), sizeof(cplx<T>) * gft.Ly);
                 spec_ft = (cplx<T>*)bk.alloc(sizeof(cplx<T>) * spec_elems(gft, gft.Ny));
                 bk.sync();
+            } else {
+                std::vector<cplx<double> > tw;
+                tw.resize(g.Nx); fill_twiddles<double>(g.Nx, tw.data());
+                tw_dx = (cplx<double>*)bk.alloc(sizeof(cplx<double>) * g.Nx);
+                bk.upload(tw_dx, tw.data(), sizeof(cplx<double>) * g.Nx);
+                tw.resize(g.Ny); fill_twiddles<double>(g.Ny, tw.data());
+                tw_dy = (cplx<double>*)bk.alloc(sizeof(cplx<double>) * g.Ny);
+                bk.upload(tw_dy, tw.data(), sizeof(cplx<double>) * g.Ny);
+                spec_direct = (cplx<double>*)bk.alloc(sizeof(cplx<double>) * npix);
+                bk.sync();
             }
         }
-        if (!ft_ok) return false;
         const T* x = estimate;
         if (image_host) {
             bk.upload(stage64, image_host, sizeof(double) * npix);
@@ -436,6 +447,16 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
             x = scratch;
         }
         bk.subtract(scratch, x, true_object, npix);
+        if (!ft_ok) {
+            DftArgs<T> da;
+            memset(&da, 0, sizeof(da));
+            da.real_in = scratch; da.spec = spec_direct; da.twx = tw_dx; da.twy = tw_dy;
+            da.logmag = stage64; da.Ny = g.Ny; da.Nx = g.Nx;
+            bk.template dft_direct<0, T>(da);
+            bk.template dft_direct<1, T>(da);
+            bk.download(out_host, stage64, sizeof(double) * npix);
+            return true;
+        }
         RowArgs<T> ra;
         memset(&ra, 0, sizeof(ra));
         ra.g = gft; ra.tw = tw_fx; ra.nimg = 1; ra.real_in = scratch; ra.spec_out = spec_ft;
@@ -480,6 +501,7 @@ template <typename T, class BK> class DeconvEngine : public EngineBase {
     ConvGeom gft;                       // un-padded transform of the error spectrum (ft_error)
     bool ft_tried = false, ft_ok = false;
     cplx<T>*tw_fx = 0, *tw_fy = 0, *spec_ft = 0;
+    cplx<double>*tw_dx = 0, *tw_dy = 0, *spec_direct = 0;   // direct transform (sides without a plan)
     T* tmpK;  // K images, allocated on first use by the host-array forms of H / H_t
     cplx<T>* p2p_recv; unsigned* p2p_flags; size_t p2p_words;
     bool tmaps_tried; void* tmap_specK; void* tmap_spec1;

@@ -26,6 +26,49 @@ template <int OP, typename T> LSTED_HD void ew_apply(const EwArgs<T>& a, size_t 
     else if (OP == EW_SUB) a.t0[i] = a.t1[i] - a.t2[i];
 }
 
+
+// Direct (O(N) per bin) 2-D transform for record_iteration's error spectrum on image sides the
+// Stockham plans do not cover (a prime factor above 5, or a column that does not fit a CTA):
+// pass 0 = rows (real image -> full complex spectrum), pass 1 = columns + log(1 + |.|) + fftshift.
+// Twiddles come from a table by a running index (j*k mod N without a multiply), sums are fp64
+// whatever the engine's precision -- this is a diagnostic output, not the iteration.
+template <typename T> struct DftArgs {
+    const T* real_in;              // [Ny][Nx] (pass 0)
+    cplx<double>* spec;            // [Ny][Nx] pass 0 out / pass 1 in
+    const cplx<double>* twx;       // exp(-2 pi i j / Nx), j < Nx
+    const cplx<double>* twy;       // exp(-2 pi i j / Ny), j < Ny
+    double* logmag;                // [Ny][Nx] (pass 1), fftshifted like np.fft.fftshift
+    int Ny, Nx;
+};
+
+template <int PASS, typename T> LSTED_HD void dft_direct_apply(const DftArgs<T>& a, size_t e) {
+    const int y = (int)(e / a.Nx), x = (int)(e - (size_t)y * a.Nx);   // output bin (ky | y, kx)
+    double re = 0.0, im = 0.0;
+    if (PASS == 0) {
+        const T* row = a.real_in + (size_t)y * a.Nx;
+        int idx = 0;
+        for (int n = 0; n < a.Nx; ++n) {
+            const cplx<double> w = a.twx[idx];
+            const double v = (double)row[n];
+            re += v * w.x; im += v * w.y;
+            idx += x; if (idx >= a.Nx) idx -= a.Nx;
+        }
+        a.spec[e] = mk<double>(re, im);
+    } else {
+        int idx = 0;
+        for (int n = 0; n < a.Ny; ++n) {
+            const cplx<double> w = a.twy[idx];
+            const cplx<double> v = a.spec[(size_t)n * a.Nx + x];
+            re += v.x * w.x - v.y * w.y; im += v.x * w.y + v.y * w.x;
+            idx += y; if (idx >= a.Ny) idx -= a.Ny;
+        }
+        int ys = y + a.Ny / 2, xs = x + a.Nx / 2;
+        if (ys >= a.Ny) ys -= a.Ny;
+        if (xs >= a.Nx) xs -= a.Nx;
+        a.logmag[(size_t)ys * a.Nx + xs] = log(1.0 + sqrt(re * re + im * im));
+    }
+}
+
 }  // namespace lsted
 
 // ---------------------------------------------------------------------------

@@ -181,6 +181,14 @@ __global__ void __launch_bounds__(kEwThreads) ew_kernel(const lsted::EwArgs<T> a
         lsted::ew_apply<OP, T>(a, i);
 }
 
+template <int PASS, typename T>
+__global__ void __launch_bounds__(kEwThreads) dft_direct_kernel(const lsted::DftArgs<T> a) {
+    const size_t n = (size_t)a.Ny * a.Nx;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+        lsted::dft_direct_apply<PASS, T>(a, e);
+}
+
 template <int OP, typename T>
 __global__ void __launch_bounds__(kEwThreads) win_kernel(const lsted::WinArgs<T> a) {
     const size_t n = (size_t)a.nimg * a.W * a.W;
@@ -1045,6 +1053,15 @@ class CudaBackend {
         if (blocks > cap) blocks = cap;
         before(KK_EW);
         ew_kernel<OP, T><<<(int)blocks, kEwThreads, 0, stream_>>>(a);
+        after();
+    }
+    // record_iteration's error spectrum on sides without a Stockham plan (ew_bodies.cuh)
+    template <int PASS, typename T> void dft_direct(const lsted::DftArgs<T>& a) {
+        const size_t n = (size_t)a.Ny * a.Nx;
+        if (n == 0) return;
+        const size_t blocks = (n + kEwThreads - 1) / kEwThreads;   // one bin per thread: O(N) work each
+        before(KK_EW);
+        dft_direct_kernel<PASS, T><<<(unsigned)blocks, kEwThreads, 0, stream_>>>(a);
         after();
     }
     template <int OP, typename T> void launch_win(const lsted::WinArgs<T>& a) {

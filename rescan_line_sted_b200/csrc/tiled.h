@@ -73,7 +73,8 @@ template <typename T, class BK> class TiledEngine : public EngineBase {
     }
     ~TiledEngine() {
         void* all[] = {true_object, estimate, norm, noiseless, noisy, ratio, win1, win2, winK,
-                       stage64, partial, halo_send, halo_recv, stage_region};
+                       stage64, partial, halo_send, halo_recv, stage_region,
+                       ft_scratch, tw_dx, tw_dy, spec_direct};
         for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); ++i) bk.free(all[i]);
     }
 
@@ -155,7 +156,40 @@ template <typename T, class BK> class TiledEngine : public EngineBase {
         halo_pixels = total_recv;
         have_norm = false; have_estimate = false;
     }
-    bool ft_error(const double*, double*) { return false; }   // tiled objects: host transform
+    // record_iteration's error spectrum of a tiled object: the direct transform of
+    // ew_bodies.cuh over the whole image (a tiled object's sides have no single-CTA plan).
+    // A rank of a sharded object holds only its region of the estimate: false without a host
+    // image there (the caller passes the gathered estimate instead).
+    bool ft_error(const double* image_host, double* out_host) {
+        if (!image_host && world > 1) return false;
+        if (!ft_scratch) {
+            std::vector<cplx<double> > tw;
+            tw.resize(Nx); fill_twiddles<double>(Nx, tw.data());
+            tw_dx = (cplx<double>*)bk.alloc(sizeof(cplx<double>) * Nx);
+            bk.upload(tw_dx, tw.data(), sizeof(cplx<double>) * Nx);
+            tw.resize(Ny); fill_twiddles<double>(Ny, tw.data());
+            tw_dy = (cplx<double>*)bk.alloc(sizeof(cplx<double>) * Ny);
+            bk.upload(tw_dy, tw.data(), sizeof(cplx<double>) * Ny);
+            spec_direct = (cplx<double>*)bk.alloc(sizeof(cplx<double>) * npix);
+            ft_scratch = (T*)bk.alloc(sizeof(T) * npix);
+            bk.sync();
+        }
+        const T* x = estimate;
+        if (image_host) {
+            bk.upload(stage64, image_host, sizeof(double) * npix);
+            bk.cast_in(ft_scratch, stage64, npix, 1.0);
+            x = ft_scratch;
+        }
+        bk.subtract(ft_scratch, x, true_object, npix);
+        DftArgs<T> da;
+        memset(&da, 0, sizeof(da));
+        da.real_in = ft_scratch; da.spec = spec_direct; da.twx = tw_dx; da.twy = tw_dy;
+        da.logmag = stage64; da.Ny = Ny; da.Nx = Nx;
+        bk.template dft_direct<0, T>(da);
+        bk.template dft_direct<1, T>(da);
+        bk.download(out_host, stage64, sizeof(double) * npix);
+        return true;
+    }
     void info(EngineInfo* o) {
         tile.info(o);
         o->Ny = Ny; o->Nx = Nx; o->iterations_done = iterations_done;
@@ -370,6 +404,8 @@ template <typename T, class BK> class TiledEngine : public EngineBase {
     T *true_object, *estimate, *norm, *noiseless, *noisy, *ratio, *win1, *win2, *winK;
     T *halo_send, *halo_recv;
     double *stage64, *partial, *stage_region;
+    T* ft_scratch = 0;                                      // ft_error (lazy)
+    cplx<double>*tw_dx = 0, *tw_dy = 0, *spec_direct = 0;
 
     // Tile (ty, tx) of the global tile grid; `region` = the big arrays hold the rank's
     // rectangle E rather than the full image.  Only pixels of O are written back.

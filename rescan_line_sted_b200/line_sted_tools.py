@@ -805,18 +805,17 @@ class Deconvolver:
                 del cache[:]                       # new object: start over
             if len(cache) < len(self.estimate_history):
                 # on the device (un-padded 2-D transform + log-magnitude + fftshift in the
-                # column kernel's epilogue); numpy where the size has no device transform
+                # column kernel's epilogue; sides without a Stockham plan and tiled objects take
+                # the direct transform of ew_bodies.cuh) -- there is no host transform
                 h = self._need(_lib.TRUE_OBJECT, 'true_object')
-                true_object = None
                 first_new = len(cache)
                 for i, est in enumerate(self.estimate_history[first_new:], first_new):
                     newest = i == len(self.estimate_history) - 1   # = the estimate in HBM
                     spectrum = h.ft_error(None if newest else est)
+                    if spectrum is None:       # a rank of a sharded object: the gathered estimate
+                        spectrum = h.ft_error(est)
                     if spectrum is None:
-                        if true_object is None:
-                            true_object = self.true_object
-                        spectrum = np.log(1 + np.abs(np.fft.fftshift(
-                            np.fft.fftn(est - true_object, axes=(1, 2)), axes=(1, 2))))
+                        raise RuntimeError('lsted_deconv_ft_error: no device transform ran')
                     cache.append((self._data_version, spectrum))
             spectrum = np.concatenate([c[1] for c in cache], axis=0)
             np_tif.array_to_tif(

@@ -337,6 +337,11 @@ class HostBackend {
     template <int OP, typename T> void ew(const lsted::EwArgs<T>& a) {
         for (size_t i = 0; i < a.n; ++i) lsted::ew_apply<OP, T>(a, i);
     }
+    template <int PASS, typename T> void dft_direct(const lsted::DftArgs<T>& a) {
+        const size_t n = (size_t)a.Ny * a.Nx;
+#pragma omp parallel for schedule(static)
+        for (long long e = 0; e < (long long)n; ++e) lsted::dft_direct_apply<PASS, T>(a, (size_t)e);
+    }
     template <typename T> void launch_rect(const lsted::RectArgs<T>& a) {
         const size_t n = (size_t)a.nimg * a.h * a.w;
         for (size_t e = 0; e < n; ++e) lsted::rect_apply<T>(a, e);

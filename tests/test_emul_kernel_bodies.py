@@ -417,11 +417,11 @@ def test_row_kernels_with_staged_spectrum_chunks(lib, shape):
     assert rel_l2(est[1], o.estimate) < 1e-4
 
 
-@pytest.mark.parametrize('shape', [(96, 128), (45, 50), (128, 75), (14, 128)])
+@pytest.mark.parametrize('shape', [(96, 128), (45, 50), (128, 75), (14, 128), (77, 91)])
 def test_error_spectrum_on_device(lib, shape):
     """record_iteration's log(1 + |fftshift(fft2(estimate - true_object))|) (ref:539-546)
     from the un-padded device transform: even / odd sides, the estimate in HBM or a host
-    image; sizes with a prime factor above 5 report "not done" (host transform instead)."""
+    image; sides with a prime factor above 5 go through the direct transform (no host path)."""
     rng = np.random.default_rng(3)
     psfs = rng.random((2, 5, 5))
     obj = rng.random((1,) + shape) + 0.1
@@ -431,10 +431,7 @@ def test_error_spectrum_on_device(lib, shape):
         h.iterate(2)
         est, true = h.get(_lib.ESTIMATE), h.get(_lib.TRUE_OBJECT)
         got = h.ft_error()
-        if shape[0] == 14:
-            assert got is None
-            h.close()
-            continue
+        assert got is not None
         want = np.log(1 + np.abs(np.fft.fftshift(np.fft.fftn(est - true, axes=(1, 2)), axes=(1, 2))))
         assert got.shape == want.shape
         assert np.abs(got - want).max() <= tol * np.abs(want).max()

@@ -48,6 +48,12 @@ def test_tiled_equals_untiled_and_oracle(lib, shape, precision, tol):
     plain.iterate(3)
     assert rel_l2(tiled.get(_lib.ESTIMATE), plain.get(_lib.ESTIMATE)) < 10 * tol
     assert tiled.info().iterations_done == 3
+    # record_iteration's error spectrum of a tiled object (direct transform, ref:539-546)
+    est, true = tiled.get(_lib.ESTIMATE), tiled.get(_lib.TRUE_OBJECT)
+    want = np.log(1 + np.abs(np.fft.fftshift(np.fft.fftn(est - true, axes=(1, 2)), axes=(1, 2))))
+    ft_tol = 1e-12 if precision == 64 else 2e-4
+    assert np.abs(tiled.ft_error() - want).max() <= ft_tol * np.abs(want).max()
+    assert np.abs(tiled.ft_error(est) - want).max() <= ft_tol * np.abs(want).max()
     tiled.close(), plain.close()
 
 
