@@ -606,6 +606,10 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     const size_t xb_stride = (size_t)Nye * C;  // elements between consecutive column blocks
     // XB2: the pair (row y, row y+1) of column c sits at ((xb*Nye + y)*C + 2c) + {0, 1}
     const bool LEAN = TMA == 2 && (MODE == ROW_MID || MODE == ROW_FINAL);
+    // ROW_INV_SIM: dense rounds of exact PTRS attempts before the per-lane sampler loop takes
+    // the rest (queue sizes fall 24 % -> 10 % -> 1 % -> 0.1 % -> 0.01 % of the pixels)
+    enum { NOISE_ROUNDS = 4 };
+    static_assert(2 * P::L + NOISE_ROUNDS + 1 <= 2 * P::LSM_ROW, "noise queue + its counters must fit one row buffer");
     const int NBUF = LEAN ? (MODE == ROW_MID ? 2 : 3) : MODE == ROW_FINAL ? (int)P::ROW_FINAL_BUFS : (int)P::ROW_BUFS;
     const bool stage_est = MODE == ROW_FINAL && P::ROW_FINAL_BUFS == 4 && !LEAN;
     enum { CHUNK = 2 * P::PR * P::C,                                  // complex numbers per chunk
@@ -812,7 +816,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         }
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
-            if (MODE == ROW_INV_SIM && t == 0) *(int*)stage = 0;   // noise queue (below)
+            if (MODE == ROW_INV_SIM && t < NOISE_ROUNDS + 1) ((int*)stage)[t] = 0;   // noise queue counters (below)
             if (!live) return;
             if (!LEAN) I::pass_c(r.v, t, s1, r.twi);
             const T* const rows_s = LEAN ? (const T*)s0 : stage;   // staged measurement / normalisation rows
@@ -837,8 +841,12 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                                 out[o] = a.accumulate ? out[o] + z.x : z.x;
                                 if (two) out[o + Nx] = a.accumulate ? out[o + Nx] + z.y : z.y;
                             } else if (MODE == ROW_INV_SIM) {
-                                out[o] = clip0(z.x);       // noisy image: second loop below
-                                if (two) out[o + Nx] = clip0(z.y);
+                                // noiseless image; the noise steps below read lambda from the
+                                // idle first exchange buffer, not back from global memory
+                                const T l0 = clip0(z.x), l1 = clip0(z.y);
+                                out[o] = l0;
+                                ((T*)s0)[i] = l0;
+                                if (two) { out[o + Nx] = l1; ((T*)s0)[P::L + i] = l1; }
                             } else if (MODE == ROW_MID) {
                                 w.x = rl_ratio<true>(rows_s[i], z.x);
                                 if (two) w.y = rl_ratio<true>(rows_s[P::L + i], z.y);
@@ -859,15 +867,24 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             if (MODE == ROW_MID || MODE == ROW_FINAL) F::pass_a(r.v, t, LEAN ? s1 : s0);
         });
         if (MODE == ROW_INV_SIM) {
-            // Shot noise in two dense steps.  (1) every pixel this thread just wrote gets the
-            // first PTRS attempt (or the whole small-lambda sampler); the ~10 % the squeeze does
-            // not accept go to a queue in shared memory; (2) the queue is drained by all threads
-            // with the full sampler, so its logarithms never run behind a half-empty warp.
+            // Shot noise in dense steps.  (1) Every pixel this thread just wrote gets the squeeze
+            // test of PTRS attempt 0 (or the whole small-lambda sampler); the ~24 % it does not
+            // accept go to a queue in shared memory.  (2) Round r = 0..NOISE_ROUNDS-1: all
+            // threads share the pixels of queue r, one exact attempt r each (logarithms on full
+            // warps only); a pixel whose attempt is rejected moves to queue r + 1, so no lane
+            // waits for another lane's retries (a per-lane retry loop runs every warp for its
+            // unluckiest lane: 3.1 instead of 1.5 attempts per queued pixel).  (3) The handful
+            // left after the last round finish with the plain sampler loop.  The counters are
+            // the same as poisson_sample's, so the field is the one it would give everywhere.
+            // queue counters: stage[0..NOISE_ROUNDS]; entries of even rounds behind them, of
+            // odd rounds in the second exchange buffer; lambda rows in the first one.
             cx.phase(regs, [&](int tid, RowRegs<P>& r) {
                 LSTED_ROW_IDS
                 (void)r;
                 if (!live) return;
-                int* const queue = (int*)stage;       // [0] = count, [1..] = pixel offsets
+                int* const cnt = (int*)stage;
+                int* const queue = cnt + NOISE_ROUNDS + 1;
+                const T* const lam_s = (const T*)s0;
                 const int nr = two ? 2 : 1;
                 LSTED_NOUNROLL
                 for (int mq = 0; mq < I::MC * I::RC; ++mq) {
@@ -883,7 +900,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                     LSTED_UNROLL
                     for (int rr = 0; rr < 2; ++rr) {
                         o[rr] = (size_t)(y + (rr < nr ? rr : 0)) * Nx + i;
-                        lam[rr] = (double)out[o[rr]];
+                        lam[rr] = (double)lam_s[(rr < nr ? rr : 0) * P::L + i];
                         ok[rr] = poisson_fast_ptrs(lam[rr] >= 10.0 ? lam[rr] : 10.0, a.seed, o[rr],
                                                    a.img0 + img, k[rr]);
                     }
@@ -895,21 +912,49 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                         } else if (ok[rr]) {
                             out2[o[rr]] = (T)(k[rr] + 1e-9);
                         } else {
-                            queue[1 + smem_counter_next(queue)] = rr * Nx + i;
+                            queue[smem_counter_next(cnt)] = rr * Nx + i;
                         }
                     }
                 }
             });
+            LSTED_NOUNROLL
+            for (int round = 0; round < NOISE_ROUNDS; ++round) {
+                cx.phase(regs, [&](int tid, RowRegs<P>& r) {
+                    LSTED_ROW_IDS
+                    (void)r;
+                    if (pair >= Py) return;
+                    int* const cnt = (int*)stage;
+                    const int* const qin = (round & 1) ? (const int*)s1 : cnt + NOISE_ROUNDS + 1;
+                    int* const qout = (round & 1) ? cnt + NOISE_ROUNDS + 1 : (int*)s1;
+                    const T* const lam_s = (const T*)s0;
+                    const int n = cnt[round];
+                    LSTED_NOUNROLL
+                    for (int e = t; e < n; e += P::NTG) {
+                        const int off = qin[e];                        // rr * Nx + i
+                        const size_t o = (size_t)y * Nx + off;
+                        const double lam = (double)lam_s[off < Nx ? off : P::L + off - Nx];
+                        double k;
+                        if (ptrs_attempt<true>(lam, a.seed, o, a.img0 + img, (uint32_t)round, k))
+                            out2[o] = (T)(k + 1e-9);
+                        else
+                            qout[smem_counter_next(cnt + round + 1)] = off;
+                    }
+                });
+            }
             cx.phase_nosync(regs, [&](int tid, RowRegs<P>& r) {
                 LSTED_ROW_IDS
                 (void)r;
                 if (pair >= Py) return;
-                const int* const queue = (const int*)stage;
-                const int n = queue[0];
+                const int* const cnt = (const int*)stage;
+                const int* const qin = (NOISE_ROUNDS & 1) ? (const int*)s1 : cnt + NOISE_ROUNDS + 1;
+                const T* const lam_s = (const T*)s0;
+                const int n = cnt[NOISE_ROUNDS];
                 LSTED_NOUNROLL
                 for (int e = t; e < n; e += P::NTG) {
-                    const size_t o = (size_t)y * Nx + queue[1 + e];
-                    out2[o] = (T)(poisson_sample((double)out[o], a.seed, o, a.img0 + img) + 1e-9);
+                    const int off = qin[e];
+                    const size_t o = (size_t)y * Nx + off;
+                    const double lam = (double)lam_s[off < Nx ? off : P::L + off - Nx];
+                    out2[o] = (T)(poisson_sample(lam, a.seed, o, a.img0 + img, (uint32_t)NOISE_ROUNDS) + 1e-9);
                 }
             });
         }

@@ -48,9 +48,51 @@ LSTED_HD double u01(uint32_t hi, uint32_t lo) {
     return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// One attempt `att` of Hoermann's PTRS for lam >= 10: true + the variate when it is accepted.
+// FULL = false stops after the squeeze `us >= 0.07 && V <= vr` (~76 % of the attempts at
+// large lam: no logarithm); FULL = true goes on to the exact test
+//     log(V * invalpha / (a / us^2 + b)) <= -lam + k log(lam) - lgamma(k + 1).
+// Both tests are evaluated in forms that cost less than the textbook ones and decide the same
+// inequality: the squeeze multiplied through by (b - 2) > 0 (no division for vr), and, for
+// k + 1 >= 16, Stirling's series for lgamma with its 0.5 log(k + 1) moved into the left-hand
+// logarithm and k log(lam) - k log(k + 1) taken as k log(lam / (k + 1)) -- two logarithms,
+// one quotient, a reciprocal and a square root instead of four logarithms, three quotients
+// and a library lgamma (series through x^-9: below 2e-16 at x = 16).
+template <bool FULL>
+LSTED_HD bool ptrs_attempt(double lam, unsigned long long seed, unsigned long long pixel,
+                           uint32_t image, uint32_t att, double& out) {
+    const double slam = sqrt(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double aa = -0.059 + 0.02483 * b;
+    const Philox4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(pixel >> 32), image, att,
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double U = u01(r.v[0], r.v[1]) - 0.5;
+    const double V = u01(r.v[2], r.v[3]);
+    const double us = 0.5 - fabs(U);
+    const double k = floor((2.0 * aa / us + b) * U + lam + 0.43);
+    out = k;
+    if (us >= 0.07 && V * (b - 2.0) <= 0.9277 * (b - 2.0) - 3.6224) return true;
+    if (!FULL) return false;
+    if (k < 0.0 || (us < 0.013 && V > us)) return false;
+    // V * invalpha / (a / us^2 + b) with invalpha = 1.1239 + 1.1328 / (b - 3.4), as ONE quotient
+    const double us2 = us * us;
+    const double num = V * (1.1239 * (b - 3.4) + 1.1328) * us2;
+    const double den = (b - 3.4) * (aa + b * us2);
+    const double x = k + 1.0;
+    if (x >= 16.0) {
+        const double xi = 1.0 / x, xi2 = xi * xi;
+        const double series = xi * (8.3333333333333329e-02 + xi2 * (-2.7777777777777779e-03 + xi2 *
+                              (7.9365079365079365e-04 + xi2 * (-5.9523809523809529e-04 + xi2 *
+                              8.4175084175084182e-04))));
+        return log(num * sqrt(x) / den) <=
+               (x - lam) + k * log(lam * xi) - 0.91893853320467278 - series;
+    }
+    return log(num / den) <= -lam + k * log(lam) - lgamma(x);
+}
+
 // One Poisson(lam) variate.  Counter = (pixel lo, pixel hi, image, attempt).
 LSTED_HD double poisson_sample(double lam, unsigned long long seed, unsigned long long pixel,
-                               uint32_t image) {
+                               uint32_t image, uint32_t first_attempt = 0u) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t c0 = (uint32_t)pixel, c1 = (uint32_t)(pixel >> 32);
     if (!(lam > 0.0)) return 0.0;  // lam == 0 (or NaN/negative): no events
@@ -67,46 +109,22 @@ LSTED_HD double poisson_sample(double lam, unsigned long long seed, unsigned lon
             x += 1.0;
         }
     }
-    // PTRS.  The squeeze `us >= 0.07 && V <= vr` accepts ~90 % of the attempts, so
-    // the logarithms (and invalpha) are evaluated only on the slow path.
-    const double slam = sqrt(lam);
-    const double b = 0.931 + 2.53 * slam;
-    const double aa = -0.059 + 0.02483 * b;
-    const double vr = 0.9277 - 3.6224 / (b - 2.0);
-    for (uint32_t att = 0;; ++att) {
-        const Philox4 r = philox4x32_10(c0, c1, image, att, k0, k1);
-        const double U = u01(r.v[0], r.v[1]) - 0.5;
-        const double V = u01(r.v[2], r.v[3]);
-        const double us = 0.5 - fabs(U);
-        const double k = floor((2.0 * aa / us + b) * U + lam + 0.43);
-        if (us >= 0.07 && V <= vr) return k;
-        if (k < 0.0 || (us < 0.013 && V > us)) continue;
-        const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
-        if (log(V) + log(invalpha) - log(aa / (us * us) + b) <=
-            -lam + k * log(lam) - lgamma(k + 1.0))
-            return k;
+    // PTRS: attempts first_attempt, first_attempt + 1, ... until one is accepted (the fast
+    // path's dense rounds have already spent the earlier ones)
+    for (uint32_t att = first_attempt;; ++att) {
+        double k;
+        if (ptrs_attempt<true>(lam, seed, pixel, image, att, k)) return k;
     }
 }
 
-// First PTRS attempt only (lam >= 10): true + the variate when the squeeze accepts it
-// (~90 % of the pixels), false when the pixel needs the full sampler.  Splitting the
-// two keeps the logarithm / lgamma path out of the common instruction stream: a warp
-// would otherwise run it whenever any of its 32 lanes misses the squeeze (97 % of the
-// time).  `poisson_sample` on a rejected pixel replays the same counters, so the field
-// is identical to calling `poisson_sample` everywhere.
+// First PTRS attempt only (lam >= 10): true + the variate when the squeeze accepts it,
+// false when the pixel needs the exact test.  Splitting the two keeps the logarithms out
+// of the common instruction stream: a warp would otherwise run them whenever any of its
+// 32 lanes misses the squeeze (practically always).  The exact test replays the same
+// counters, so the field is identical to calling `poisson_sample` everywhere.
 LSTED_HD bool poisson_fast_ptrs(double lam, unsigned long long seed, unsigned long long pixel,
                                 uint32_t image, double& out) {
-    const double slam = sqrt(lam);
-    const double b = 0.931 + 2.53 * slam;
-    const double aa = -0.059 + 0.02483 * b;
-    const double vr = 0.9277 - 3.6224 / (b - 2.0);
-    const Philox4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(pixel >> 32), image, 0u,
-                                    (uint32_t)seed, (uint32_t)(seed >> 32));
-    const double U = u01(r.v[0], r.v[1]) - 0.5;
-    const double V = u01(r.v[2], r.v[3]);
-    const double us = 0.5 - fabs(U);
-    out = floor((2.0 * aa / us + b) * U + lam + 0.43);
-    return us >= 0.07 && V <= vr;
+    return ptrs_attempt<false>(lam, seed, pixel, image, 0u, out);
 }
 
 }  // namespace lsted
