@@ -252,6 +252,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
 
 #define LSTED_COL_IDS                                          \
     const int t = tid / CC, cl = tid - t * CC, c = sub * CC + cl;  \
+    LSTED_ASSUME(tid >= 0 && t < P::NT);                       \
     cplx<T>* const s0 = buf0 + cl * LSM;                       \
     cplx<T>* const s1 = buf1 + cl * LSM;                       \
     (void)cl;
@@ -575,6 +576,7 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
 // Compile-time image geometry of the row kernels: with Nx and the crop offset known, the
 // per-pixel bounds tests `0 <= i < Nx` fold away for all but the first and last butterfly leg
 // (and the row strides become constants).  RowGeomRuntime keeps everything in registers.
+// A fixed geometry also promises an even number of rows: every pair is whole (`two`).
 struct RowGeomRuntime { enum { NX = 0, SX = 0 }; };
 template <int NX_, int SX_> struct RowGeomFixed { enum { NX = NX_, SX = SX_ }; };
 
@@ -626,7 +628,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
     const int pair = pair0 + f;                            \
     const bool live = pair < Py && t < P::NT;              \
     const int y = 2 * pair;                                \
-    const bool two = y + 1 < Ny;                           \
+    const bool two = G::NX ? true : y + 1 < Ny;  /* fixed geometry: Ny even (checked at launch) */ \
     cplx<T>* const s0 = smem + (size_t)(NBUF * f) * P::LSM_ROW;      \
     cplx<T>* const s1 = smem + (size_t)(NBUF * f + 1) * P::LSM_ROW;  \
     T* const stage = (T*)(smem + (size_t)(NBUF * f + 2) * P::LSM_ROW); \
@@ -665,6 +667,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         cx.phase(regs, [&](int tid, RowRegs<P>& r) {
             LSTED_ROW_IDS
             if (!live) return;
+            LSTED_ASSUME(t >= 0 && t < P::NT);
             F::load_tw(r.twf, t, tw);
             LSTED_UNROLL
             for (int m = 0; m < F::MA; ++m) {
@@ -754,6 +757,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 }
             }
             if (!live) return;
+            LSTED_ASSUME(t >= 0 && t < P::NT);
             I::load_tw(r.twi, t, tw);
             if (MODE == ROW_MID || MODE == ROW_FINAL) {
                 F::load_tw(r.twf, t, tw);
@@ -777,7 +781,10 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 cplx<T> A, B;
                 load_pair(p, A, B);   // one 16-byte (fp32) access; the slot of a missing last row is never used
                 if (!two) B = mk<T>(0, 0);
-                if ((q == 0 && t == 0) || 2 * i == Lx) { A.y = 0; B.y = 0; }
+                // bin 0 and the Nyquist bin L/2 = t + q*NC (one q, one t: a compile-time q, so
+                // the other RA - 2 iterations carry no test) hold the spectra of real rows
+                if ((q == 0 && t == 0) ||
+                    (P::L % 2 == 0 && q == (P::L / 2) / P::NC && t == (P::L / 2) % P::NC)) { A.y = 0; B.y = 0; }
                 r.v[q] = upper ? mk<T>(A.x + B.y, B.x - A.y) : mk<T>(A.x - B.y, A.y + B.x);
             }
             I::pass_a(r.v, t, s0);
@@ -811,6 +818,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                     for (int rr = 0; rr < nrow; ++rr) bulk_copy((T*)s0 + rr * P::L, m0 + (size_t)rr * Nx, row_bytes, mb);
                 }
                 if (!live) return;
+                LSTED_ASSUME(t >= 0 && t < P::NT);
                 I::pass_c(r.v, t, s1, r.twi);
             });
         }
@@ -818,6 +826,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
             LSTED_ROW_IDS
             if (MODE == ROW_INV_SIM && t < NOISE_ROUNDS + 1) ((int*)stage)[t] = 0;   // noise queue counters (below)
             if (!live) return;
+            LSTED_ASSUME(t >= 0 && t < P::NT);
             if (!LEAN) I::pass_c(r.v, t, s1, r.twi);
             const T* const rows_s = LEAN ? (const T*)s0 : stage;   // staged measurement / normalisation rows
             (void)rows_s;
@@ -882,6 +891,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
                 LSTED_ROW_IDS
                 (void)r;
                 if (!live) return;
+                LSTED_ASSUME(t >= 0 && t < P::NT);
                 int* const cnt = (int*)stage;
                 int* const queue = cnt + NOISE_ROUNDS + 1;
                 const T* const lam_s = (const T*)s0;
@@ -966,6 +976,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         LSTED_ROW_IDS
         LSTED_ROW_FWD_BUFS
         if (!live) return;
+        LSTED_ASSUME(t >= 0 && t < P::NT);
         F::load_b(r.v, t, fa, r.twf);
         F::pass_b(r.v, t, fb);
     });
@@ -974,6 +985,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         LSTED_ROW_IDS
         LSTED_ROW_FWD_BUFS
         if (!live) return;
+        LSTED_ASSUME(t >= 0 && t < P::NT);
         F::pass_c(r.v, t, fb, r.twf);
         LSTED_UNROLL
         for (int q = P::QH; q < P::RCF; ++q) fa[(q - P::QH) * P::PX + t] = r.v[q];
@@ -985,6 +997,7 @@ LSTED_HD void row_fast_body(Ctx& cx, int block, const RowArgs<typename P::T>& a,
         LSTED_ROW_IDS
         LSTED_ROW_FWD_BUFS
         if (!live) return;
+        LSTED_ASSUME(t >= 0 && t < P::NT);
         const int tp = t == 0 ? 0 : P::NC - t;         // mirror thread
         const int qoff = t == 0 ? 1 : 0;               // thread 0 mirrors onto itself, one q up
         // TMA: the pair's chunks are assembled in s1 (bin k at s1[2k], s1[2k+1]) and leave in bulk

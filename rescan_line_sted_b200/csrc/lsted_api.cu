@@ -64,6 +64,9 @@ struct DeviceCtx {
 #ifndef LSTED_ROW_LEAN_CTAS
 #define LSTED_ROW_LEAN_CTAS 6   // "lean" ROW_MID (two shared-memory buffers, 35 KB): CTAs per SM -> 64 registers, no spills
 #endif
+#ifndef LSTED_ROW_SIM_CTAS
+#define LSTED_ROW_SIM_CTAS 4   // ROW_INV_SIM (fp64 Poisson arithmetic in an fp32 kernel): CTAs per SM
+#endif
 #ifndef LSTED_ROW_RESIDENT_THREADS
 #define LSTED_ROW_RESIDENT_THREADS 480  // 3 row CTAs per SM: no register spills
 #endif
@@ -89,7 +92,7 @@ typedef lsted::FastPlan<double, 16, 9, 15, 144, 2, LSTED_FP64_PR, LSTED_FP64_CS>
 typedef lsted::RowGeomFixed<2048, 53> RowGeom2048;
 typedef lsted::RowGeomFixed<2048, 0> RowGeom2048c;    // centred real OTFs: no crop offset
 template <int MODE, class P, class G = lsted::RowGeomRuntime, int TMA = 0>
-__global__ void __launch_bounds__(P::ROW_THREADS, TMA == 2 ? (MODE == lsted::ROW_MID ? LSTED_ROW_LEAN_CTAS : 4) : sizeof(typename P::T) == 4 ? (LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
+__global__ void __launch_bounds__(P::ROW_THREADS, TMA == 2 ? (MODE == lsted::ROW_MID ? LSTED_ROW_LEAN_CTAS : 4) : sizeof(typename P::T) == 4 ? (MODE == lsted::ROW_INV_SIM ? LSTED_ROW_SIM_CTAS : LSTED_ROW_RESIDENT_THREADS / P::ROW_THREADS) : 1)
 row_fast_kernel(const __grid_constant__ lsted::RowArgs<typename P::T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DeviceCtx cx;
@@ -810,9 +813,9 @@ class CudaBackend {
         const size_t smem = lsted::fast_row_smem_bytes<P>(MODE);
         // fp32 kernels that index pixels have an instance with the headline geometry folded in
         const bool fixed = sizeof(typename P::T) == 4 && MODE != lsted::ROW_FWD &&
-                           a.g.Nx == (int)RowGeom2048::NX && a.g.sx == (int)RowGeom2048::SX;
+                           a.g.Nx == (int)RowGeom2048::NX && a.g.sx == (int)RowGeom2048::SX && a.g.Ny % 2 == 0;
         const bool fixed_c = sizeof(typename P::T) == 4 && MODE != lsted::ROW_FWD &&
-                             a.g.Nx == (int)RowGeom2048c::NX && a.g.sx == 0;   // centred OTFs
+                             a.g.Nx == (int)RowGeom2048c::NX && a.g.sx == 0 && a.g.Ny % 2 == 0;   // centred OTFs
         ensure_smem(row_fast_kernel<MODE, P>, smem);
         if (sizeof(typename P::T) == 4) {
             ensure_smem(row_fast_kernel<MODE, P, RowGeom2048>, smem);

@@ -187,7 +187,7 @@ class HostBackend {
                 HostCtx cx;
                 cx.nthreads = P::ROW_THREADS;
                 // same dispatch as the CUDA backend: compile-time geometry for 2048-wide rows
-                const bool fixed = sizeof(T) == 4 && MODE != lsted::ROW_FWD && a.g.Nx == 2048 && a.g.sx == 53;
+                const bool fixed = sizeof(T) == 4 && MODE != lsted::ROW_FWD && a.g.Nx == 2048 && a.g.sx == 53 && a.g.Ny % 2 == 0;
 #pragma omp for schedule(dynamic)
                 for (int b = 0; b < grid; ++b) {
                     if (run_row_tma<MODE, P>(cx, b, a, smem.data(), regs.data())) continue;
@@ -241,7 +241,7 @@ class HostBackend {
             std::vector<lsted::Row2Regs<P> > regs(P::ROW_THREADS);
             HostCtx cx;
             cx.nthreads = P::ROW_THREADS;
-            const bool fixed = MODE != lsted::ROW_FWD && a.g.Nx == 2048 && a.g.sx == 53;
+            const bool fixed = MODE != lsted::ROW_FWD && a.g.Nx == 2048 && a.g.sx == 53 && a.g.Ny % 2 == 0;
 #pragma omp for schedule(dynamic)
             for (int b = 0; b < grid; ++b) {
                 if (fixed)
