@@ -10,7 +10,10 @@ raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-so
 rows = list(csv.reader(raw.splitlines()))
 print(rows[0][1][:120])
 hdr = rows[1]; idx = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[2:] if len(r) == len(hdr) and r[0] != 'Address']
+data, seen = [], set()
+for r in rows[2:]:      # (ncu prints the listing twice when the report holds source + SASS)
+    if len(r) == len(hdr) and r[0] != 'Address' and r[0] not in seen:
+        seen.add(r[0]); data.append(r)
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 tot = collections.Counter()
 for r in data:
