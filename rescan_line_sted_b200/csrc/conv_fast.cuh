@@ -40,7 +40,8 @@ template <typename T_, int RA, int RB, int RC, int NT_, int C_, int PR_, int CS_
         COL_THREADS = NT_ * C_,
         COL_SMEM_ELEMS = 2 * C_ * LSM_COL,          // two ping-pong buffers
         COL_OTF_ELEMS = C_ * RA * RB * RC,          // + one staged OTF slab [L][C] (bulk copy)
-        COL_TW = 256,                               // + base twiddles
+        COL_TW = 256,                               // + base twiddles ...
+        COL_TW_PAD = 256 + 32,                      // ... + the pass-B ones gathered (ColTwTable, fft_static.cuh)
         CS = CS_, NSUB = C_ / CS_,
         LSM_SUB = (SEQ + 15) / 16 * 16 + 16 / CS_,
         SUB_THREADS = NT_ * CS_,
@@ -93,14 +94,14 @@ template <class P> struct RowRegs {
 // per CTA the L1 is too small to keep the global table resident (the LDGs at the head of
 // each pass went to L2)
 template <class P> LSTED_HD size_t fast_col_smem_bytes() {
-    return sizeof(cplx<typename P::T>) * (size_t)(P::COL_SMEM_ELEMS + P::COL_TW +
+    return sizeof(cplx<typename P::T>) * (size_t)(P::COL_SMEM_ELEMS + P::COL_TW_PAD +
                                                   (LSTED_COL_STAGE_OTF ? P::COL_OTF_ELEMS : 0)) +
            (LSTED_COL_STAGE_OTF ? 16 : 0);
 }
 // column CTA on a sub-block of CS columns with real OTFs: exchange buffers + twiddles + one
 // real OTF slab [L][CS] + its mbarrier
 template <class P> LSTED_HD size_t fast_col_sub_smem_bytes() {
-    return sizeof(cplx<typename P::T>) * (size_t)(P::SUB_SMEM_ELEMS + P::COL_TW) +
+    return sizeof(cplx<typename P::T>) * (size_t)(P::SUB_SMEM_ELEMS + P::COL_TW_PAD) +
            sizeof(typename P::T) * (size_t)P::CS * P::L + 16;
 }
 template <class P> LSTED_HD size_t fast_row_smem_bytes(int mode, bool lean = false) {
@@ -242,7 +243,9 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     const size_t slab_ly = (size_t)P::C * Ly, img_ly = (size_t)g.nxb * slab_ly;
     const size_t slab_ny = (size_t)P::C * even_rows(Ny), img_ny = (size_t)g.nxb * slab_ny;   // XB2
     cplx<T>* const tw_s = smem + (size_t)XELEMS;   // base twiddles (filled below)
-    const cplx<T>* tw = tw_s;
+    typedef ColTwTable<cplx<T>, P::COL_TW, F::RC, I::RC> TwTable;
+    static_assert(F::RA <= 16 && I::RA <= 16 && (int)TwTable::ELEMS == (int)P::COL_TW_PAD, "gathered pass-B twiddles: 16 slots per transform");
+    const TwTable tw = {tw_s};
     cplx<T>* const buf0 = smem;
     cplx<T>* const buf1 = smem + (size_t)CC * LSM;
     const int K = a.K;
@@ -261,7 +264,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
     // orientation k+1 is requested as soon as every thread is done with slab k and
     // lands while the transform of k runs (no registers, no per-thread copy work).
     const bool stage = LSTED_COL_STAGE_OTF != 0;
-    cplx<T>* const otf_s = tw_s + P::COL_TW;
+    cplx<T>* const otf_s = tw_s + P::COL_TW_PAD;
     mbar_t* const mbar = SUB ? (mbar_t*)((T*)otf_s + (size_t)P::CS * Ly)
                              : (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
     // one OTF slab: complex, or real when RO (`otf0` then counts T elements; a sub-block's
@@ -274,7 +277,7 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
 #define LSTED_OTF_AT(base) (SUB ? (const T*)(base) + cl : real_otf_at<P>((const T*)(base), c))
     cx.phase(regs, [&](int tid, ColRegs<P>& r) {
         // (hoisting base twiddles into registers costs spills at 96 registers / 576 threads)
-        for (int i = tid; i < (int)P::COL_TW; i += NTHR) tw_s[i] = a.tw[i];
+        for (int i = tid; i < (int)TwTable::ELEMS; i += NTHR) tw_s[i] = a.tw[TwTable::source_index(i)];
         if (MODE == COL_HT) {
             LSTED_UNROLL
             for (int i = 0; i < P::NKEEP; ++i) r.keep[i] = mk<T>(0, 0);
@@ -434,7 +437,7 @@ LSTED_HD void col_ht_p2p_body(Ctx& cx, int cta, int ncta, const ColArgs<typename
     const cplx<T>* tw = tw_s;
     cplx<T>* const buf0 = smem;
     cplx<T>* const buf1 = smem + (size_t)P::C * P::LSM_COL;
-    cplx<T>* const otf_s = tw_s + P::COL_TW;
+    cplx<T>* const otf_s = tw_s + P::COL_TW_PAD;
     mbar_t* const mbar = (mbar_t*)(otf_s + (size_t)P::COL_OTF_ELEMS);
     typedef typename std::conditional<RO, T, cplx<T> >::type OtfT;   // real OTFs: see col_fast_body
     const unsigned slab_bytes = (unsigned)(slab_ly * sizeof(OtfT));

@@ -32,6 +32,28 @@ constexpr int pitch_congruent(int n, int r) {
     return p;
 }
 
+// The base twiddles of pass B are tw[RC * k], k = j % RA.  In a dense table in shared memory
+// the RC = 16 ones sit 128 bytes apart -- all in one bank group: a 15-way conflict, 16
+// wavefronts per load (ncu: 14 % of all shared-memory wavefronts of col_h).  ColTwTable keeps
+// them a second time, gathered: b<RC>(k) at p[N + 16 * (RC == RC1) + k], consecutive k in
+// consecutive banks; tw[j] (16 consecutive j per warp) stays in the dense part p[0 .. N).
+template <class W, int N_, int RC0_, int RC1_> struct ColTwTable {
+    enum { N = N_, RC0 = RC0_, RC1 = RC1_, ELEMS = N_ + 32 };
+    const W* p;
+    LSTED_HD const W& operator[](int i) const { return p[i]; }
+    template <int RC> LSTED_HD const W& b(int k) const {
+        static_assert(RC == RC0_ || RC == RC1_, "no gathered table for this stride");
+        return p[N_ + (RC == RC0_ ? 0 : 16) + k];
+    }
+    // fill from the global table (entry i of ELEMS)
+    static LSTED_HD int source_index(int i) {
+        return i < N_ ? i : i < N_ + 16 ? RC0_ * (i - N_) : RC1_ * (i - N_ - 16);
+    }
+};
+template <int RC, class W> LSTED_HD W tw_base_b(const W* tw, int k) { return tw[RC * k]; }
+template <int RC, class W, int N, int RC0, int RC1>
+LSTED_HD W tw_base_b(const ColTwTable<W, N, RC0, RC1>& tw, int k) { return tw.template b<RC>(k); }
+
 template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
     typedef typename ScalarOf<V>::type T;
     typedef cplx<T> W;   // twiddles are always single complex numbers
@@ -74,11 +96,12 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
     // Base twiddles of one thread (they depend on t only): loaded once per kernel, not
     // once per transform -- no global load sits at the head of a pass any more.
     struct Tw { W b[(NT_ % RA_ == 0) ? 1 : MB]; W c[MC]; };
-    static LSTED_HD void load_tw(Tw& w, int t, const W* tw) {
+    // TWP: the twiddle table -- a pointer, or a ColTwTable (above)
+    template <class TWP> static LSTED_HD void load_tw(Tw& w, int t, TWP tw) {
         LSTED_UNROLL
         for (int m = 0; m < ((NT % RA == 0) ? 1 : (int)MB); ++m) {
             const int j = t + m * NT;
-            w.b[m] = tw[(j < NB) ? RC * (j % RA) : 0];
+            w.b[m] = tw_base_b<RC>(tw, (j < NB) ? j % RA : 0);
         }
         LSTED_UNROLL
         for (int m = 0; m < MC; ++m) {
@@ -106,7 +129,7 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
             }
         }
     }
-    static LSTED_HD void load_b(V* v, int t, const V* sm, const W* tw) {
+    template <class TWP> static LSTED_HD void load_b(V* v, int t, const V* sm, TWP tw) {
         Tw bw;
         load_tw(bw, t, tw);
         load_b(v, t, sm, bw);
@@ -142,7 +165,7 @@ template <class V, int DIR, int RA_, int RB_, int RC_, int NT_> struct Fft3E {
             }
         }
     }
-    static LSTED_HD void pass_c(V* v, int t, const V* sm, const W* tw) {
+    template <class TWP> static LSTED_HD void pass_c(V* v, int t, const V* sm, TWP tw) {
         Tw bw;
         load_tw(bw, t, tw);
         pass_c(v, t, sm, bw);
