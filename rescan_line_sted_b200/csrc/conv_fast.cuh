@@ -86,6 +86,9 @@ template <class P> struct RowRegs {
 #ifndef LSTED_ROW_BULK_STAGE
 #define LSTED_ROW_BULK_STAGE 1   // measurement / normalisation / estimate rows by cp.async.bulk
 #endif
+#ifndef LSTED_COL_HT_PRELOAD
+#define LSTED_COL_HT_PRELOAD 1   // COL_HT: next orientation's pass-A operands requested before the barrier
+#endif
 #ifndef LSTED_COL_STAGE_OTF
 #define LSTED_COL_STAGE_OTF 1   // OTF slabs travel global -> shared by cp.async.bulk, one k ahead
 #endif
@@ -337,8 +340,18 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
         }
         return;
     }
-    // COL_HT: per k [accumulate product k-1 | load k, forward pass A] then pass B
+    // COL_HT: per k [forward pass A of k | accumulate product k-1] then [pass B | operands of k+1].
+    // The pass-A operands of orientation k+1 are requested from global memory at the END of the
+    // pass-B phase of k, into the registers pass B has just emptied, and are consumed right
+    // after the barrier: their latency hides behind the barrier wait instead of sitting between
+    // the product and pass A (ncu: long_sb 16 % of col_ht's stall samples before).
     const cplx<T>* src0 = a.src + (size_t)xb * slab_ny;
+    const bool preload = LSTED_COL_HT_PRELOAD != 0;
+    if (preload && K > 0)
+        cx.phase_nosync(regs, [&](int tid, ColRegs<P>& r) {
+            LSTED_COL_IDS
+            col_load_fwd_a<P>(r.v, t, c, src0, Ny);
+        });
     for (int k = 0; k <= K; ++k) {
         cx.phase(regs, [&](int tid, ColRegs<P>& r) {
             LSTED_COL_IDS
@@ -352,6 +365,8 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
             } else if (k < K) {   // product k happens at the start of the next phase
                 prefetch_l2_range(otf0 + (size_t)k * img_ly, slab_bytes, tid, NTHR);
             }
+            // (pass A writes the first exchange buffer, pass C below reads the second one)
+            if (preload && k < K) F::pass_a(r.v, t, s0);
             if (k > 0) {
                 F::pass_c(r.v, t, s1, tw);
                 if (stage) {
@@ -364,8 +379,10 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                 }
             }
             if (k < K) {
-                col_load_fwd_a<P>(r.v, t, c, src0 + (a.src_same ? 0 : (size_t)k * img_ny), Ny);
-                F::pass_a(r.v, t, s0);
+                if (!preload) {
+                    col_load_fwd_a<P>(r.v, t, c, src0 + (a.src_same ? 0 : (size_t)k * img_ny), Ny);
+                    F::pass_a(r.v, t, s0);
+                }
             } else {
                 LSTED_UNROLL
                 for (int i = 0; i < P::NKEEP; ++i) r.v[i] = r.keep[i];
@@ -379,6 +396,8 @@ LSTED_HD void col_fast_body(Ctx& cx, int block, const ColArgs<typename P::T>& a,
                 bulk_load(otf_s, otf0 + (size_t)k * img_ly, slab_bytes, mbar);
             F::load_b(r.v, t, s0, tw);
             F::pass_b(r.v, t, s1);
+            if (preload && k + 1 < K)
+                col_load_fwd_a<P>(r.v, t, c, src0 + (a.src_same ? 0 : (size_t)(k + 1) * img_ny), Ny);
         });
     }
     cplx<T>* dst = a.dst + (size_t)xb * slab_ny;
