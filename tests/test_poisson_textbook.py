@@ -78,3 +78,44 @@ def test_sampler_is_textbook_ptrs_on_the_same_counters(lam):
     # the two spellings of the tests can only disagree when a uniform falls within rounding of
     # a decision boundary (~1e-13 per sample)
     assert np.array_equal(got, want)
+
+
+def textbook_multiplication(lam, seed, pixels):
+    """Knuth's multiplication method (numpy's legacy `random_poisson_mult`): count uniforms
+    until their product drops to exp(-lam); each Philox call supplies two of them."""
+    enlam = np.exp(-lam)
+    out = np.zeros(pixels.size)
+    prod = np.ones(pixels.size)
+    running = np.ones(pixels.size, dtype=bool)
+    for att in range(200):
+        idx = np.flatnonzero(running)
+        if idx.size == 0:
+            break
+        p = pixels[idx].astype(np.uint64)
+        zero = np.zeros_like(p)
+        v = philox4x32_10(p & M32, p >> np.uint64(32), zero, zero + np.uint64(att),
+                          seed & 0xFFFFFFFF, seed >> 32)
+        ua, ub = u01(v[0], v[1]), u01(v[2], v[3])
+        prod[idx] *= ua
+        done = ~(prod[idx] > enlam)
+        running[idx[done]] = False
+        idx, ub = idx[~done], ub[~done]     # the second uniform: pixels still running only
+        out[idx] += 1.0
+        prod[idx] *= ub
+        done = ~(prod[idx] > enlam)
+        running[idx[done]] = False
+        out[idx[~done]] += 1.0
+    assert not running.any()
+    return out
+
+
+@pytest.mark.parametrize('lam', [0.5, 5.0, 9.9])
+def test_small_lambda_sampler_is_the_multiplication_method(lam):
+    lib = emul_support.emulator_library()
+    lib.cdll.emul_poisson.argtypes = [ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64,
+                                      ctypes.c_int, dp]
+    n, seed, first = 50000, 987654321, 12345
+    got = np.empty(n)
+    lib.cdll.emul_poisson(lam, seed, first, n, got.ctypes.data_as(dp))
+    want = textbook_multiplication(lam, seed, first + np.arange(n, dtype=np.int64))
+    assert np.array_equal(got, want)
